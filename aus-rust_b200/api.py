@@ -1,0 +1,248 @@
+"""Context object over the C ABI: numpy (host-pointer) entry points and torch (device-pointer) entry points.
+
+torch is used only for device memory and streams (plumbing); all arithmetic happens in csrc/libaus_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_int, c_uint64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import NUM_FEATURES
+
+F64, F32 = 0, 1
+
+
+def _prec(precision) -> int:
+    if precision in (0, "f64", "float64", np.float64):
+        return F64
+    if precision in (1, "f32", "float32", np.float32):
+        return F32
+    raise ValueError(f"unknown precision {precision!r}")
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pd(a: np.ndarray):
+    return a.ctypes.data_as(_lib._p_d)
+
+
+def _pu64(a: np.ndarray):
+    return a.ctypes.data_as(_lib._p_u64)
+
+
+def num_frames(n_samples: int, fft_size: int, hop: int) -> int:
+    """Frame count of the loop in spectrum/fft.rs:126-176."""
+    return int(_lib.load_library().aus_num_frames(int(n_samples), int(fft_size), int(hop)))
+
+
+def irstft_len(n_frames: int, fft_size: int, hop: int) -> int:
+    """spectrum/fft.rs:208."""
+    return int(_lib.load_library().aus_irstft_len(int(n_frames), int(fft_size), int(hop)))
+
+
+def batch_num_frames(lengths, fft_size: int, hop: int) -> int:
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    return int(_lib.load_library().aus_batch_num_frames(_pu64(ln), ln.size, int(fft_size), int(hop)))
+
+
+class Context:
+    """One per device and caller thread (opaque ``aus_ctx``): stream, twiddle/window tables, scratch."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load_library()
+        h = c_void_p()
+        _lib.check(self._lib.aus_ctx_create(int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.aus_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing
+    def synchronize(self):
+        _lib.check(self._lib.aus_ctx_synchronize(self._h))
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _lib.check(self._lib.aus_ctx_set_stream(self._h, c_void_p(int(cuda_stream_ptr))))
+
+    def use_torch_stream(self):
+        """Launch on torch's current stream of this device, so torch.cuda.Event timing sees the kernels."""
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.aus_ctx_launch_count(self._h))
+
+    # ---- host-pointer API (numpy in, numpy out; H2D + kernels + D2H inside the call)
+    def stft_features(self, audio, fft_size: int, hop: int, window_type: int, sample_rate: int, precision="f64"):
+        """rstft -> |X| -> analyzer per frame, fused (analysis/analyzer.rs:99-104 with general hop/window)."""
+        a = _f64(audio)
+        out = np.empty((num_frames(a.size, fft_size, hop), NUM_FEATURES), dtype=np.float64)
+        _lib.check(self._lib.aus_stft_features(self._h, _pd(a), a.size, int(fft_size), int(hop), int(window_type),
+                                               int(sample_rate), _prec(precision), _pd(out)))
+        return out
+
+    def stft_analysis(self, audio, fft_size: int, sample_rate: int, max_num_threads=None):
+        """mp.rs:26 ``stft_analysis``: hop = fft_size/2, Hamming."""
+        a = _f64(audio)
+        out = np.empty((num_frames(a.size, fft_size, max(1, fft_size // 2)), NUM_FEATURES), dtype=np.float64)
+        _lib.check(self._lib.aus_stft_analysis(self._h, _pd(a), a.size, int(fft_size), int(sample_rate),
+                                               int(max_num_threads or 0), out.ctypes.data_as(c_void_p)))
+        return out
+
+    def stft_features_batch(self, audio, offsets, lengths, fft_size: int, hop: int, window_type: int,
+                            sample_rate: int, precision="f64"):
+        a = _f64(audio)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        total = batch_num_frames(ln, fft_size, hop)
+        out = np.empty((total, NUM_FEATURES), dtype=np.float64)
+        starts = np.empty(ln.size + 1, dtype=np.uint64)
+        _lib.check(self._lib.aus_stft_features_batch(self._h, _pd(a), _pu64(off), _pu64(ln), ln.size, int(fft_size),
+                                                     int(hop), int(window_type), int(sample_rate), _prec(precision),
+                                                     _pd(out), _pu64(starts)))
+        return out, starts.astype(np.int64)
+
+    def rstft(self, audio, fft_size: int, hop: int, window_type: int, precision="f64") -> np.ndarray:
+        """spectrum/fft.rs:119 -> complex128 [F, fft_size/2+1]."""
+        a = _f64(audio)
+        out = np.empty((num_frames(a.size, fft_size, hop), fft_size // 2 + 1), dtype=np.complex128)
+        _lib.check(self._lib.aus_rstft(self._h, _pd(a), a.size, int(fft_size), int(hop), int(window_type),
+                                       _prec(precision), out.ctypes.data_as(_lib._p_d)))
+        return out
+
+    def rfft(self, audio, fft_size: int, precision="f64") -> np.ndarray:
+        """spectrum/fft.rs:37."""
+        a = _f64(audio)
+        if a.size != fft_size:
+            raise ValueError("rfft: audio must have exactly fft_size samples (zero-pad first, fft.rs:23-24)")
+        out = np.empty(fft_size // 2 + 1, dtype=np.complex128)
+        _lib.check(self._lib.aus_rfft(self._h, _pd(a), int(fft_size), _prec(precision), out.ctypes.data_as(_lib._p_d)))
+        return out
+
+    def irstft(self, spectrogram, fft_size: int, hop: int, window_type: int, precision="f64", normalize=True):
+        """spectrum/fft.rs:204."""
+        s = np.ascontiguousarray(spectrogram, dtype=np.complex128)
+        if s.ndim != 2:
+            raise ValueError("spectrogram must be [frames, bins]")
+        out = np.empty(irstft_len(s.shape[0], fft_size, hop), dtype=np.float64)
+        _lib.check(self._lib.aus_irstft(self._h, s.ctypes.data_as(_lib._p_d), s.shape[0], s.shape[1], int(fft_size),
+                                        int(hop), int(window_type), _prec(precision), 1 if normalize else 0, _pd(out)))
+        return out
+
+    def irfft(self, spectrum, fft_size: int, precision="f64") -> np.ndarray:
+        """spectrum/fft.rs:66."""
+        s = np.ascontiguousarray(spectrum, dtype=np.complex128).reshape(-1)
+        out = np.empty(int(fft_size), dtype=np.float64)
+        _lib.check(self._lib.aus_irfft(self._h, s.ctypes.data_as(_lib._p_d), s.size, int(fft_size), _prec(precision),
+                                       _pd(out)))
+        return out
+
+    def complex_to_polar(self, spectra, want_phase=True):
+        """spectrum/fft_tools.rs:21-55."""
+        s = np.ascontiguousarray(spectra, dtype=np.complex128)
+        mag = np.empty(s.shape, dtype=np.float64)
+        ph = np.empty(s.shape, dtype=np.float64) if want_phase else None
+        _lib.check(self._lib.aus_complex_to_polar(self._h, s.ctypes.data_as(_lib._p_d), s.size, _pd(mag),
+                                                  _pd(ph) if want_phase else None))
+        return mag, ph
+
+    def polar_to_complex(self, mag, ph) -> np.ndarray:
+        """spectrum/fft_tools.rs:131-188."""
+        m, p = _f64(mag), _f64(ph)
+        out = np.empty(m.shape, dtype=np.complex128)
+        _lib.check(self._lib.aus_polar_to_complex(self._h, _pd(m), _pd(p), m.size, out.ctypes.data_as(_lib._p_d)))
+        return out
+
+    def analyzer_batch(self, magnitudes, fft_size: int, sample_rate: int, precision="f64") -> np.ndarray:
+        """analysis/analyzer.rs:41 over rows."""
+        m = _f64(magnitudes)
+        if m.ndim == 1:
+            m = m[None, :]
+        if m.shape[1] != fft_size // 2 + 1:
+            raise IndexError("magnitude rows must have fft_size/2+1 bins (the reference indexes out of bounds otherwise)")
+        out = np.empty((m.shape[0], NUM_FEATURES), dtype=np.float64)
+        _lib.check(self._lib.aus_analyzer_batch(self._h, _pd(m), m.shape[0], int(fft_size), int(sample_rate),
+                                                _prec(precision), _pd(out)))
+        return out
+
+    # ---- device-pointer API (torch CUDA tensors; stream-ordered, no sync)
+    def _check_dev(self, t, precision, name):
+        import torch
+        want = torch.float64 if _prec(precision) == F64 else torch.float32
+        if t is None:
+            return None
+        if not t.is_cuda or t.device.index != self.device or t.dtype != want or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous {want} CUDA tensor on device {self.device}")
+        return c_void_p(t.data_ptr())
+
+    def stft_features_batch_dev(self, d_audio, offsets, lengths, fft_size: int, hop: int, window_type: int,
+                                sample_rate: int, precision="f64", d_features=None, d_spectra=None):
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        _lib.check(self._lib.aus_stft_features_batch_dev(
+            self._h, self._check_dev(d_audio, precision, "d_audio"), _pu64(off), _pu64(ln), ln.size, int(fft_size),
+            int(hop), int(window_type), int(sample_rate), _prec(precision),
+            self._check_dev(d_features, precision, "d_features"), self._check_dev(d_spectra, precision, "d_spectra")))
+
+    def analyzer_batch_dev(self, d_mags, n_frames: int, fft_size: int, sample_rate: int, precision, d_features):
+        _lib.check(self._lib.aus_analyzer_batch_dev(self._h, self._check_dev(d_mags, precision, "d_mags"), int(n_frames),
+                                                    int(fft_size), int(sample_rate), _prec(precision),
+                                                    self._check_dev(d_features, precision, "d_features")))
+
+    def irstft_dev(self, d_spectra, n_frames: int, fft_size: int, hop: int, window_type: int, precision, d_audio,
+                   normalize=True):
+        _lib.check(self._lib.aus_irstft_dev(self._h, self._check_dev(d_spectra, precision, "d_spectra"), int(n_frames),
+                                            int(fft_size), int(hop), int(window_type), _prec(precision),
+                                            1 if normalize else 0, self._check_dev(d_audio, precision, "d_audio")))
+
+    def synth_dev(self, d_audio, n0: int = 0, sample_rate: int = 44100, freq: float = 440.0, seed: int = 0,
+                  file_id: int = 0, precision="f64"):
+        _lib.check(self._lib.aus_synth_dev(self._h, self._check_dev(d_audio, precision, "d_audio"), d_audio.numel(),
+                                           int(n0), int(sample_rate), float(freq), int(seed), int(file_id),
+                                           _prec(precision)))
+
+
+def stft_features_multi(devices, audio, offsets, lengths, fft_size: int, hop: int, window_type: int, sample_rate: int,
+                        precision="f64") -> np.ndarray:
+    """Shard a batch (or one long file) over several GPUs of this box; host threads, ordered gather."""
+    lib = _lib.load_library()
+    a = _f64(audio)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    devs = (c_int * len(devices))(*[int(d) for d in devices])
+    out = np.empty((batch_num_frames(ln, fft_size, hop), NUM_FEATURES), dtype=np.float64)
+    _lib.check(lib.aus_stft_features_multi(devs, len(devices), _pd(a), _pu64(off), _pu64(ln), ln.size, int(fft_size),
+                                           int(hop), int(window_type), int(sample_rate), _prec(precision), _pd(out)))
+    return out
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context() -> Context:
+    """Process-wide context used by the reference-named free functions (device = LOCAL_RANK or 0), one per thread."""
+    key = threading.get_ident()
+    with _default_lock:
+        ctx = _default.get(key)
+        if ctx is None:
+            ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+            _default[key] = ctx
+        return ctx

@@ -1,0 +1,846 @@
+// aus_b200.cu -- host side of the C ABI declared in include/aus_b200.h: per-device context, twiddle/window
+// tables, feature-parameter derivation, kernel dispatch.  There is no CPU compute path in this file: every
+// entry point either launches the sm_100a kernels or returns an error.
+#include "../../include/aus_b200.h"
+#include "aus_istft_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace aus;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err = "";
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(...)                                                                               \
+    do {                                                                                            \
+        cudaError_t e_ = (__VA_ARGS__);                                                             \
+        if (e_ != cudaSuccess) return fail(AUS_ERR_CUDA, std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define AUS_TRY(...)                   \
+    do {                               \
+        int r_ = (__VA_ARGS__);        \
+        if (r_ != AUS_OK) return r_;   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ context
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return AUS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(AUS_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return AUS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Tables {
+    void *twM = nullptr, *twN = nullptr;
+    void *win2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct aus_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    std::map<int, Tables> tables;          // key = log2n * 2 + precision
+    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc;
+};
+
+static int log2_exact(size_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while (((size_t)1 << l) < n) ++l;
+    return l;
+}
+
+static int check_fft_args(size_t N, size_t hop) {
+    const int lg = log2_exact(N);
+    if (lg < 0) return fail(AUS_ERR_UNSUPPORTED, "fft_size must be a power of two (rustfft accepts any size; this build does not)");
+    if (lg < 6 || lg > 14) return fail(AUS_ERR_UNSUPPORTED, "fft_size must be in [64, 16384]");
+    if (hop == 0) return fail(AUS_ERR_INVALID, "hop_size must be > 0 (the reference loops forever, fft.rs:126)");
+    if (hop > N) return fail(AUS_ERR_INVALID, "hop_size must be <= fft_size (the reference panics on slice bounds, fft.rs:153)");
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers (ABI)
+extern "C" const char *aus_version(void) { return "aus_b200 0.1.0 (sm_100a)"; }
+extern "C" const char *aus_last_error(void) { return g_err.c_str(); }
+
+extern "C" int aus_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail(AUS_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        return AUS_ERR_CUDA;
+    }
+    return n;
+}
+
+extern "C" size_t aus_num_frames(size_t n, size_t N, size_t hop) {          // fft.rs:126-176
+    if (hop == 0) return 0;
+    if (n <= N) return 1;
+    return (n - N + hop - 1) / hop + 1;
+}
+extern "C" size_t aus_irstft_len(size_t F, size_t N, size_t hop) { return F ? N + hop * (F - 1) : 0; }   // fft.rs:208
+
+extern "C" uint64_t aus_batch_num_frames(const uint64_t *lengths, size_t n_files, size_t N, size_t hop) {
+    uint64_t t = 0;
+    for (size_t i = 0; i < n_files; ++i) t += aus_num_frames((size_t)lengths[i], N, hop);
+    return t;
+}
+
+extern "C" int aus_generate_window(int type, size_t L, double *w) {         // window.rs:26-118
+    if (type < 0 || type > 4) return fail(AUS_ERR_INVALID, "unknown window type");
+    if (!w && L) return fail(AUS_ERR_INVALID, "null output");
+    const double PI = 3.14159265358979323846264338327950288;
+    const double Lf = (double)L;
+    for (size_t i = 0; i < L; ++i) {
+        const double x = (double)i;
+        switch (type) {
+        case 0: w[i] = (2.0 / (Lf - 1.0)) * ((Lf - 1.0) / 2.0 - std::fabs(x - (Lf - 1.0) / 2.0)); break;
+        case 1: w[i] = 0.42 - 0.5 * std::cos((2.0 * PI * x) / Lf) + 0.08 * std::cos((4.0 * PI * x) / Lf); break;
+        case 2: w[i] = 0.5 - 0.5 * std::cos((2.0 * PI * x) / (Lf - 1.0)); break;
+        case 3: w[i] = 0.54 - 0.46 * std::cos((2.0 * PI * x) / (Lf - 1.0)); break;
+        default: w[i] = 1.0; break;
+        }
+    }
+    return AUS_OK;
+}
+
+extern "C" int aus_rfftfreq(size_t N, uint32_t sr, double *out) {            // fft_tools.rs:199-206
+    if (!out || N < 2) return fail(AUS_ERR_INVALID, "bad arguments");
+    const double f0 = (double)sr / (double)N;
+    out[0] = 0.0;
+    for (size_t i = 1; i < N / 2 + 1; ++i) out[i] = f0 * (double)i;
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ context (ABI)
+extern "C" int aus_ctx_create(int device, aus_ctx **out) {
+    if (!out) return fail(AUS_ERR_INVALID, "null out");
+    *out = nullptr;
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(AUS_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(AUS_ERR_CUDA, "device is not sm_100-class; kernels are built for sm_100a only");
+    aus_ctx *c = new (std::nothrow) aus_ctx();
+    if (!c) return fail(AUS_ERR_ALLOC, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(AUS_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return AUS_OK;
+}
+
+extern "C" void aus_ctx_destroy(aus_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->tables) {
+        cudaFree(kv.second.twM);
+        cudaFree(kv.second.twN);
+        for (void *w : kv.second.win2) cudaFree(w);
+    }
+    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc}) b->release();
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" int aus_ctx_device(const aus_ctx *c) { return c ? c->device : -1; }
+extern "C" void *aus_ctx_stream(const aus_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int aus_ctx_set_stream(aus_ctx *c, void *s) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (c->own_stream && c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    c->stream = (cudaStream_t)s;
+    c->own_stream = false;
+    return AUS_OK;
+}
+extern "C" int aus_ctx_synchronize(aus_ctx *c) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+extern "C" uint64_t aus_ctx_launch_count(const aus_ctx *c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ tables
+template <typename T> static int upload(void **dst, const std::vector<Cx<T>> &h, cudaStream_t s) {
+    CUDA_TRY(cudaMalloc(dst, h.size() * sizeof(Cx<T>)));
+    CUDA_TRY(cudaMemcpyAsync(*dst, h.data(), h.size() * sizeof(Cx<T>), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // h is a temporary
+    return AUS_OK;
+}
+
+template <typename T> static int get_tables(aus_ctx *c, int lg, int wtype, Tables **out) {
+    const int key = lg * 2 + (sizeof(T) == 4 ? 1 : 0);
+    Tables &tb = c->tables[key];
+    const size_t N = (size_t)1 << lg, Mh = N / 2;
+    const long double TWO_PI = 6.283185307179586476925286766559005768L;
+    if (!tb.twM) {
+        std::vector<Cx<T>> h(Mh);
+        for (size_t k = 0; k < Mh; ++k) {
+            const long double a = TWO_PI * (long double)k / (long double)Mh;
+            h[k].x = (T)cosl(a);
+            h[k].y = (T)(-sinl(a));
+        }
+        AUS_TRY(upload<T>(&tb.twM, h, c->stream));
+    }
+    if (!tb.twN) {
+        std::vector<Cx<T>> h(Mh / 2 + 1);
+        for (size_t k = 0; k <= Mh / 2; ++k) {
+            const long double a = TWO_PI * (long double)k / (long double)N;
+            h[k].x = (T)cosl(a);
+            h[k].y = (T)sinl(a);
+        }
+        AUS_TRY(upload<T>(&tb.twN, h, c->stream));
+    }
+    if (wtype >= 0 && !tb.win2[wtype]) {
+        std::vector<double> w(N);
+        AUS_TRY(aus_generate_window(wtype, N, w.data()));
+        std::vector<Cx<T>> h(Mh);
+        for (size_t n = 0; n < Mh; ++n) {
+            h[n].x = (T)(0.5 * w[2 * n]);       // 0.5: E = (Z[k] + conj Z[M-k]) / 2 of the real-FFT split, exact
+            h[n].y = (T)(0.5 * w[2 * n + 1]);
+        }
+        AUS_TRY(upload<T>(&tb.win2[wtype], h, c->stream));
+    }
+    *out = &tb;
+    return AUS_OK;
+}
+
+// feature constants that depend only on (fft_size, sample_rate): analyzer.rs:46, :60-62; s_a_t.rs:167-230
+template <typename T> static int fill_feature_params(StftParams<T> &p, size_t N, uint32_t sr) {
+    const size_t K = N / 2 + 1;
+    const double n = (double)K;
+    p.f0 = (double)sr / (double)N;
+    const double sum_x = n * (n - 1.0) / 2.0;
+    const double sum_x2 = n * (n - 1.0) * (2.0 * n - 1.0) / 6.0;
+    p.slope_sx = sum_x;
+    p.slope_den = n * sum_x2 - std::pow(sum_x, 2.0);
+    const double fund = (double)sr / ((double)(K - 1) * 2.0);
+    const double fl[3] = {0.0, 1000.0, 0.0}, fu[3] = {1000.0, 5000.0, 5000.0};     // analyzer.rs:60-62
+    long ac[3], af[3], bc[3], bf[3];
+    for (int b = 0; b < 3; ++b) {
+        const double m_fl = fl[b] / fund, m_fu = fu[b] / fund;
+        ac[b] = (long)std::ceil(m_fl);
+        af[b] = (long)std::floor(m_fl);
+        bc[b] = (long)std::ceil(m_fu);
+        bf[b] = (long)std::floor(m_fu);
+        if (bc[b] >= (long)K || ac[b] > bf[b])
+            return fail(AUS_ERR_INVALID, "spectral_slope_region band reaches past the Nyquist bin for this sample_rate "
+                                         "(the reference panics with an index out of bounds, s_a_t.rs:208-215)");
+        double sx = 0.0, sxx = 0.0;                       // sequential, ascending, like the reference's iterators
+        for (long k = ac[b]; k < bf[b]; ++k) {
+            const double f = (k == 0) ? 0.0 : p.f0 * (double)k;
+            sx += f;
+            sxx += f * f;
+        }
+        p.band_fl[b] = fl[b];
+        p.band_fu[b] = fu[b];
+        p.band_tl[b] = m_fl - (double)af[b];
+        p.band_tu[b] = m_fu - (double)bf[b];
+        p.band_sx[b] = fl[b] + sx + fu[b];
+        const double x2 = std::pow(fl[b], 2.0) + sxx + std::pow(fu[b], 2.0);
+        p.band_den[b] = n * x2 - std::pow(p.band_sx[b], 2.0);
+    }
+    p.pick[0] = (int)af[0]; p.pick[1] = (int)ac[0];
+    p.pick[2] = (int)bf[0]; p.pick[3] = (int)bc[0];
+    p.pick[4] = (int)bf[1]; p.pick[5] = (int)bc[1];
+    p.r_lo[0] = (int)ac[0]; p.r_hi[0] = (int)bf[0];
+    p.r_lo[1] = (int)ac[1]; p.r_hi[1] = (int)bf[1];
+    p.bands_low = (bc[1] <= (long)(N / 4)) ? 1 : 0;
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
+    using C = Cfg<T, LG>;
+    static bool attr_done[64] = {false};
+    auto kern = stft_kernel<T, LG>;
+    const size_t smem = C::smem_bytes();
+    if (!attr_done[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 63] = true;
+    }
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+    if (occ < 1) return fail(AUS_ERR_CUDA, "stft kernel does not fit on an SM");
+    const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
+    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
+    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
+    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
+    using C = Cfg<T, LG>;
+    auto kern = analyzer_kernel<T, LG>;
+    const size_t smem = (size_t)C::FPB * C::SCR * sizeof(double);
+    const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
+    const unsigned long long cap = (unsigned long long)c->sm_count * 4;
+    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
+    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+template <typename T, int LG> static int launch_istft_t(aus_ctx *c, const IstftParams<T> &p) {
+    using C = Cfg<T, LG>;
+    static bool attr_done[64] = {false};
+    auto kern = istft_kernel<T, LG>;
+    const size_t smem = C::smem_bytes();
+    if (!attr_done[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 63] = true;
+    }
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+    if (occ < 1) return fail(AUS_ERR_CUDA, "istft kernel does not fit on an SM");
+    const unsigned long long need = (p.n_seg + C::FPB - 1) / C::FPB;
+    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
+    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
+    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+
+#define AUS_DISPATCH_LG(lg, FN, ...)                                          \
+    switch (lg) {                                                             \
+    case 6: return FN<T, 6>(__VA_ARGS__);                                     \
+    case 7: return FN<T, 7>(__VA_ARGS__);                                     \
+    case 8: return FN<T, 8>(__VA_ARGS__);                                     \
+    case 9: return FN<T, 9>(__VA_ARGS__);                                     \
+    case 10: return FN<T, 10>(__VA_ARGS__);                                   \
+    case 11: return FN<T, 11>(__VA_ARGS__);                                   \
+    case 12: return FN<T, 12>(__VA_ARGS__);                                   \
+    case 13: return FN<T, 13>(__VA_ARGS__);                                   \
+    case 14: return FN<T, 14>(__VA_ARGS__);                                   \
+    default: return fail(AUS_ERR_UNSUPPORTED, "fft_size must be in [64, 16384]"); \
+    }
+template <typename T> static int launch_stft(aus_ctx *c, int lg, const StftParams<T> &p) { AUS_DISPATCH_LG(lg, launch_stft_t, c, p) }
+template <typename T> static int launch_analyzer(aus_ctx *c, int lg, const StftParams<T> &p) { AUS_DISPATCH_LG(lg, launch_analyzer_t, c, p) }
+template <typename T> static int launch_istft(aus_ctx *c, int lg, const IstftParams<T> &p) { AUS_DISPATCH_LG(lg, launch_istft_t, c, p) }
+
+// small elementwise kernels
+template <typename A, typename B> __global__ void cast_kernel(const A *in, B *out, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = (B)in[i];
+}
+template <typename A, typename B> static int cast_dev(aus_ctx *c, const A *in, B *out, unsigned long long n) {
+    if (n == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 16);
+    cast_kernel<A, B><<<grid, 256, 0, c->stream>>>(in, out, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+// fft_tools.rs:41-55
+__global__ void to_polar_kernel(const double2 *s, double *mag, double *ph, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 v = s[i];
+        mag[i] = sqrt(v.x * v.x + v.y * v.y);
+        if (ph) ph[i] = atan2(v.y, v.x);
+    }
+}
+// fft_tools.rs:164-188
+__global__ void from_polar_kernel(const double *mag, const double *ph, double2 *s, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        double sn, cs;
+        sincos(ph[i], &sn, &cs);
+        s[i] = make_double2(cs * mag[i], sn * mag[i]);
+    }
+}
+// SURVEY 8d synthetic input: 0.5 sin(c n) + 0.1 u[n], u from a splitmix64-finalised (seed, file, n) counter
+template <typename T>
+__global__ void synth_kernel(T *x, unsigned long long count, unsigned long long n0, double coef,
+                             unsigned long long seed, unsigned long long file_id) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long n = n0 + i;
+        unsigned long long z = seed * 0x9E3779B97F4A7C15ull + file_id * 0xD1B54A32D192ED03ull + n * 0x94D049BB133111EBull +
+                               0x2545F4914F6CDD1Dull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        const double u = (double)(z >> 11) * 0x1p-52 - 1.0;
+        x[i] = (T)(0.5 * sin(coef * (double)n) + 0.1 * u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ forward core
+struct Batch {
+    std::vector<unsigned long long> off, len, first;   // first has n_files + 1 entries
+    unsigned long long total_frames = 0, span = 0;     // span = samples [0, max(off+len))
+};
+static void make_batch(Batch &b, const uint64_t *offsets, const uint64_t *lengths, size_t n_files, size_t N, size_t hop) {
+    b.off.resize(n_files);
+    b.len.resize(n_files);
+    b.first.resize(n_files + 1);
+    unsigned long long f = 0, span = 0;
+    for (size_t i = 0; i < n_files; ++i) {
+        b.off[i] = offsets ? offsets[i] : 0;
+        b.len[i] = lengths[i];
+        b.first[i] = f;
+        f += aus_num_frames((size_t)lengths[i], N, hop);
+        span = std::max(span, b.off[i] + b.len[i]);
+    }
+    b.first[n_files] = f;
+    b.total_frames = f;
+    b.span = span;
+}
+// descriptor arrays -> device (pageable source: cudaMemcpyAsync returns after staging, so the vectors may die)
+static int upload_desc(aus_ctx *c, DevBuf &buf, const std::vector<const std::vector<unsigned long long> *> &arrs,
+                       std::vector<const unsigned long long *> &dptr) {
+    size_t total = 0;
+    for (auto *a : arrs) total += a->size();
+    AUS_TRY(buf.ensure(std::max<size_t>(total, 1) * sizeof(unsigned long long)));
+    unsigned long long *d = (unsigned long long *)buf.p;
+    dptr.clear();
+    for (auto *a : arrs) {
+        if (!a->empty())
+            CUDA_TRY(cudaMemcpyAsync(d, a->data(), a->size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        dptr.push_back(d);
+        d += a->size();
+    }
+    return AUS_OK;
+}
+
+// features and/or spectra of a batch already resident on the device, in compute type T
+template <typename T>
+static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t N, size_t hop, int wtype, uint32_t sr,
+                            T *d_feat, Cx<T> *d_spec) {
+    if (b.total_frames == 0) return AUS_OK;
+    const int lg = log2_exact(N);
+    Tables *tb = nullptr;
+    AUS_TRY(get_tables<T>(c, lg, wtype, &tb));
+    StftParams<T> p;
+    memset(&p, 0, sizeof(p));
+    if (d_feat) AUS_TRY(fill_feature_params<T>(p, N, sr));
+    std::vector<const unsigned long long *> dp;
+    AUS_TRY(upload_desc(c, c->desc, {&b.off, &b.len, &b.first}, dp));
+    p.audio = d_audio;
+    p.file_off = dp[0];
+    p.file_len = dp[1];
+    p.file_first = dp[2];
+    p.n_files = (int)b.off.size();
+    p.total_frames = b.total_frames;
+    p.hop = (int)hop;
+    p.wtype = wtype;
+    p.tma_ok = ((reinterpret_cast<uintptr_t>(d_audio) & 15) == 0) ? 1 : 0;
+    p.win2 = (const Cx<T> *)tb->win2[wtype];
+    p.twM = (const Cx<T> *)tb->twM;
+    p.twN = (const Cx<T> *)tb->twN;
+    p.feat = d_feat;
+    p.spec = d_spec;
+    return launch_stft<T>(c, lg, p);
+}
+
+static int check_common(aus_ctx *c, size_t N, size_t hop, int wtype, int precision) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    AUS_TRY(check_fft_args(N, hop));
+    if (wtype < 0 || wtype > 4) return fail(AUS_ERR_INVALID, "unknown window type");
+    if (precision != AUS_F64 && precision != AUS_F32) return fail(AUS_ERR_INVALID, "unknown precision");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return AUS_OK;
+}
+
+extern "C" int aus_stft_features_batch_dev(aus_ctx *c, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
+                                           size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr, int precision,
+                                           void *d_features, void *d_spectra) {
+    AUS_TRY(check_common(c, N, hop, wtype, precision));
+    if (!lengths || (!d_audio && n_files)) return fail(AUS_ERR_INVALID, "null input");
+    if (!d_features && !d_spectra) return fail(AUS_ERR_INVALID, "no output requested");
+    Batch b;
+    make_batch(b, offsets, lengths, n_files, N, hop);
+    if (precision == AUS_F64)
+        return stft_batch_dev_t<double>(c, (const double *)d_audio, b, N, hop, wtype, sr, (double *)d_features, (Cx<double> *)d_spectra);
+    return stft_batch_dev_t<float>(c, (const float *)d_audio, b, N, hop, wtype, sr, (float *)d_features, (Cx<float> *)d_spectra);
+}
+
+// host-pointer core: upload f64, (convert), run, (convert), download f64
+static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offsets, const uint64_t *lengths, size_t n_files,
+                           size_t N, size_t hop, int wtype, uint32_t sr, int precision, double *features, double *spectra,
+                           uint64_t *frame_starts) {
+    AUS_TRY(check_common(c, N, hop, wtype, precision));
+    if (!lengths) return fail(AUS_ERR_INVALID, "null lengths");
+    Batch b;
+    make_batch(b, offsets, lengths, n_files, N, hop);
+    if (frame_starts) for (size_t i = 0; i <= n_files; ++i) frame_starts[i] = b.first[i];
+    if (b.total_frames == 0) return AUS_OK;
+    if (!audio && b.span) return fail(AUS_ERR_INVALID, "null audio");
+    const size_t K = N / 2 + 1;
+    const unsigned long long nfeat = b.total_frames * 14ull, nspec = b.total_frames * K * 2ull;
+    AUS_TRY(c->in64.ensure(std::max<size_t>(b.span, 2) * sizeof(double)));
+    if (b.span) CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, b.span * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (features) AUS_TRY(c->out64.ensure(nfeat * sizeof(double)));
+    if (spectra) AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
+    if (precision == AUS_F64) {
+        AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->in64.p, b, N, hop, wtype, sr, features ? (double *)c->out64.p : nullptr,
+                                         spectra ? (Cx<double> *)c->aux64.p : nullptr));
+    } else {
+        AUS_TRY(c->in32.ensure(std::max<size_t>(b.span, 4) * sizeof(float)));
+        AUS_TRY(cast_dev<double, float>(c, (const double *)c->in64.p, (float *)c->in32.p, b.span));
+        if (features) AUS_TRY(c->out32.ensure(nfeat * sizeof(float)));
+        if (spectra) AUS_TRY(c->aux32.ensure(nspec * sizeof(float)));
+        AUS_TRY(stft_batch_dev_t<float>(c, (const float *)c->in32.p, b, N, hop, wtype, sr, features ? (float *)c->out32.p : nullptr,
+                                        spectra ? (Cx<float> *)c->aux32.p : nullptr));
+        if (features) AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nfeat));
+        if (spectra) AUS_TRY(cast_dev<float, double>(c, (const float *)c->aux32.p, (double *)c->aux64.p, nspec));
+    }
+    if (features) CUDA_TRY(cudaMemcpyAsync(features, c->out64.p, nfeat * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (spectra) CUDA_TRY(cudaMemcpyAsync(spectra, c->aux64.p, nspec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+extern "C" int aus_stft_features_batch(aus_ctx *c, const double *audio, const uint64_t *offsets, const uint64_t *lengths,
+                                       size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr, int precision,
+                                       double *features, uint64_t *frame_starts) {
+    if (!features) return fail(AUS_ERR_INVALID, "null features");
+    return stft_batch_host(c, audio, offsets, lengths, n_files, N, hop, wtype, sr, precision, features, nullptr, frame_starts);
+}
+
+extern "C" int aus_stft_features(aus_ctx *c, const double *audio, size_t n, size_t N, size_t hop, int wtype, uint32_t sr,
+                                 int precision, double *features) {
+    if (!features) return fail(AUS_ERR_INVALID, "null features");
+    const uint64_t off = 0, len = n;
+    return stft_batch_host(c, audio, &off, &len, 1, N, hop, wtype, sr, precision, features, nullptr, nullptr);
+}
+
+extern "C" int aus_stft_analysis(aus_ctx *c, const double *audio, size_t n, size_t N, uint32_t sr, size_t max_num_threads,
+                                 aus_analysis *out) {                           // mp.rs:26-119
+    (void)max_num_threads;
+    static_assert(sizeof(aus_analysis) == 14 * sizeof(double), "aus_analysis must be 14 packed doubles");
+    return aus_stft_features(c, audio, n, N, N / 2, AUS_WINDOW_HAMMING, sr, AUS_F64, reinterpret_cast<double *>(out));
+}
+
+extern "C" int aus_rstft(aus_ctx *c, const double *audio, size_t n, size_t N, size_t hop, int wtype, int precision,
+                         double *spectra) {                                     // fft.rs:119-178
+    if (!spectra) return fail(AUS_ERR_INVALID, "null spectra");
+    const uint64_t off = 0, len = n;
+    return stft_batch_host(c, audio, &off, &len, 1, N, hop, wtype, 44100, precision, nullptr, spectra, nullptr);
+}
+extern "C" int aus_rstft_dev(aus_ctx *c, const void *d_audio, size_t n, size_t N, size_t hop, int wtype, int precision,
+                             void *d_spectra) {
+    const uint64_t off = 0, len = n;
+    return aus_stft_features_batch_dev(c, d_audio, &off, &len, 1, N, hop, wtype, 44100, precision, nullptr, d_spectra);
+}
+extern "C" int aus_rfft(aus_ctx *c, const double *audio, size_t N, int precision, double *spectrum) {   // fft.rs:37-47
+    return aus_rstft(c, audio, N, N, N, AUS_WINDOW_RECTANGULAR, precision, spectrum);
+}
+
+// ------------------------------------------------------------------------------------------------ polar
+extern "C" int aus_complex_to_polar(aus_ctx *c, const double *spectra, size_t n, double *mag, double *ph) {
+    if (!c || !spectra || !mag) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return AUS_OK;
+    AUS_TRY(c->aux64.ensure(n * 2 * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->aux64.p, spectra, n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    double *dm = (double *)c->out64.p, *dp = ph ? dm + n : nullptr;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 16);
+    to_polar_kernel<<<grid, 256, 0, c->stream>>>((const double2 *)c->aux64.p, dm, dp, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(mag, dm, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (ph) CUDA_TRY(cudaMemcpyAsync(ph, dp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+extern "C" int aus_polar_to_complex(aus_ctx *c, const double *mag, const double *ph, size_t n, double *spectra) {
+    if (!c || !spectra || !mag || !ph) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return AUS_OK;
+    AUS_TRY(c->aux64.ensure(n * 2 * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n * 2 * sizeof(double)));
+    double *dm = (double *)c->out64.p, *dp = dm + n;
+    CUDA_TRY(cudaMemcpyAsync(dm, mag, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dp, ph, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 16);
+    from_polar_kernel<<<grid, 256, 0, c->stream>>>(dm, dp, (double2 *)c->aux64.p, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(spectra, c->aux64.p, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ analyzer (K3)
+template <typename T> static int analyzer_dev_t(aus_ctx *c, const T *d_mags, size_t F, size_t N, uint32_t sr, T *d_feat) {
+    if (F == 0) return AUS_OK;
+    StftParams<T> p;
+    memset(&p, 0, sizeof(p));
+    AUS_TRY(fill_feature_params<T>(p, N, sr));
+    p.mags = d_mags;
+    p.total_frames = F;
+    p.feat = d_feat;
+    p.bands_low = 0;
+    return launch_analyzer<T>(c, log2_exact(N), p);
+}
+extern "C" int aus_analyzer_batch_dev(aus_ctx *c, const void *d_mags, size_t F, size_t N, uint32_t sr, int precision, void *d_feat) {
+    AUS_TRY(check_common(c, N, 1, 0, precision));
+    if (!d_mags || !d_feat) return fail(AUS_ERR_INVALID, "null argument");
+    if (precision == AUS_F64) return analyzer_dev_t<double>(c, (const double *)d_mags, F, N, sr, (double *)d_feat);
+    return analyzer_dev_t<float>(c, (const float *)d_mags, F, N, sr, (float *)d_feat);
+}
+extern "C" int aus_analyzer_batch(aus_ctx *c, const double *mags, size_t F, size_t N, uint32_t sr, int precision, double *features) {
+    AUS_TRY(check_common(c, N, 1, 0, precision));
+    if (!mags || !features) return fail(AUS_ERR_INVALID, "null argument");
+    if (F == 0) return AUS_OK;
+    const size_t K = N / 2 + 1, nm = F * K, nf = F * 14;
+    AUS_TRY(c->in64.ensure(nm * sizeof(double)));
+    AUS_TRY(c->out64.ensure(nf * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->in64.p, mags, nm * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (precision == AUS_F64) {
+        AUS_TRY(analyzer_dev_t<double>(c, (const double *)c->in64.p, F, N, sr, (double *)c->out64.p));
+    } else {
+        AUS_TRY(c->in32.ensure(nm * sizeof(float)));
+        AUS_TRY(c->out32.ensure(nf * sizeof(float)));
+        AUS_TRY(cast_dev<double, float>(c, (const double *)c->in64.p, (float *)c->in32.p, nm));
+        AUS_TRY(analyzer_dev_t<float>(c, (const float *)c->in32.p, F, N, sr, (float *)c->out32.p));
+        AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nf));
+    }
+    CUDA_TRY(cudaMemcpyAsync(features, c->out64.p, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ inverse (K4/K5)
+template <typename T>
+static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, size_t hop, int wtype, int normalize,
+                        int apply_window, T *d_out) {
+    const int lg = log2_exact(N);
+    Tables *tb = nullptr;
+    AUS_TRY(get_tables<T>(c, lg, wtype, &tb));
+    const long long halo = (long long)((N + hop - 1) / hop) - 1;
+    // segments: contiguous frame ranges, about one per resident frame group, never shorter than 4 * (halo + 1)
+    const unsigned long long groups = (unsigned long long)c->sm_count * (256 / std::max<size_t>(1, N / 64)) * (sizeof(T) == 4 ? 2 : 1);
+    unsigned long long seglen = std::max<unsigned long long>((F + groups - 1) / groups, 4ull * (unsigned long long)(halo + 1));
+    const unsigned long long nseg = std::max<unsigned long long>(1, (F + seglen / 2) / seglen);
+    std::vector<unsigned long long> sfile(nseg, 0), sa(nseg), sb(nseg), first = {0ull, (unsigned long long)F}, ooff = {0ull},
+                                    olen = {(unsigned long long)aus_irstft_len(F, N, hop)};
+    for (unsigned long long s = 0; s < nseg; ++s) {
+        sa[s] = F * s / nseg;
+        sb[s] = F * (s + 1) / nseg;
+    }
+    std::vector<const unsigned long long *> dp;
+    AUS_TRY(upload_desc(c, c->desc, {&sfile, &sa, &sb, &first, &ooff, &olen}, dp));
+    AUS_TRY(c->misc.ensure(sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, sizeof(unsigned long long), c->stream));      // maxval = 0.0, fft.rs:255
+    IstftParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.spec = d_spec;
+    p.out = d_out;
+    p.seg_file = dp[0];
+    p.seg_a = dp[1];
+    p.seg_b = dp[2];
+    p.file_first = dp[3];
+    p.file_out_off = dp[4];
+    p.file_max_bits = (unsigned long long *)c->misc.p;
+    p.n_seg = nseg;
+    p.hop = (int)hop;
+    p.halo = (int)halo;
+    p.apply_window = apply_window;
+    p.tma_ok = ((reinterpret_cast<uintptr_t>(d_spec) & 15) == 0) ? 1 : 0;
+    p.fwd.win2 = (const Cx<T> *)tb->win2[wtype];
+    p.fwd.twM = (const Cx<T> *)tb->twM;
+    p.fwd.twN = (const Cx<T> *)tb->twN;
+    AUS_TRY(launch_istft<T>(c, lg, p));
+    if (apply_window && normalize) {
+        const double level = std::pow(10.0, -6.0 / 20.0);                                  // fft.rs:261-262
+        dim3 grid((unsigned int)std::min<unsigned long long>((olen[0] + 255) / 256, (unsigned long long)c->sm_count * 8), 1);
+        peak_scale_kernel<T><<<grid, 256, 0, c->stream>>>(d_out, dp[4], dp[5], (const unsigned long long *)c->misc.p, level);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    return AUS_OK;
+}
+
+extern "C" int aus_irstft_dev(aus_ctx *c, const void *d_spec, size_t F, size_t N, size_t hop, int wtype, int precision,
+                              int normalize, void *d_audio) {
+    AUS_TRY(check_common(c, N, hop, wtype, precision));
+    if (F == 0) return fail(AUS_ERR_INVALID, "empty spectrogram (the reference underflows at fft.rs:208)");
+    if (!d_spec || !d_audio) return fail(AUS_ERR_INVALID, "null argument");
+    if (precision == AUS_F64) return irstft_dev_t<double>(c, (const Cx<double> *)d_spec, F, N, hop, wtype, normalize, 1, (double *)d_audio);
+    return irstft_dev_t<float>(c, (const Cx<float> *)d_spec, F, N, hop, wtype, normalize, 1, (float *)d_audio);
+}
+
+static int irstft_host(aus_ctx *c, const double *spectra, size_t F, size_t N, size_t hop, int wtype, int precision, int normalize,
+                       int apply_window, double *audio) {
+    const size_t K = N / 2 + 1, nspec = F * K * 2, nout = aus_irstft_len(F, N, hop);
+    AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
+    AUS_TRY(c->out64.ensure(nout * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->aux64.p, spectra, nspec * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (precision == AUS_F64) {
+        AUS_TRY(irstft_dev_t<double>(c, (const Cx<double> *)c->aux64.p, F, N, hop, wtype, normalize, apply_window, (double *)c->out64.p));
+    } else {
+        AUS_TRY(c->aux32.ensure(nspec * sizeof(float)));
+        AUS_TRY(c->out32.ensure(nout * sizeof(float)));
+        AUS_TRY(cast_dev<double, float>(c, (const double *)c->aux64.p, (float *)c->aux32.p, nspec));
+        AUS_TRY(irstft_dev_t<float>(c, (const Cx<float> *)c->aux32.p, F, N, hop, wtype, normalize, apply_window, (float *)c->out32.p));
+        AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nout));
+    }
+    CUDA_TRY(cudaMemcpyAsync(audio, c->out64.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+extern "C" int aus_irstft(aus_ctx *c, const double *spectra, size_t F, size_t frame_len, size_t N, size_t hop, int wtype,
+                          int precision, int normalize, double *audio) {                 // fft.rs:204-268
+    AUS_TRY(check_common(c, N, hop, wtype, precision));
+    if (F == 0) return fail(AUS_ERR_INVALID, "empty spectrogram (the reference underflows at fft.rs:208)");
+    if (frame_len != N / 2 + 1) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "The spectrum at frame %d has an incorrect length. It should be %zu, but it is actually %zu.",
+                 0, N / 2 + 1, frame_len);                                               // fft.rs:218
+        return fail(AUS_ERR_SIZE, msg);
+    }
+    if (!spectra || !audio) return fail(AUS_ERR_INVALID, "null argument");
+    return irstft_host(c, spectra, F, N, hop, wtype, precision, normalize, 1, audio);
+}
+
+extern "C" int aus_irfft(aus_ctx *c, const double *spectrum, size_t spectrum_len, size_t N, int precision, double *audio) {  // fft.rs:66-93
+    AUS_TRY(check_common(c, N, N, AUS_WINDOW_RECTANGULAR, precision));
+    if (spectrum_len != N / 2 + 1) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "The spectrum is the wrong size. It should be %zu, but it is actually %zu.", N / 2 + 1,
+                 spectrum_len);                                                          // fft.rs:71
+        return fail(AUS_ERR_SIZE, msg);
+    }
+    if (!spectrum || !audio) return fail(AUS_ERR_INVALID, "null argument");
+    return irstft_host(c, spectrum, 1, N, N, AUS_WINDOW_RECTANGULAR, precision, 0, 0, audio);
+}
+
+// ------------------------------------------------------------------------------------------------ synthetic input
+extern "C" int aus_synth_dev(aus_ctx *c, void *d_audio, uint64_t n, uint64_t n0, uint32_t sr, double freq, uint64_t seed,
+                             uint64_t file_id, int precision) {
+    if (!c || (!d_audio && n)) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return AUS_OK;
+    const double coef = 2.0 * 3.14159265358979323846264338327950288 * freq / (double)sr;   // synthesis.rs:52
+    const unsigned int grid = (unsigned int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 16);
+    if (precision == AUS_F64) synth_kernel<double><<<grid, 256, 0, c->stream>>>((double *)d_audio, n, n0, coef, seed, file_id);
+    else synth_kernel<float><<<grid, 256, 0, c->stream>>>((float *)d_audio, n, n0, coef, seed, file_id);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU sharding
+// No collective: frames and files are independent.  Each device gets a contiguous run of (virtual) files; a
+// single long file is cut into contiguous frame ranges whose sample spans overlap by fft_size - hop, and only the span
+// that ends at the true end of the file can produce the short last frame.  Host threads, ordered gather into `features`.
+static std::mutex g_multi_mu;
+static std::map<int, aus_ctx *> g_multi_ctx;
+
+extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
+                                       const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr,
+                                       int precision, double *features) {
+    if (n_devices < 1) return fail(AUS_ERR_INVALID, "n_devices must be >= 1");
+    AUS_TRY(check_fft_args(N, hop));
+    if (!lengths || !features) return fail(AUS_ERR_INVALID, "null argument");
+    // virtual files: (offset, length, first output row)
+    struct VF { uint64_t off, len, row, frames; };
+    std::vector<VF> vf;
+    uint64_t row = 0;
+    for (size_t i = 0; i < n_files; ++i) {
+        const uint64_t off = offsets ? offsets[i] : 0, len = lengths[i];
+        const uint64_t F = aus_num_frames((size_t)len, N, hop);
+        const uint64_t parts = (n_files >= (size_t)n_devices) ? 1 : std::min<uint64_t>(F, (uint64_t)n_devices);
+        for (uint64_t s = 0; s < parts; ++s) {
+            const uint64_t a = F * s / parts, b = F * (s + 1) / parts;
+            VF v;
+            v.off = off + a * hop;
+            v.len = (b == F) ? len - std::min<uint64_t>(len, a * hop) : (b - a - 1) * hop + N;   // full frames only unless it holds the end
+            v.row = row + a;
+            v.frames = b - a;
+            vf.push_back(v);
+        }
+        row += F;
+    }
+    const uint64_t total = row;
+    // contiguous split of the virtual files over devices, balanced by frame count
+    std::vector<size_t> cut(n_devices + 1, vf.size());
+    cut[0] = 0;
+    {
+        uint64_t acc = 0;
+        int d = 1;
+        for (size_t i = 0; i < vf.size() && d < n_devices; ++i) {
+            acc += vf[i].frames;
+            while (d < n_devices && acc * (uint64_t)n_devices >= total * (uint64_t)d) cut[d++] = i + 1;
+        }
+    }
+    std::vector<int> rc(n_devices, AUS_OK);
+    std::vector<std::string> msg(n_devices);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_devices; ++d) {
+        th.emplace_back([&, d]() {
+            const size_t lo = cut[d], hi = cut[d + 1];
+            if (lo >= hi) return;
+            const int dev = devices ? devices[d] : d;
+            aus_ctx *ctx = nullptr;
+            {
+                std::lock_guard<std::mutex> lk(g_multi_mu);
+                auto it = g_multi_ctx.find(dev);
+                if (it == g_multi_ctx.end()) {
+                    rc[d] = aus_ctx_create(dev, &ctx);
+                    if (rc[d] != AUS_OK) { msg[d] = g_err; return; }
+                    g_multi_ctx[dev] = ctx;
+                } else ctx = it->second;
+            }
+            // the device's sample span, re-based to its first sample
+            uint64_t s0 = UINT64_MAX, s1 = 0;
+            for (size_t i = lo; i < hi; ++i) { s0 = std::min(s0, vf[i].off); s1 = std::max(s1, vf[i].off + vf[i].len); }
+            std::vector<uint64_t> o(hi - lo), l(hi - lo);
+            for (size_t i = lo; i < hi; ++i) { o[i - lo] = vf[i].off - s0; l[i - lo] = vf[i].len; }
+            rc[d] = aus_stft_features_batch(ctx, audio + s0, o.data(), l.data(), hi - lo, N, hop, wtype, sr, precision,
+                                            features + vf[lo].row * 14, nullptr);
+            if (rc[d] != AUS_OK) msg[d] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rc[d] != AUS_OK) return fail(rc[d], msg[d]);
+    return AUS_OK;
+}

@@ -1,0 +1,185 @@
+// aus_istft_kernel.cuh -- inverse real STFT: Hermitian pre-twiddle + packed inverse FFT + window + deterministic
+// overlap-add + window-norm divide + peak tracking (K4), and the -6 dBFS rescale pass (K5).  sm_100a.
+//
+// Replaces spectrum/fft.rs:204-268 (`irstft`), spectrum/fft_tools.rs:69-112 (`overlap_add`) and, as a batch of
+// one frame without window/normalisation, spectrum/fft.rs:66-93 (`irfft`).
+//
+// A frame group (same TPF / 32-points-per-thread layout as the forward kernel) owns one *segment*: a contiguous
+// frame range [a, b) of one file and the output samples [a*hop, b*hop) (to the end of the signal for the last
+// segment).  It walks its frames in ascending order and accumulates each windowed chunk straight into the output
+// array (L2-resident read-modify-write, no atomics), so every sample sums its covering frames in ascending frame
+// order exactly like fft_tools.rs:102-105.  The ceil(N/hop)-1 frames before `a` that still overlap the segment are
+// recomputed instead of communicated.  A sample is divided by its window norm the moment its last frame lands.
+#pragma once
+#include "aus_stft_kernel.cuh"
+
+namespace aus {
+
+template <typename T> struct IstftParams {
+    const Cx<T> *spec;                       // [total_frames][K]
+    T *out;                                  // all files' outputs, contiguous
+    const unsigned long long *seg_file;      // [n_seg] file index
+    const unsigned long long *seg_a, *seg_b; // [n_seg] frame range inside the file
+    const unsigned long long *file_first;    // [n_files + 1] first global frame of each file
+    const unsigned long long *file_out_off;  // [n_files] first output sample of each file
+    unsigned long long *file_max_bits;       // [n_files] bit pattern of max(out, 0.0) as f64 (fft.rs:255-258)
+    unsigned long long n_seg;
+    int hop;
+    int halo;                                // ceil(N / hop) - 1
+    int apply_window;                        // 0: irfft (plain inverse, no window / norm)
+    int tma_ok;
+    StftParams<T> fwd;                       // tables (win2, twM, twN) for frame_fft
+};
+
+template <typename T, int LOG2N>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) istft_kernel(const IstftParams<T> p) {
+    using C = Cfg<T, LOG2N>;
+    constexpr int N = C::N, M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
+    Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FPB * C::BUF * sizeof(Cx<T>) +
+                                                 (size_t)FPB * C::SCR * sizeof(double)) + grp;
+    if (t == 0) mbar_init(bar, 1);
+    fence_mbar_init();
+    __syncthreads();
+    uint32_t parity = 0;
+
+    const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
+    const unsigned long long iters = (p.n_seg + stride - 1) / stride;
+    const long long hop = p.hop;
+    for (unsigned long long it = 0; it < iters; ++it) {
+        const unsigned long long sidx = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
+        const bool seg_ok = sidx < p.n_seg;
+        long long a = 0, b = 0, F = 0, h_begin = 0;
+        unsigned long long gfirst = 0, ooff = 0;
+        int file = 0;
+        if (seg_ok) {
+            file = (int)p.seg_file[sidx];
+            a = (long long)p.seg_a[sidx];
+            b = (long long)p.seg_b[sidx];
+            gfirst = p.file_first[file];
+            F = (long long)(p.file_first[file + 1] - gfirst);
+            ooff = p.file_out_off[file];
+            h_begin = a - p.halo > 0 ? a - p.halo : 0;
+        }
+        // groups that share a warp must run the same number of frame steps (barriers are warp-wide for TPF <= 32)
+        long long steps = seg_ok ? b - h_begin : 0;
+        if constexpr (TPF < 32) {
+#pragma unroll
+            for (int off = 16; off >= TPF; off >>= 1) {
+                const long long o = __shfl_xor_sync(0xffffffffu, steps, off);
+                steps = o > steps ? o : steps;
+            }
+        }
+        const long long own_lo = a * hop;
+        const long long out_len = (F > 0) ? (long long)N + hop * (F - 1) : 0;
+        const long long own_hi = (b == F) ? out_len : b * hop;
+        T vmax = (T)0;
+
+        for (long long st = 0; st < steps; ++st) {
+            const long long h = h_begin + st;
+            const bool active = seg_ok && h < b;
+            const Cx<T> *row = p.spec + (gfirst + (unsigned long long)(active ? h : 0)) * (unsigned long long)K;
+            // ---- stage the K bins of this frame (TMA bulk copy when the row is 16-byte sized and aligned)
+            const bool use_tma = active && p.tma_ok && ((K * sizeof(Cx<T>)) % 16 == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+            if (use_tma) {
+                if (t == 0) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)(K * sizeof(Cx<T>)));
+                    tma_load_1d(buf, row, (uint32_t)(K * sizeof(Cx<T>)), bar);
+                }
+            } else {
+                for (int i = t; i < K; i += TPF) buf[i] = active ? row[i] : Cx<T>{(T)0, (T)0};
+            }
+            if (use_tma) {
+                mbar_wait(bar, parity);
+                parity ^= 1u;
+            }
+            group_sync<TPF, C::BLOCK>(grp);
+
+            // ---- Hermitian pre-twiddle, in place: buf[k] <- conj(Zi[k]),
+            //      Zi[k] = (Y[k] + conj Y[M-k]) + i W_N^{-k} (Y[k] - conj Y[M-k])   (fft.rs:221-229 folded in)
+#pragma unroll 4
+            for (int i = 0; i <= 16; ++i) {
+                const int k = t + TPF * i;                 // pairs (k, M-k), k = 0 .. M/2
+                if (i == 16 && t != 0) break;
+                Cx<T> Yk = buf[k], Ym = buf[M - k];
+                if (k == 0) { Yk.y = (T)0; Ym.y = (T)0; }   // imaginary parts of DC / Nyquist vanish under `.re` (fft.rs:235)
+                const Cx<T> W = ldg_cx(&p.fwd.twN[k]);      // (cos, sin)(2 pi k / N)
+                const T sx = Yk.x + Ym.x, sy = Yk.y - Ym.y;
+                const T dx = Yk.x - Ym.x, dy = Yk.y + Ym.y;
+                const T ux = W.x * dx - W.y * dy;          // U = W^{-k} D, W^{-k} = c + i s
+                const T uy = W.x * dy + W.y * dx;
+                buf[k] = Cx<T>{sx - uy, -(sy + ux)};
+                if (k != 0 && k != M / 2) buf[M - k] = Cx<T>{sx + uy, sy - ux};
+            }
+            group_sync<TPF, C::BLOCK>(grp);
+
+            frame_fft<T, LOG2N>(buf, p.fwd, t, grp, /*prewindowed=*/true);     // buf: conj(z) in the Z layout
+
+            // ---- window + overlap-add into the output (ascending frame order), finalise completed samples
+            if (active) {
+                T *out = p.out + ooff;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    const int n = t + TPF * i;
+                    const Cx<T> z = buf[padi<4>(n)];
+                    const Cx<T> w = ldg_cx(&p.fwd.win2[n]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const long long j = h * hop + 2 * n + e;
+                        if (j < own_lo || j >= own_hi) continue;
+                        T val = (e == 0) ? z.x : -z.y;
+                        if (!p.apply_window) { out[j] = val; continue; }
+                        val *= (T)2 * (e == 0 ? w.x : w.y);                                    // fft.rs:234-236
+                        const long long h_first = (j >= N) ? (j - N) / hop + 1 : 0;
+                        const long long h_last = (j / hop < F - 1) ? j / hop : F - 1;
+                        if (h > h_first) val += __ldcg(out + j);
+                        if (h == h_last) {
+                            T norm = (T)0;                                                     // fft.rs:239-243
+                            for (long long hh = h_first; hh <= h_last; ++hh) {
+                                const int idx = (int)(j - hh * hop);
+                                const Cx<T> ww = ldg_cx(&p.fwd.win2[idx >> 1]);
+                                const T wv = (T)2 * ((idx & 1) ? ww.y : ww.x);
+                                norm += wv * wv;
+                            }
+                            val /= norm;                                                       // fft.rs:250-252
+                            if (val > vmax) vmax = val;                                        // f64::max skips NaN
+                        }
+                        out[j] = val;
+                    }
+                }
+            }
+            fence_proxy_async();
+            group_sync<TPF, C::BLOCK>(grp);                 // frame h's writes visible before frame h+1 reads them
+        }
+        // ---- per-file peak (signed max, starts at 0.0): positive IEEE doubles order like unsigned integers
+        if (p.apply_window) {
+            constexpr int W = TPF < 32 ? TPF : 32;
+#pragma unroll
+            for (int off = W / 2; off >= 1; off >>= 1) {
+                const T o = __shfl_xor_sync(0xffffffffu, vmax, off);
+                vmax = o > vmax ? o : vmax;
+            }
+            if ((t & (W - 1)) == 0 && seg_ok && vmax > (T)0)
+                atomicMax(p.file_max_bits + file, (unsigned long long)__double_as_longlong((double)vmax));
+        }
+    }
+}
+
+// K5: audio *= 10^(-6/20) / maxval per file (fft.rs:260-265).  grid.y = file.
+template <typename T>
+__global__ void peak_scale_kernel(T *out, const unsigned long long *file_out_off, const unsigned long long *file_out_len,
+                                  const unsigned long long *file_max_bits, double level) {
+    const int file = blockIdx.y;
+    const double maxval = __longlong_as_double((long long)file_max_bits[file]);
+    const T scaler = (T)(level / maxval);
+    T *o = out + file_out_off[file];
+    const unsigned long long n = file_out_len[file];
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        o[i] *= scaler;
+}
+
+}  // namespace aus

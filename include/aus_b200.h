@@ -1,0 +1,169 @@
+/* aus_b200.h -- C ABI of the B200-native (sm_100a) STFT + spectral-feature path of `aus`.
+ *
+ * This is the drop-in boundary: the functions a Rust shim (aus-rust_b200/rust/, `extern "C"` block) or any
+ * FFI (ctypes, cgo, JNI) binds in place of the reference's CPU code.  The reference has no FFI of its own;
+ * its boundary is the crate's public Rust API (src/lib.rs:8-21), so each entry point below cites the Rust
+ * function it replaces (paths relative to the reference's src/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; nothing throws across the boundary.
+ *   - every call returns AUS_OK (0) or a negative aus_status; aus_last_error() returns a thread-local
+ *     message the shim can wrap into `SpectrumError { error_msg }` (spectrum/fft.rs:16-19).
+ *   - outputs are caller-allocated, flat and row-major, sized with aus_num_frames():
+ *       spectra   : frames x (fft_size/2+1) x {re, im}
+ *       features  : frames x 14, in the declaration order of `Analysis` (analysis/analyzer.rs:10-23)
+ *   - `precision` selects the arithmetic type on the device: AUS_F64 (reference-exact API, default) or AUS_F32
+ *     (opt-in).  Host-pointer entry points always take and return f64 and convert on the device; `_dev` entry
+ *     points take device buffers already in the compute type (double* / float*).
+ *   - `_dev` entry points are stream-ordered on the context's stream and do NOT synchronise; host-pointer entry
+ *     points copy H2D, run, copy D2H and return when the result is in the caller's buffer.
+ *   - there is no CPU fallback: without a usable CUDA device every compute call fails with AUS_ERR_CUDA.
+ *   - fft_size must be a power of two in [64, 16384]; 1 <= hop <= fft_size.  (The reference loops forever on
+ *     hop == 0 and panics on hop > fft_size, spectrum/fft.rs:126-144; here both are AUS_ERR_INVALID.)
+ */
+#ifndef AUS_B200_H
+#define AUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum aus_status {
+    AUS_OK = 0,
+    AUS_ERR_INVALID = -1,      /* bad argument (hop, fft_size, null pointer, band above Nyquist, ...) */
+    AUS_ERR_CUDA = -2,         /* CUDA runtime error or no device */
+    AUS_ERR_ALLOC = -3,        /* host or device allocation failed */
+    AUS_ERR_SIZE = -4,         /* spectrum length mismatch (irfft / irstft `Err(SpectrumError)`, fft.rs:70-72, :217-219) */
+    AUS_ERR_UNSUPPORTED = -5   /* valid for the reference but not built here (e.g. non power-of-two fft_size) */
+} aus_status;
+
+/* window.rs:9-15 `WindowType`, same order */
+typedef enum aus_window {
+    AUS_WINDOW_BARTLETT = 0,
+    AUS_WINDOW_BLACKMAN = 1,
+    AUS_WINDOW_HANNING = 2,
+    AUS_WINDOW_HAMMING = 3,
+    AUS_WINDOW_RECTANGULAR = 4
+} aus_window;
+
+typedef enum aus_precision { AUS_F64 = 0, AUS_F32 = 1 } aus_precision;
+
+#define AUS_NUM_FEATURES 14
+
+/* analysis/analyzer.rs:9-24 `Analysis`, #[repr(C)] mirror (field order = declaration order) */
+typedef struct aus_analysis {
+    double spectral_centroid;
+    double spectral_variance;
+    double spectral_skewness;
+    double spectral_kurtosis;
+    double spectral_entropy;
+    double spectral_flatness;
+    double spectral_roll_off_50;
+    double spectral_roll_off_75;
+    double spectral_roll_off_90;
+    double spectral_roll_off_95;
+    double spectral_slope;
+    double spectral_slope_0_1_khz;
+    double spectral_slope_1_5_khz;
+    double spectral_slope_0_5_khz;
+} aus_analysis;
+
+/* Opaque per-device context: device id, stream, twiddle/window tables, scratch.  Not shared between threads
+ * concurrently; create one per caller thread (the reference's functions are stateless and re-entrant). */
+typedef struct aus_ctx aus_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------------- */
+const char *aus_version(void);
+const char *aus_last_error(void);                       /* thread-local, never NULL */
+int aus_device_count(void);                             /* < 0 on CUDA error */
+int aus_ctx_create(int device, aus_ctx **out);
+void aus_ctx_destroy(aus_ctx *ctx);
+int aus_ctx_device(const aus_ctx *ctx);
+void *aus_ctx_stream(const aus_ctx *ctx);               /* cudaStream_t, for callers that enqueue their own work */
+int aus_ctx_set_stream(aus_ctx *ctx, void *cuda_stream);/* run on a caller-owned stream (e.g. torch's current stream) */
+int aus_ctx_synchronize(aus_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t aus_ctx_launch_count(const aus_ctx *ctx);
+
+/* ---- pure host helpers ------------------------------------------------------------------------------- */
+/* frame count of the loop in spectrum/fft.rs:126-176 (strict `<` at :131; len <= fft_size -> 1 frame) */
+size_t aus_num_frames(size_t n_samples, size_t fft_size, size_t hop);
+/* irstft output length, spectrum/fft.rs:208: fft_size + hop * (frames - 1) */
+size_t aus_irstft_len(size_t n_frames, size_t fft_size, size_t hop);
+/* window.rs:110-118 `generate_window` (and the five generators at :26-98), f64, host */
+int aus_generate_window(int window_type, size_t window_length, double *out);
+/* spectrum/fft_tools.rs:199-206 `rfftfreq` */
+int aus_rfftfreq(size_t fft_size, uint32_t sample_rate, double *out /* fft_size/2+1 */);
+
+/* ---- fused STFT -> magnitude -> 14 features (kernel K1) ---------------------------------------------- */
+/* replaces the loop rstft -> complex_to_polar_rstft -> analyzer per frame (analysis/analyzer.rs:99-104,
+ * mp.rs:42-88) for a general hop and window. */
+int aus_stft_features(aus_ctx *ctx, const double *audio, size_t n_samples, size_t fft_size, size_t hop,
+                      int window_type, uint32_t sample_rate, int precision, double *features /* F x 14 */);
+/* mp.rs:26 `stft_analysis(audio, fft_size, sample_rate, max_num_threads)`: hop = fft_size/2, Hamming (mp.rs:42).
+ * `max_num_threads` is accepted and ignored (the GPU replaces the thread pool). */
+int aus_stft_analysis(aus_ctx *ctx, const double *audio, size_t n_samples, size_t fft_size, uint32_t sample_rate,
+                      size_t max_num_threads, aus_analysis *out /* F */);
+/* batch of files in one launch: file i is audio[offsets[i] .. offsets[i]+lengths[i]); features of file i start at
+ * row frame_starts[i] (frame_starts has n_files+1 entries, filled by the call; may be NULL). */
+int aus_stft_features_batch(aus_ctx *ctx, const double *audio, const uint64_t *offsets, const uint64_t *lengths,
+                            size_t n_files, size_t fft_size, size_t hop, int window_type, uint32_t sample_rate,
+                            int precision, double *features, uint64_t *frame_starts);
+/* device-resident variant: d_audio is T[...], d_features is T[total_frames x 14] (T = double or float per
+ * `precision`); offsets/lengths are HOST arrays.  Optionally also writes spectra (d_spectra: T[frames x K x 2],
+ * may be NULL).  Stream-ordered, no sync. */
+int aus_stft_features_batch_dev(aus_ctx *ctx, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
+                                size_t n_files, size_t fft_size, size_t hop, int window_type, uint32_t sample_rate,
+                                int precision, void *d_features, void *d_spectra);
+/* total frames of a batch (sum of aus_num_frames over files) */
+uint64_t aus_batch_num_frames(const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop);
+
+/* one file / batch sharded over several GPUs (contiguous frame ranges or whole files per device), host gather in
+ * shard order like mp.rs:100-116.  devices == NULL -> devices 0..n_devices-1. */
+int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
+                            const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop, int window_type,
+                            uint32_t sample_rate, int precision, double *features);
+
+/* ---- STFT with spectra written out (kernel K2) ------------------------------------------------------- */
+/* spectrum/fft.rs:119 `rstft` */
+int aus_rstft(aus_ctx *ctx, const double *audio, size_t n_samples, size_t fft_size, size_t hop, int window_type,
+              int precision, double *spectra /* F x K x 2 */);
+int aus_rstft_dev(aus_ctx *ctx, const void *d_audio, size_t n_samples, size_t fft_size, size_t hop,
+                  int window_type, int precision, void *d_spectra);
+/* spectrum/fft.rs:37 `rfft` (one frame, no window; audio has fft_size samples) */
+int aus_rfft(aus_ctx *ctx, const double *audio, size_t fft_size, int precision, double *spectrum /* K x 2 */);
+
+/* ---- polar conversion on device (spectrum/fft_tools.rs:21-55, :131-188) ------------------------------- */
+int aus_complex_to_polar(aus_ctx *ctx, const double *spectra, size_t n_bins_total, double *magnitudes, double *phases);
+int aus_polar_to_complex(aus_ctx *ctx, const double *magnitudes, const double *phases, size_t n_bins_total, double *spectra);
+
+/* ---- features from caller-supplied magnitude spectra (kernel K3) ------------------------------------- */
+/* analysis/analyzer.rs:41 `analyzer` over a batch of rows; each row has fft_size/2+1 magnitudes */
+int aus_analyzer_batch(aus_ctx *ctx, const double *magnitudes, size_t n_frames, size_t fft_size,
+                       uint32_t sample_rate, int precision, double *features /* n_frames x 14 */);
+int aus_analyzer_batch_dev(aus_ctx *ctx, const void *d_magnitudes, size_t n_frames, size_t fft_size,
+                           uint32_t sample_rate, int precision, void *d_features);
+
+/* ---- inverse (kernels K4/K5) ------------------------------------------------------------------------- */
+/* spectrum/fft.rs:204 `irstft`: Hermitian extend, un-normalised inverse, window, overlap-add, window-norm divide,
+ * peak-normalise to -6 dBFS.  frame_len must be fft_size/2+1, else AUS_ERR_SIZE with the reference's message.
+ * normalize == 0 skips the peak normalisation (new knob; the reference always normalises -> pass 1). */
+int aus_irstft(aus_ctx *ctx, const double *spectra, size_t n_frames, size_t frame_len, size_t fft_size, size_t hop,
+               int window_type, int precision, int normalize, double *audio /* aus_irstft_len */);
+int aus_irstft_dev(aus_ctx *ctx, const void *d_spectra, size_t n_frames, size_t fft_size, size_t hop,
+                   int window_type, int precision, int normalize, void *d_audio);
+/* spectrum/fft.rs:66 `irfft` (output is fft_size x the signal: rustfft does not normalise) */
+int aus_irfft(aus_ctx *ctx, const double *spectrum, size_t spectrum_len, size_t fft_size, int precision,
+              double *audio /* fft_size */);
+
+/* ---- synthetic input generator used by the benchmark (synthesis.rs:50-59 sine + counter noise) --- */
+int aus_synth_dev(aus_ctx *ctx, void *d_audio, uint64_t n_samples, uint64_t n0, uint32_t sample_rate, double freq,
+                  uint64_t seed, uint64_t file_id, int precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUS_B200_H */
