@@ -5,7 +5,6 @@ fleximeter/aus-rust: ``window``, ``spectrum``, ``analysis``, ``mp``), implemente
 C ABI in ``include/aus_b200.h`` (``csrc/libaus_b200.so``).  There is no CPU fallback: importing works anywhere, but
 every compute call needs the CUDA library and a B200, and fails loudly otherwise.
 """
-__package__ = "aus_rust_b200"
 
 from ._lib import AusError, SpectrumError, lib_path, load_library, FEATURE_NAMES, NUM_FEATURES  # noqa: F401
 from .api import Context, default_context, num_frames, irstft_len, batch_num_frames  # noqa: F401

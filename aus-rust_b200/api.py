@@ -107,12 +107,17 @@ class Context:
         return out
 
     def stft_features_batch(self, audio, offsets, lengths, fft_size: int, hop: int, window_type: int,
-                            sample_rate: int, precision="f64"):
+                            sample_rate: int, precision="f64", out=None):
+        """Batch of files in one launch.  ``audio`` / ``out`` may be views of pinned host memory (then the copies
+        inside the call run at full PCIe rate)."""
         a = _f64(audio)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         ln = np.ascontiguousarray(lengths, dtype=np.uint64)
         total = batch_num_frames(ln, fft_size, hop)
-        out = np.empty((total, NUM_FEATURES), dtype=np.float64)
+        if out is None:
+            out = np.empty((total, NUM_FEATURES), dtype=np.float64)
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != total * NUM_FEATURES:
+            raise ValueError("out must be a C-contiguous float64 array of total_frames x 14")
         starts = np.empty(ln.size + 1, dtype=np.uint64)
         _lib.check(self._lib.aus_stft_features_batch(self._h, _pd(a), _pu64(off), _pu64(ln), ln.size, int(fft_size),
                                                      int(hop), int(window_type), int(sample_rate), _prec(precision),

@@ -25,7 +25,10 @@ static int fail(int code, const std::string &msg) {
 #define CUDA_TRY(...)                                                                               \
     do {                                                                                            \
         cudaError_t e_ = (__VA_ARGS__);                                                             \
-        if (e_ != cudaSuccess) return fail(AUS_ERR_CUDA, std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_)); \
+        if (e_ != cudaSuccess) {                                                                    \
+            (void)cudaGetLastError(); /* un-latch, or the next launch check would report this one */ \
+            return fail(AUS_ERR_CUDA, std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_));   \
+        }                                                                                           \
     } while (0)
 #define AUS_TRY(...)                   \
     do {                               \
@@ -70,7 +73,8 @@ struct aus_ctx {
     int sm_count = 148;
     uint64_t launches = 0;
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
-    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc;
+    void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
+    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw;
 };
 
 static int log2_exact(size_t n) {
@@ -162,6 +166,22 @@ extern "C" int aus_ctx_create(int device, aus_ctx **out) {
         delete c;
         return fail(AUS_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
+    {   // log2 table: c_i = centre of the i-th mantissa interval; both columns derive from the ROUNDED 1/c_i
+        std::vector<double2> h(LOG2_TAB);
+        for (int i = 0; i < LOG2_TAB; ++i) {
+            const long double ci = 1.0L + ((long double)i + 0.5L) / (long double)LOG2_TAB;
+            const double invc = (double)(1.0L / ci);
+            h[i].x = invc;
+            h[i].y = (double)(-log2l((long double)invc));
+        }
+        e = cudaMalloc(&c->log2tab, h.size() * sizeof(double2));
+        if (e == cudaSuccess) e = cudaMemcpy(c->log2tab, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaStreamDestroy(c->stream);
+            delete c;
+            return fail(AUS_ERR_CUDA, std::string("log2 table: ") + cudaGetErrorString(e));
+        }
+    }
     *out = c;
     return AUS_OK;
 }
@@ -175,7 +195,8 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
         cudaFree(kv.second.twN);
         for (void *w : kv.second.win2) cudaFree(w);
     }
-    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc}) b->release();
+    cudaFree(c->log2tab);
+    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw}) b->release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -284,7 +305,6 @@ template <typename T> static int fill_feature_params(StftParams<T> &p, size_t N,
     p.pick[4] = (int)bf[1]; p.pick[5] = (int)bc[1];
     p.r_lo[0] = (int)ac[0]; p.r_hi[0] = (int)bf[0];
     p.r_lo[1] = (int)ac[1]; p.r_hi[1] = (int)bf[1];
-    p.bands_low = (bc[1] <= (long)(N / 4)) ? 1 : 0;
     return AUS_OK;
 }
 
@@ -311,10 +331,18 @@ template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftPar
 }
 template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
     using C = Cfg<T, LG>;
+    static bool attr_done[64] = {false};
     auto kern = analyzer_kernel<T, LG>;
-    const size_t smem = (size_t)C::FPB * C::SCR * sizeof(double);
+    const size_t smem = C::smem_bytes();
+    if (!attr_done[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 63] = true;
+    }
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+    if (occ < 1) return fail(AUS_ERR_CUDA, "analyzer kernel does not fit on an SM");
     const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
-    const unsigned long long cap = (unsigned long long)c->sm_count * 4;
+    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
     const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
     kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
@@ -369,6 +397,15 @@ template <typename A, typename B> static int cast_dev(aus_ctx *c, const A *in, B
     if (n == 0) return AUS_OK;
     const unsigned int grid = (unsigned int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 16);
     cast_kernel<A, B><<<grid, 256, 0, c->stream>>>(in, out, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+// raw per-frame sums -> 14 features, one thread per frame
+template <typename T> static int launch_finalize(aus_ctx *c, const StftParams<T> &p, size_t N) {
+    if (p.total_frames == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)((p.total_frames + 255) / 256);
+    finalize_kernel<T><<<grid, 256, 0, c->stream>>>(p, (int)(N / 2 + 1));
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return AUS_OK;
@@ -471,9 +508,17 @@ static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t
     p.win2 = (const Cx<T> *)tb->win2[wtype];
     p.twM = (const Cx<T> *)tb->twM;
     p.twN = (const Cx<T> *)tb->twN;
+    p.log2tab = (const double2 *)c->log2tab;
+    p.npass = 2;
     p.feat = d_feat;
     p.spec = d_spec;
-    return launch_stft<T>(c, lg, p);
+    if (d_feat) {
+        AUS_TRY(c->raw.ensure((size_t)b.total_frames * RAW_N * sizeof(double)));
+        p.raw = (double *)c->raw.p;
+    }
+    AUS_TRY(launch_stft<T>(c, lg, p));
+    if (d_feat) AUS_TRY(launch_finalize<T>(c, p, N));
+    return AUS_OK;
 }
 
 static int check_common(aus_ctx *c, size_t N, size_t hop, int wtype, int precision) {
@@ -615,8 +660,12 @@ template <typename T> static int analyzer_dev_t(aus_ctx *c, const T *d_mags, siz
     p.mags = d_mags;
     p.total_frames = F;
     p.feat = d_feat;
-    p.bands_low = 0;
-    return launch_analyzer<T>(c, log2_exact(N), p);
+    p.log2tab = (const double2 *)c->log2tab;
+    p.npass = 2;
+    AUS_TRY(c->raw.ensure(F * RAW_N * sizeof(double)));
+    p.raw = (double *)c->raw.p;
+    AUS_TRY(launch_analyzer<T>(c, log2_exact(N), p));
+    return launch_finalize<T>(c, p, N);
 }
 extern "C" int aus_analyzer_batch_dev(aus_ctx *c, const void *d_mags, size_t F, size_t N, uint32_t sr, int precision, void *d_feat) {
     AUS_TRY(check_common(c, N, 1, 0, precision));
@@ -655,7 +704,8 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     AUS_TRY(get_tables<T>(c, lg, wtype, &tb));
     const long long halo = (long long)((N + hop - 1) / hop) - 1;
     // segments: contiguous frame ranges, about one per resident frame group, never shorter than 4 * (halo + 1)
-    const unsigned long long groups = (unsigned long long)c->sm_count * (256 / std::max<size_t>(1, N / 64)) * (sizeof(T) == 4 ? 2 : 1);
+    const size_t tpf = std::max<size_t>(1, N / 64);
+    const unsigned long long groups = (unsigned long long)c->sm_count * (((sizeof(T) == 8 && tpf >= 16 && tpf <= 128) ? 384 : 256) / tpf) * (sizeof(T) == 4 ? 2 : 1);
     unsigned long long seglen = std::max<unsigned long long>((F + groups - 1) / groups, 4ull * (unsigned long long)(halo + 1));
     const unsigned long long nseg = std::max<unsigned long long>(1, (F + seglen / 2) / seglen);
     std::vector<unsigned long long> sfile(nseg, 0), sa(nseg), sb(nseg), first = {0ull, (unsigned long long)F}, ooff = {0ull},
@@ -686,6 +736,7 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     p.fwd.win2 = (const Cx<T> *)tb->win2[wtype];
     p.fwd.twM = (const Cx<T> *)tb->twM;
     p.fwd.twN = (const Cx<T> *)tb->twN;
+    p.fwd.npass = 2;
     AUS_TRY(launch_istft<T>(c, lg, p));
     if (apply_window && normalize) {
         const double level = std::pow(10.0, -6.0 / 20.0);                                  // fft.rs:261-262

@@ -67,6 +67,35 @@ __host__ __device__ constexpr double w32_sin(int i) {
     return t[i];
 }
 
+// FP64 twiddles live in the constant bank so DFMA/DMUL read them as c[bank][offset] operands; a 64-bit literal
+// would cost two MOVs at every use.  FP32 twiddles fit a 32-bit immediate.
+__constant__ double c_w32_cos[16] = {1.0,
+                                     0.98078528040323044912618223613424, 0.92387953251128675612818318939679,
+                                     0.83146961230254523707878837761791, 0.70710678118654752440084436210485,
+                                     0.55557023301960222474283081394853, 0.38268343236508977172845998403040,
+                                     0.19509032201612826784828486847702, 0.0,
+                                     -0.19509032201612826784828486847702, -0.38268343236508977172845998403040,
+                                     -0.55557023301960222474283081394853, -0.70710678118654752440084436210485,
+                                     -0.83146961230254523707878837761791, -0.92387953251128675612818318939679,
+                                     -0.98078528040323044912618223613424};
+__constant__ double c_w32_sin[16] = {0.0,
+                                     0.19509032201612826784828486847702, 0.38268343236508977172845998403040,
+                                     0.55557023301960222474283081394853, 0.70710678118654752440084436210485,
+                                     0.83146961230254523707878837761791, 0.92387953251128675612818318939679,
+                                     0.98078528040323044912618223613424, 1.0,
+                                     0.98078528040323044912618223613424, 0.92387953251128675612818318939679,
+                                     0.83146961230254523707878837761791, 0.70710678118654752440084436210485,
+                                     0.55557023301960222474283081394853, 0.38268343236508977172845998403040,
+                                     0.19509032201612826784828486847702};
+template <typename T, int IDX> __device__ __forceinline__ T tw32_cos() {
+    if constexpr (sizeof(T) == 8) return c_w32_cos[IDX];
+    else { constexpr T c = (T)w32_cos(IDX); return c; }
+}
+template <typename T, int IDX> __device__ __forceinline__ T tw32_sin() {
+    if constexpr (sizeof(T) == 8) return c_w32_sin[IDX];
+    else { constexpr T c = (T)w32_sin(IDX); return c; }
+}
+
 // ------------------------------------------------------------------------------------------------ radix-R DFT
 // Forward DFT (sign -1) of v[0..R) held in registers: decimation-in-frequency radix-2 network, fully unrolled.
 // The result is left in bit-reversed order: natural output q is v[bitrev(q, log2 R)].  All indices are
@@ -90,7 +119,7 @@ template <int R, typename T> __device__ __forceinline__ void dft_dif(Cx<T> (&v)[
                 } else if constexpr (idx == 8) {              // multiply by -i
                     v[blk + k + half] = Cx<T>{d.y, -d.x};
                 } else {
-                    constexpr T c = (T)w32_cos(idx), sn = (T)w32_sin(idx);
+                    const T c = tw32_cos<T, idx>(), sn = tw32_sin<T, idx>();
                     v[blk + k + half] = Cx<T>{d.x * c + d.y * sn, d.y * c - d.x * sn};   // d * (c - i s)
                 }
             });
@@ -204,14 +233,72 @@ __device__ __forceinline__ void group_inclusive_scan2(double &a, double &b, doub
 }
 
 // ------------------------------------------------------------------------------------------------ math traits
+// The f64 feature pass needs one sqrt and one log2 per bin at ~1e-12 relative accuracy (tolerance 1e-9), not the
+// ~45 FP64 instructions each of the correctly rounded library versions.
+//   sqrt:  y0 = rsqrt.approx (MUFU.RSQ64H, ~2^-20), one Newton step -> ~1e-12; 4 FP64 ops.
+//   log2:  x = 2^e z, z in [1,2); 128-entry table of (1/c_i, -log2(1/c_i)) on the top 7 mantissa bits,
+//          r = z/c_i - 1 (|r| < 2^-8), degree-5 Taylor of log2(1+r) (|err| < 1e-15); 7 FP64 ops.
+// Zero, subnormal, negative, inf and NaN arguments take the library function (out of line, rare).
+constexpr int LOG2_TAB = 128;
+
+// true for +0, subnormals, negatives, inf and NaN: the arguments the fast paths below do not handle
+__device__ __forceinline__ bool abnormal(double x) { return (unsigned)__double2hiint(x) - 0x00100000u >= 0x7fe00000u; }
+__device__ __forceinline__ bool abnormal(float) { return false; }
+
 template <typename T> struct Mth;
 template <> struct Mth<double> {
-    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
-    static __device__ __forceinline__ double log2_(double x) { return log2(x); }
+    static __device__ __forceinline__ double sqrt_exact(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double log2_exact(double x) { return log2(x); }
+    // positive normal x only (see abnormal())
+    static __device__ __forceinline__ double sqrt_(double x) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        const double h = x * y;
+        const double r = fma(-h, y, 1.0);
+        return fma(h * 0.5, r, h);
+    }
+    static __device__ __forceinline__ double log2_(double x, const double2 *tab) {
+        const unsigned hi = (unsigned)__double2hiint(x);
+        const double2 tc = tab[(hi >> 13) & (LOG2_TAB - 1)];
+        const double z = __hiloint2double((int)((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
+        // exponent as a double without an I2F: 2^52 + 2^31 + (e ^ 0x80000000) trick
+        const double ed = __hiloint2double(0x43300000, (int)(((hi >> 20) - 1023u) ^ 0x80000000u)) - 4503601774854144.0;
+        const double r = fma(z, tc.x, -1.0);
+        double pl = fma(r, 0.28853900817779268147, -0.36067376022224085184);   // 1/(5 ln2), -1/(4 ln2)
+        pl = fma(pl, r, 0.48089834696298780245);                                // 1/(3 ln2)
+        pl = fma(pl, r, -0.72134752044448170368);                               // -1/(2 ln2)
+        pl = fma(pl, r, 1.44269504088896340736);                                // 1/ln2
+        return fma(pl, r, ed + tc.y);
+    }
 };
 template <> struct Mth<float> {
+    static __device__ __forceinline__ float sqrt_exact(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float log2_exact(float x) { return log2f(x); }
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-    static __device__ __forceinline__ float log2_(float x) { return log2f(x); }
+    static __device__ __forceinline__ float log2_(float x, const double2 *) { return log2f(x); }
 };
+
+// any-of over the TPF threads of a frame group (warp vote; cross-warp through shared scratch)
+template <int TPF, int BLOCK>
+__device__ __forceinline__ bool group_any(bool pred, double *scratch, int t, int grp) {
+    if constexpr (TPF >= 32) {
+        bool w = __any_sync(0xffffffffu, pred);
+        if constexpr (TPF > 32) {
+            int *flag = reinterpret_cast<int *>(scratch);
+            if (t == 0) *flag = 0;
+            group_sync<TPF, BLOCK>(grp);
+            if (w && (t & 31) == 0) *flag = 1;
+            group_sync<TPF, BLOCK>(grp);
+            w = *flag != 0;
+            group_sync<TPF, BLOCK>(grp);
+        }
+        return w;
+    } else {
+        const unsigned b = __ballot_sync(0xffffffffu, pred);
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned m = ((TPF == 32 ? 0xffffffffu : ((1u << TPF) - 1u))) << (lane & ~(unsigned)(TPF - 1));
+        return (b & m) != 0;
+    }
+}
 
 }  // namespace aus

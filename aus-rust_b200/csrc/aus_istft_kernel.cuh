@@ -32,14 +32,13 @@ template <typename T> struct IstftParams {
 };
 
 template <typename T, int LOG2N>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) istft_kernel(const IstftParams<T> p) {
+__global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) istft_kernel(const IstftParams<T> p) {
     using C = Cfg<T, LOG2N>;
     constexpr int N = C::N, M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
     Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FPB * C::BUF * sizeof(Cx<T>) +
-                                                 (size_t)FPB * C::SCR * sizeof(double)) + grp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + C::off_bar()) + grp;
     if (t == 0) mbar_init(bar, 1);
     fence_mbar_init();
     __syncthreads();

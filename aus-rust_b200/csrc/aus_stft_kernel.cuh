@@ -8,8 +8,13 @@
 // P = 32 complex points in registers.  The N-point real transform is an M = N/2 point complex Stockham FFT of
 // z[n] = x[2n] + i x[2n+1] with radices {TPF, 32} (M <= 1024) or {32, 32, M/1024} (M > 1024), followed by the
 // real-to-complex post-twiddle fused into the feature pass.  One shared-memory buffer of M(+pad) complex per
-// group is the TMA landing zone for the frame's samples and then the exchange space between passes; spectra
-// never touch HBM unless the caller asks for them.
+// group is the TMA landing zone for the frame's samples, then the exchange space between passes, then the home
+// of the power spectrum and its running sum during the feature passes; spectra never touch HBM unless the
+// caller asks for them.
+//
+// Code-size discipline matters as much as FLOPs here: the kernel is instruction-issue bound, so the two radix-32
+// passes share ONE butterfly body (a rolled 2-trip loop with linear address generators) and the per-bin feature
+// loops are rolled, keeping the hot loop inside the instruction cache.
 #pragma once
 #include "aus_device.cuh"
 
@@ -23,15 +28,18 @@ template <typename T, int LOG2N> struct Cfg {
     static constexpr bool THREE = (M > 1024);
     static constexpr int R1 = THREE ? 32 : TPF;              // first radix (TPF == 1: single radix-32 pass)
     static constexpr int R3 = THREE ? M / 1024 : 1;
-    static constexpr int BLOCK = 256;
+    // f64: 12 warps x 168 registers per SM (3 per scheduler) when the group buffers fit; f32: 2 CTAs x 8 warps x 128 regs
+    static constexpr int BLOCK = (sizeof(T) == 8 && TPF >= 16 && TPF <= 128) ? 384 : 256;
+    static constexpr int MINB = (sizeof(T) == 4) ? 2 : 1;
     static constexpr int FPB = BLOCK / TPF;                  // frame groups per CTA
     static constexpr int XS = (R1 >= 16) ? ilog2(R1) : 5;    // exchange-layout pad shift
-    static constexpr int BUF = M + M / 16 + 8;               // complex elements per group buffer (max pad M/16)
+    static constexpr int BUF = M + M / 16 + 2;               // complex elements per group buffer: slots 0 .. zslot(M), even
     static constexpr int NW = TPF > 32 ? TPF / 32 : 1;
-    static constexpr int SCR = 16 * NW + 8;                  // doubles of reduction scratch per group (+6 picks)
-    static constexpr size_t smem_bytes() {
-        return (size_t)FPB * BUF * sizeof(Cx<T>) + (size_t)FPB * SCR * sizeof(double) + (size_t)FPB * sizeof(uint64_t);
-    }
+    static constexpr int SCR = TPF > 32 ? 16 * NW : 2;       // doubles of cross-warp reduction scratch per group
+    __host__ __device__ static constexpr size_t off_scratch() { return (size_t)FPB * BUF * sizeof(Cx<T>); }
+    __host__ __device__ static constexpr size_t off_bar() { return off_scratch() + (size_t)FPB * SCR * sizeof(double); }
+    __host__ __device__ static constexpr size_t off_log() { return (off_bar() + (size_t)FPB * sizeof(uint64_t) + 15) & ~(size_t)15; }
+    __host__ __device__ static constexpr size_t smem_bytes() { return off_log() + LOG2_TAB * sizeof(double2); }
     static_assert(LOG2N >= 6 && LOG2N <= 14, "fft_size must be 64..16384");
 };
 
@@ -47,23 +55,29 @@ template <typename T> struct StftParams {
     int hop;
     int wtype;
     int tma_ok;                        // audio base is 16-byte aligned
+    int npass;                         // always 2; a runtime value so the shared radix-32 body stays one rolled loop
     const Cx<T> *win2;                 // [M] (0.5 w[2n], 0.5 w[2n+1]) -- the 1/2 of the real-FFT split is folded in
     const Cx<T> *twM;                  // [M] exp(-2 pi i k / M)
     const Cx<T> *twN;                  // [M/2 + 1] (cos, sin)(2 pi k / N)
-    T *feat;                           // [frames][14] or nullptr
+    const double2 *log2tab;            // [LOG2_TAB] (1/c_i, -log2(1/c_i))
+    double *raw;                       // [frames][RAW_N] per-frame sums for finalize_kernel, or nullptr (no features)
+    T *feat;                           // [frames][14] (written by finalize_kernel)
     Cx<T> *spec;                       // [frames][K] or nullptr
     double f0;                         // sample_rate / fft_size   (fft_tools.rs:201)
     double slope_sx, slope_den;        // n(n-1)/2 and n*Sxx - Sx^2 with n = K (spectral_analysis_tools.rs:177-180)
-    int pick[6];                       // bins a1-, a1+, b1- (= a2-), b1+ (= a2+), b2-, b2+ (…:198-201)
+    int pick[6];                       // bins a1-, a1+, b1- (= a2-), b1+ (= a2+), b2-, b2+ (s_a_t.rs:198-201)
     int r_lo[2], r_hi[2];              // half-open bin ranges [ceil(m_fl), floor(m_fu)) of bands 1 and 2
     double band_fl[3], band_fu[3];     // Hz
     double band_tl[3], band_tu[3];     // fractional parts m_fl - floor(m_fl), m_fu - floor(m_fu)
     double band_sx[3], band_den[3];    // sum_x and n*sum_x2 - sum_x^2 (host, reference summation order)
-    int bands_low;                     // all band bins <= M/2 (skip band tests on the mirrored half)
 };
 
+// layout of one raw record (doubles): everything finalize_kernel needs to produce the 14 features of a frame
+enum RawIdx { RAW_SM = 0, RAW_SMK, RAW_SPK, RAW_B1P, RAW_B1PK, RAW_B2P, RAW_B2PK, RAW_P, RAW_D2, RAW_D3, RAW_D4,
+              RAW_ENT, RAW_SLQ, RAW_ROLL0, RAW_ROLL1, RAW_ROLL2, RAW_ROLL3, RAW_PICK0, RAW_N = RAW_PICK0 + 6 };
+
 // window.rs:26-98 evaluated for one index (used only for the short last frame of a file, fft.rs:148-159)
-__device__ __forceinline__ double window_value(int wtype, double i, double L) {
+__device__ __noinline__ double window_value(int wtype, double i, double L) {
     const double PI = 3.14159265358979323846264338327950288;
     switch (wtype) {
     case 0: return (2.0 / (L - 1.0)) * ((L - 1.0) / 2.0 - fabs(i - (L - 1.0) / 2.0));
@@ -99,8 +113,59 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
         });
         group_sync<TPF, C::BLOCK>(grp);
         return;
+    } else if constexpr (R1 == 32) {
+        // ---- passes 1 and 2 are both radix 32 with one butterfly per thread (j = t): one rolled loop whose
+        //      loads / table reads / stores are linear in r:  address = base + r * stride.
+        //      pass 1 (Ns = 1):  in  = buf[j + r TPF] (raw samples)   x win2[j + r TPF]      out = X[33 j + r]
+        //      pass 2 (Ns = 32): in  = X[pad5(j + r TPF)]             x twM[jm r]            out = Z or X layout
+        const int j = t;
+        int lbase = j, lstride = TPF;
+        const Cx<T> *tab = p.win2 + j;
+        int tstride = TPF;
+        int sbase = 33 * j, sstride = 1;
+#pragma unroll 1
+        for (int pass = 0; pass < p.npass; ++pass) {
+            if (pass == 0) {
+                if (prewindowed) {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = buf[lbase + r * lstride];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const Cx<T> z = buf[lbase + r * lstride];
+                        const Cx<T> w = ldg_cx(tab + r * tstride);
+                        v[r] = Cx<T>{z.x * w.x, z.y * w.y};
+                    }
+                }
+            } else {
+                v[0] = buf[lbase];
+#pragma unroll
+                for (int r = 1; r < 32; ++r) v[r] = cmul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
+            }
+            group_sync<TPF, C::BLOCK>(grp);                   // every load done before buf is overwritten
+            dft_dif<32>(v);
+            static_for<0, 32>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                buf[sbase + r * sstride] = v[bitrev(r, 5)];
+            });
+            group_sync<TPF, C::BLOCK>(grp);
+            // address generators of pass 2
+            lbase = j + (j >> 5);
+            lstride = TPF + TPF / 32;
+            tab = p.twM;
+            if constexpr (!C::THREE) {
+                tstride = j;                                   // W_M^(j r)
+                sbase = j + (j >> 4);                          // Z layout: pad4(j + 32 r) = j + (j >> 4) + 34 r
+                sstride = 34;
+            } else {
+                tstride = (j & 31) * R3;                       // W_M^((j mod 32) R3 r)
+                const int b = (j >> 5) * 1024 + (j & 31);      // exchange layout: pad5(b + 32 r) = b + (b >> 5) + 33 r
+                sbase = b + (b >> 5);
+                sstride = 33;
+            }
+        }
     } else {
-        // ---- pass 1: radix R1, Ns = 1, B1 = 32 / R1 butterflies per thread, input = windowed samples
+        // ---- pass 1: radix R1 < 32, Ns = 1, B1 = 32 / R1 butterflies per thread, input = windowed samples
         constexpr int B1 = 32 / R1;
         static_for<0, B1>([&](auto b_) {
             constexpr int b = decltype(b_)::value;
@@ -113,7 +178,7 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
                 v[b * R1 + r] = z;
             });
         });
-        group_sync<TPF, C::BLOCK>(grp);                       // every load done before buf is overwritten
+        group_sync<TPF, C::BLOCK>(grp);
         static_for<0, B1>([&](auto b_) {
             constexpr int b = decltype(b_)::value;
             const int j = t + TPF * b;
@@ -126,61 +191,51 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
             });
         });
         group_sync<TPF, C::BLOCK>(grp);
-
-        // ---- pass 2: radix 32, Ns = R1, one butterfly per thread (j = t)
+        // ---- pass 2: radix 32, Ns = R1 = TPF, one butterfly per thread (j = t), natural-order output
         {
             const int j = t;
-            const int jm = C::THREE ? (j & 31) * R3 : j;      // twiddle exponent step: W_M^(jm * r)
             static_for<0, 32>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
                 Cx<T> z = buf[padi<XS>(j + r * TPF)];
-                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.twM[jm * r]));
+                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.twM[j * r]));
                 v[r] = z;
             });
             group_sync<TPF, C::BLOCK>(grp);
             dft_dif<32>(v);
-            if constexpr (!C::THREE) {
-                static_for<0, 32>([&](auto r_) {
-                    constexpr int r = decltype(r_)::value;
-                    buf[padi<4>(j + r * TPF)] = v[bitrev(r, 5)];      // natural order k = j + r * R1
-                });
-            } else {
-                const int base = (j >> 5) * 1024 + (j & 31);
-                static_for<0, 32>([&](auto r_) {
-                    constexpr int r = decltype(r_)::value;
-                    buf[padi<XS>(base + r * 32)] = v[bitrev(r, 5)];
-                });
-            }
+            static_for<0, 32>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                buf[padi<4>(j + r * TPF)] = v[bitrev(r, 5)];
+            });
             group_sync<TPF, C::BLOCK>(grp);
         }
+    }
 
-        // ---- pass 3 (M > 1024): radix R3, Ns = 1024, B3 = 32 / R3 butterflies per thread
-        if constexpr (C::THREE) {
-            constexpr int B3 = 32 / R3;
-            static_for<0, B3>([&](auto b_) {
-                constexpr int b = decltype(b_)::value;
-                const int j = t + TPF * b;
-                static_for<0, R3>([&](auto r_) {
-                    constexpr int r = decltype(r_)::value;
-                    Cx<T> z = buf[padi<XS>(j + r * 1024)];
-                    if constexpr (r > 0) z = cmul(z, ldg_cx(&p.twM[j * r]));
-                    v[b * R3 + r] = z;
-                });
+    // ---- pass 3 (M > 1024): radix R3, Ns = 1024, B3 = 32 / R3 butterflies per thread
+    if constexpr (C::THREE) {
+        constexpr int B3 = 32 / R3;
+        static_for<0, B3>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            const int j = t + TPF * b;
+            static_for<0, R3>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                Cx<T> z = buf[padi<XS>(j + r * 1024)];
+                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.twM[j * r]));
+                v[b * R3 + r] = z;
             });
-            group_sync<TPF, C::BLOCK>(grp);
-            static_for<0, B3>([&](auto b_) {
-                constexpr int b = decltype(b_)::value;
-                const int j = t + TPF * b;
-                Cx<T> u[R3];
-                static_for<0, R3>([&](auto r_) { u[decltype(r_)::value] = v[b * R3 + decltype(r_)::value]; });
-                dft_dif<R3>(u);
-                static_for<0, R3>([&](auto r_) {
-                    constexpr int r = decltype(r_)::value;
-                    buf[padi<4>(j + r * 1024)] = u[bitrev(r, ilog2(R3))];
-                });
+        });
+        group_sync<TPF, C::BLOCK>(grp);
+        static_for<0, B3>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            const int j = t + TPF * b;
+            Cx<T> u[R3];
+            static_for<0, R3>([&](auto r_) { u[decltype(r_)::value] = v[b * R3 + decltype(r_)::value]; });
+            dft_dif<R3>(u);
+            static_for<0, R3>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                buf[padi<4>(j + r * 1024)] = u[bitrev(r, ilog2(R3))];
             });
-            group_sync<TPF, C::BLOCK>(grp);
-        }
+        });
+        group_sync<TPF, C::BLOCK>(grp);
     }
 }
 
@@ -195,150 +250,210 @@ __device__ __forceinline__ void post_twiddle(Cx<T> A, Cx<T> B, Cx<T> W, Cx<T> &X
     Xhi = Cx<T>{ex - tx, ty - ey};                   // conj(E - T)
 }
 
-// Per-thread running sums of the feature pass (arithmetic type T; cross-thread combination is always double).
+// Per-thread running sums of the first feature pass (arithmetic type T; cross-thread combination is always double).
 template <typename T> struct FeatAcc {
-    T s_m = 0, s_mk = 0, s_pk = 0, s_l = 0, s_pl = 0;
-    T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
-    template <bool BANDS>
-    __device__ __forceinline__ void add(int k, T m, T pw, const int (&rlo)[2], const int (&rhi)[2]) {
-        const T kf = (T)k;
+    T s_m = 0, s_mk = 0, s_pk = 0, lo_sum = 0, hi_sum = 0, mid = 0;
+    bool bad = false;                                 // some bin is zero / subnormal / non-finite: redo sqrt exactly
+    __device__ __forceinline__ void add(T kf, T m, T pw) {
         s_m += m;
         s_mk += m * kf;
-        const T pk = pw * kf;
-        s_pk += pk;
-        const T l = Mth<T>::log2_(pw);
-        s_l += l;
-        s_pl += pw * l;                               // 0 * -inf = NaN, like pmf * log2(pmf) in the reference
-        if constexpr (BANDS) {
-            if (k >= rlo[0] && k < rhi[0]) { b1p += pw; b1pk += pk; }
-            if (k >= rlo[1] && k < rhi[1]) { b2p += pw; b2pk += pk; }
-        }
+        s_pk += pw * kf;
     }
 };
 
+// Slot of bin b in the group buffer ("Z layout").
+__device__ __forceinline__ int zslot(int b) { return b + (b >> 4); }
+
 // ---------------------------------------------------------------------------------------------------------
-// Feature pass over one frame.  Thread t owns the pairs k in [16 t, 16 t + 16): bins k ("low") and M - k ("high"),
-// thread 0 additionally DC / Nyquist (pair 0), the last thread bin M/2.  plo/phi/pmid hold the power of those bins.
+// Feature passes over one frame.  On entry slot(b).x = |X[b]|^2 for every bin b = 0..M (written by the owning
+// threads, not yet synchronised).  Thread t owns the bins [16 t, 16 t + 16) ("low") and (M - 16 t - 16, M - 16 t]
+// ("high"); the last thread also owns bin M/2.  Writes the frame's raw record; finalize_kernel turns it into the 14
+// features (one thread per frame, so the scalar divisions / exp / log run SIMD-efficiently).
 template <typename T, int LOG2N>
-__device__ __forceinline__ void frame_features(const T (&plo)[16], const T (&phi)[16], T pmid, const FeatAcc<T> &acc,
-                                               const T *picks_smem, double *scratch, const StftParams<T> &p,
-                                               unsigned long long g, bool active, int t, int grp) {
+__device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, double *scratch, const double2 *logtab,
+                                               const StftParams<T> &p, unsigned long long g, bool active, int t,
+                                               int grp) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, K = C::K, TPF = C::TPF;
+    const int hb = M - 16 * t - 15;                   // first (lowest) bin of this thread's high chunk
 
-    T lo_sum = 0, hi_sum = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { lo_sum += plo[i]; hi_sum += phi[i]; }
+    // a zero / subnormal / non-finite power bin somewhere in the frame: redo the magnitude sums with the exact sqrt
+    if (group_any<TPF, C::BLOCK>(acc.bad, scratch, t, grp)) {
+        acc.s_m = 0;
+        acc.s_mk = 0;
+#pragma unroll 1
+        for (int u = 0; u < 33; ++u) {
+            const int b = u < 16 ? 16 * t + u : (u < 32 ? hb + (u - 16) : M / 2);
+            if (u == 32 && t != TPF - 1) break;
+            const T m = Mth<T>::sqrt_exact(buf[zslot(b)].x);
+            acc.s_m += m;
+            acc.s_mk += m * (T)b;
+        }
+    }
+    group_sync<TPF, C::BLOCK>(grp);                   // every power bin visible to the whole group
 
-    double r[12] = {(double)acc.s_m, (double)acc.s_mk, (double)acc.s_pk, (double)acc.s_l, (double)acc.s_pl,
-                    (double)acc.b1p, (double)acc.b1pk, (double)acc.b2p, (double)acc.b2pk,
-                    (double)lo_sum, (double)hi_sum, (double)pmid};
-    group_allreduce<TPF, C::BLOCK, 12>(r, scratch, t, grp);
-    const double S_m = r[0], S_mk = r[1], S_pk = r[2], S_l = r[3], S_pl = r[4];
-    const double tot_lo = r[9], tot_hi = r[10], tot_mid = r[11];
+    // sub-band sums for the three slope regions (s_a_t.rs:190-230): bins [r_lo, r_hi) of bands 1 and 2, all threads
+    T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
+#pragma unroll 1
+    for (int b = p.r_lo[0] + t; b < p.r_hi[1]; b += TPF) {
+        const T pw = buf[zslot(b)].x;
+        const T pk = pw * (T)b;
+        if (b < p.r_hi[0]) { b1p += pw; b1pk += pk; }
+        if (b >= p.r_lo[1]) { b2p += pw; b2pk += pk; }
+    }
+
+    double r[10] = {(double)acc.s_m, (double)acc.s_mk, (double)acc.s_pk, (double)b1p, (double)b1pk, (double)b2p,
+                    (double)b2pk, (double)acc.lo_sum, (double)acc.hi_sum, (double)acc.mid};
+    group_allreduce<TPF, C::BLOCK, 10>(r, scratch, t, grp);
+    const double S_m = r[0], S_mk = r[1];
+    const double tot_lo = r[7], tot_hi = r[8], tot_mid = r[9];
     const double P = tot_lo + tot_mid + tot_hi;
 
     // prefix of the power spectrum in bin order: low chunks ascending t, bin M/2, high chunks descending t
-    double inc_lo = (double)lo_sum, inc_hi = (double)hi_sum;
+    double inc_lo = (double)acc.lo_sum, inc_hi = (double)acc.hi_sum;
     group_inclusive_scan2<TPF, C::BLOCK>(inc_lo, inc_hi, scratch, t, grp);
-    const T base_lo = (T)(inc_lo - (double)lo_sum);
+    const T base_lo = (T)(inc_lo - (double)acc.lo_sum);
     const T base_hi = (T)(tot_lo + tot_mid + (tot_hi - inc_hi));
 
-    // second pass: central moments about the (magnitude-weighted) centroid, in units of bins, and the
-    // roll-off counts: index = number of bins whose inclusive cumulative power is still below theta * P
+    // central moments about the (magnitude-weighted) centroid, in units of bins; entropy and log-mean from
+    // q = p / P (a nearly pure tone keeps full relative accuracy, like the reference's pmf); running sum -> slot.y
     const T kappa = (T)(S_mk / S_m);
-    const T th0 = (T)(0.5 * P), th1 = (T)(0.75 * P), th2 = (T)(0.9 * P), th3 = (T)(0.95 * P);
-    T d2s = 0, d3s = 0, d4s = 0;
-    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    auto moment = [&](int k, T pw) {
-        const T d = (T)k - kappa;
+    const T inv_p = (T)(1.0 / P);
+    T d2s = 0, d3s = 0, d4s = 0, ent = 0, slq = 0;
+    bool badq = false;
+    auto bin = [&](int b, T d, T &cum) {
+        Cx<T> *s = buf + zslot(b);
+        const T pw = s->x;
         const T dd = d * d;
         const T w2 = dd * pw;
         d2s += w2;
         d3s += w2 * d;
         d4s += w2 * dd;
-    };
-    auto count = [&](T cum) {
-        c0 += (cum < th0) ? 1 : 0;
-        c1 += (cum < th1) ? 1 : 0;
-        c2 += (cum < th2) ? 1 : 0;
-        c3 += (cum < th3) ? 1 : 0;
+        const T q = pw * inv_p;                       // make_spectrum_pmf, s_a_t.rs:284-290
+        badq |= abnormal(q);
+        const T l = Mth<T>::log2_(q, logtab);
+        ent += q * l;
+        slq += l;
+        cum += pw;
+        s->y = cum;
     };
     {
         T cum = base_lo;
-#pragma unroll
+        T d = (T)(16 * t) - kappa;
+#pragma unroll 2
         for (int i = 0; i < 16; ++i) {
-            moment(16 * t + i, plo[i]);
-            cum += plo[i];
-            count(cum);
-        }
-        if (t == TPF - 1) {
-            moment(M / 2, pmid);
-            count((T)(tot_lo + (double)pmid));
+            bin(16 * t + i, d, cum);
+            if constexpr (sizeof(T) == 8) d += (T)1; else d = (T)(16 * t + i + 1) - kappa;   // f64: no I2F per bin
         }
         cum = base_hi;
-#pragma unroll
-        for (int i = 15; i >= 0; --i) {
-            moment(M - 16 * t - i, phi[i]);
-            cum += phi[i];
-            count(cum);
+        d = (T)hb - kappa;
+#pragma unroll 2
+        for (int u = 0; u < 16; ++u) {
+            bin(hb + u, d, cum);
+            if constexpr (sizeof(T) == 8) d += (T)1; else d = (T)(hb + u + 1) - kappa;
+        }
+        if (t == TPF - 1) {
+            T cum_mid = (T)tot_lo;
+            bin(M / 2, (T)(M / 2) - kappa, cum_mid);
         }
     }
-    double q[5] = {(double)d2s, (double)d3s, (double)d4s,
-                   (double)(c0 + (c1 << 16)), (double)(c2 + (c3 << 16))};      // counts <= 8193 each: exact in f64
-    group_allreduce<TPF, C::BLOCK, 5>(q, scratch, t, grp);
+    // zero / subnormal / non-finite q somewhere: redo the two log sums with the library log2 (0 * -inf = NaN and
+    // sum = -inf exactly like pmf * log2(pmf) and ln(m) in the reference, s_a_t.rs:93-114)
+    if (group_any<TPF, C::BLOCK>(badq, scratch, t, grp)) {
+        ent = 0;
+        slq = 0;
+#pragma unroll 1
+        for (int u = 0; u < 33; ++u) {
+            const int b = u < 16 ? 16 * t + u : (u < 32 ? hb + (u - 16) : M / 2);
+            if (u == 32 && t != TPF - 1) break;
+            const T q = buf[zslot(b)].x * inv_p;
+            const T l = Mth<T>::log2_exact(q);
+            ent += q * l;
+            slq += l;
+        }
+    }
+    double q[5] = {(double)d2s, (double)d3s, (double)d4s, (double)ent, (double)slq};
+    group_allreduce<TPF, C::BLOCK, 5>(q, scratch, t, grp);      // (its barriers also publish every slot.y)
+    if constexpr (TPF <= 32) __syncwarp();
 
-    if (t == 0 && active && p.feat != nullptr) {
-        const double f0 = p.f0, n = (double)K;
-        const double var = f0 * f0 * (q[0] / P);
-        const unsigned int cnta = (unsigned int)q[3], cntb = (unsigned int)q[4];
-        const int i50 = (int)(cnta & 0xffffu), i75 = (int)(cnta >> 16);
-        const int i90 = (int)(cntb & 0xffffu), i95 = (int)(cntb >> 16);
-        double out[14];
-        out[0] = f0 * S_mk / S_m;                                                // centroid, s_a_t.rs:79-85
-        out[1] = var;                                                            // :238-244
-        out[2] = (f0 * f0 * f0 * (q[1] / P)) / (var * sqrt(var));                // :153-160  (var^1.5)
-        out[3] = (f0 * f0 * f0 * f0 * (q[2] / P)) / (var * var);                 // :122-129
-        out[4] = -(S_pl / P - log2(P));                                          // :93-99   -sum q log2 q
-        out[5] = exp(0.5 * 0.69314718055994530942 * S_l / n) * n / S_m;          // :107-114 (ln m = ln2/2 * log2 p)
-        out[6] = f0 * (double)min(i50, K - 1);                                   // :137-145
-        out[7] = f0 * (double)min(i75, K - 1);
-        out[8] = f0 * (double)min(i90, K - 1);
-        out[9] = f0 * (double)min(i95, K - 1);
-        out[10] = (n * S_pk - p.slope_sx * P) / p.slope_den;                     // :167-182
-        const double pk0 = (double)picks_smem[0], pk1 = (double)picks_smem[1], pk2 = (double)picks_smem[2];
-        const double pk3 = (double)picks_smem[3], pk4 = (double)picks_smem[4], pk5 = (double)picks_smem[5];
-        const bool gap = p.pick[2] < p.pick[3];            // bin floor(m) sits between bands 1 and 2
-        const double bp[3] = {r[5], r[7], r[5] + r[7] + (gap ? pk2 : 0.0)};
-        const double bpk[3] = {r[6], r[8], r[6] + r[8] + (gap ? pk2 * (double)p.pick[2] : 0.0)};
-        const double pal[3] = {pk0, pk2, pk0}, pah[3] = {pk1, pk3, pk1};
-        const double pbl[3] = {pk2, pk4, pk4}, pbh[3] = {pk3, pk5, pk5};
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {                                            // :190-230
-            const double yl = pal[b] + p.band_tl[b] * (pah[b] - pal[b]);
-            const double yu = pbl[b] + p.band_tu[b] * (pbh[b] - pbl[b]);
-            const double sum_y = yl + bp[b] + yu;
-            const double sum_xy = p.band_fl[b] * yl + f0 * bpk[b] + p.band_fu[b] * yu;
-            out[11 + b] = (n * sum_xy - p.band_sx[b] * sum_y) / p.band_den[b];
+    if (active && p.raw != nullptr) {
+        double *rec = p.raw + g * (unsigned long long)RAW_N;
+        // roll-off (s_a_t.rs:137-145): index = number of bins whose inclusive cumulative power is below theta * P.
+        // The running sums in slot.y are monotone over b = 0..M: one binary search per threshold, one thread each.
+#pragma unroll 1
+        for (int qq = t; qq < 4; qq += TPF) {
+            const T th = (T)((qq == 0 ? 0.5 : qq == 1 ? 0.75 : qq == 2 ? 0.9 : 0.95) * P);
+            int lo = 0, hi = K;                        // first index in [0, K] whose running sum is not below th
+#pragma unroll 1
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (buf[zslot(mid)].y < th) lo = mid + 1; else hi = mid;
+            }
+            rec[RAW_ROLL0 + qq] = (double)lo;
         }
-        T *dst = p.feat + g * 14;
-#pragma unroll
-        for (int i = 0; i < 14; ++i) dst[i] = (T)out[i];
+#pragma unroll 1
+        for (int qq = t; qq < 6; qq += TPF) rec[RAW_PICK0 + qq] = (double)buf[zslot(p.pick[qq])].x;
+        if (t == 0) {
+            rec[RAW_SM] = r[0]; rec[RAW_SMK] = r[1]; rec[RAW_SPK] = r[2];
+            rec[RAW_B1P] = r[3]; rec[RAW_B1PK] = r[4]; rec[RAW_B2P] = r[5]; rec[RAW_B2PK] = r[6];
+            rec[RAW_P] = P;
+            rec[RAW_D2] = q[0]; rec[RAW_D3] = q[1]; rec[RAW_D4] = q[2]; rec[RAW_ENT] = q[3]; rec[RAW_SLQ] = q[4];
+        }
     }
+}
+
+// One thread per frame: raw record -> the 14 features in the declaration order of analyzer.rs:10-23.
+template <typename T>
+__global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, int K) {
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.total_frames) return;
+    const double *rec = p.raw + g * (unsigned long long)RAW_N;
+    const double f0 = p.f0, n = (double)K;
+    const double S_m = rec[RAW_SM], S_mk = rec[RAW_SMK], S_pk = rec[RAW_SPK], P = rec[RAW_P];
+    const double var = f0 * f0 * (rec[RAW_D2] / P);
+    double out[14];
+    out[0] = f0 * S_mk / S_m;                                                    // centroid, s_a_t.rs:79-85
+    out[1] = var;                                                                // :238-244
+    out[2] = (f0 * f0 * f0 * (rec[RAW_D3] / P)) / (var * sqrt(var));             // :153-160  (var^1.5)
+    out[3] = (f0 * f0 * f0 * f0 * (rec[RAW_D4] / P)) / (var * var);              // :122-129
+    out[4] = -rec[RAW_ENT];                                                      // :93-99   -sum q log2 q
+    out[5] = exp(0.5 * 0.69314718055994530942 * (rec[RAW_SLQ] / n + log2(P))) * n / S_m;   // :107-114
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[6 + i] = f0 * fmin(rec[RAW_ROLL0 + i], n - 1.0);       // :137-145
+    out[10] = (n * S_pk - p.slope_sx * P) / p.slope_den;                         // :167-182
+    const double pk0 = rec[RAW_PICK0], pk1 = rec[RAW_PICK0 + 1], pk2 = rec[RAW_PICK0 + 2];
+    const double pk3 = rec[RAW_PICK0 + 3], pk4 = rec[RAW_PICK0 + 4], pk5 = rec[RAW_PICK0 + 5];
+    const bool gap = p.pick[2] < p.pick[3];                // bin floor(m) sits between bands 1 and 2
+    const double b1p = rec[RAW_B1P], b1pk = rec[RAW_B1PK], b2p = rec[RAW_B2P], b2pk = rec[RAW_B2PK];
+    const double bp[3] = {b1p, b2p, b1p + b2p + (gap ? pk2 : 0.0)};
+    const double bpk[3] = {b1pk, b2pk, b1pk + b2pk + (gap ? pk2 * (double)p.pick[2] : 0.0)};
+    const double pal[3] = {pk0, pk2, pk0}, pah[3] = {pk1, pk3, pk1};
+    const double pbl[3] = {pk2, pk4, pk4}, pbh[3] = {pk3, pk5, pk5};
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {                                                // :190-230
+        const double yl = pal[b] + p.band_tl[b] * (pah[b] - pal[b]);
+        const double yu = pbl[b] + p.band_tu[b] * (pbh[b] - pbl[b]);
+        const double sum_y = yl + bp[b] + yu;
+        const double sum_xy = p.band_fl[b] * yl + f0 * bpk[b] + p.band_fu[b] * yu;
+        out[11 + b] = (n * sum_xy - p.band_sx[b] * sum_y) / p.band_den[b];
+    }
+    T *dst = p.feat + g * 14;
+#pragma unroll
+    for (int i = 0; i < 14; ++i) dst[i] = (T)out[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int LOG2N>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) stft_kernel(const StftParams<T> p) {
+__global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stft_kernel(const StftParams<T> p) {
     using C = Cfg<T, LOG2N>;
     constexpr int N = C::N, M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
     Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
-    double *scratch = reinterpret_cast<double *>(smem_raw + (size_t)FPB * C::BUF * sizeof(Cx<T>)) + (size_t)grp * C::SCR;
-    T *picks = reinterpret_cast<T *>(scratch + 16 * C::NW);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)FPB * C::BUF * sizeof(Cx<T>) +
-                                                 (size_t)FPB * C::SCR * sizeof(double)) + grp;
+    double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + C::off_bar()) + grp;
+    double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
+    if (threadIdx.x < LOG2_TAB) logtab[threadIdx.x] = p.log2tab[threadIdx.x];
     if (t == 0) mbar_init(bar, 1);
     fence_mbar_init();
     __syncthreads();
@@ -346,7 +461,9 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) stft_kernel(con
 
     const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
     const unsigned long long iters = (p.total_frames + stride - 1) / stride;
+    const bool want_feat = p.raw != nullptr;
     int f = 0;
+#pragma unroll 1
     for (unsigned long long it = 0; it < iters; ++it) {
         const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
         const bool active = g < p.total_frames;
@@ -372,6 +489,7 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) stft_kernel(con
             }
         } else {
             T *bufr = reinterpret_cast<T *>(buf);
+#pragma unroll 1
             for (int i = t; i < N; i += TPF) {
                 T x = (T)0;
                 if (i < L) {
@@ -389,92 +507,90 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 2 : 1)) stft_kernel(con
 
         frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed);
 
-        // ---- post-twiddle + power + first feature pass
-        T plo[16], phi[16], pmid = (T)0;
+        // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)
         FeatAcc<T> acc;
-        const bool want_feat = p.feat != nullptr;
         Cx<T> *spec = (p.spec != nullptr && active) ? p.spec + g * (unsigned long long)K : nullptr;
-#pragma unroll
+        T klo = (T)(16 * t), khi = (T)(M - 16 * t);
+#pragma unroll 2
         for (int i = 0; i < 16; ++i) {
             const int k = 16 * t + i;
-            const Cx<T> A = buf[padi<4>(k)];
-            const Cx<T> B = buf[padi<4>(k == 0 ? 0 : M - k)];
+            const int sa = 17 * t + i, sb = zslot(M - k);               // zslot(16 t + i) = 17 t + i
+            const Cx<T> A = buf[sa];
+            const Cx<T> B = (k == 0) ? A : buf[sb];
             const Cx<T> W = ldg_cx(&p.twN[k]);
             Cx<T> Xlo, Xhi;
             post_twiddle(A, B, W, Xlo, Xhi);
             if (spec) { spec[k] = Xlo; spec[M - k] = Xhi; }
-            plo[i] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
-            phi[i] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
+            const T plo = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
+            const T phi = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
+            buf[sa].x = plo;
+            buf[sb].x = phi;
             if (want_feat) {
-                acc.template add<true>(k, Mth<T>::sqrt_(plo[i]), plo[i], p.r_lo, p.r_hi);
-                if (p.bands_low) acc.template add<false>(M - k, Mth<T>::sqrt_(phi[i]), phi[i], p.r_lo, p.r_hi);
-                else             acc.template add<true>(M - k, Mth<T>::sqrt_(phi[i]), phi[i], p.r_lo, p.r_hi);
+                acc.lo_sum += plo;
+                acc.hi_sum += phi;
+                acc.bad |= abnormal(plo) | abnormal(phi);
+                acc.add(klo, Mth<T>::sqrt_(plo), plo);
+                acc.add(khi, Mth<T>::sqrt_(phi), phi);
+                klo += (T)1;
+                khi -= (T)1;
             }
         }
         if (t == TPF - 1) {
-            const Cx<T> A = buf[padi<4>(M / 2)];
+            const Cx<T> A = buf[zslot(M / 2)];
             const Cx<T> X = Cx<T>{A.x + A.x, -(A.y + A.y)};             // X[M/2] = conj(Z[M/2])
             if (spec) spec[M / 2] = X;
-            pmid = X.x * X.x + X.y * X.y;
-            if (want_feat) {
-                if (p.bands_low) acc.template add<false>(M / 2, Mth<T>::sqrt_(pmid), pmid, p.r_lo, p.r_hi);
-                else             acc.template add<true>(M / 2, Mth<T>::sqrt_(pmid), pmid, p.r_lo, p.r_hi);
-            }
+            const T pm = X.x * X.x + X.y * X.y;
+            buf[zslot(M / 2)].x = pm;
+            acc.mid = pm;
+            acc.bad |= abnormal(pm);
+            if (want_feat) acc.add((T)(M / 2), Mth<T>::sqrt_(pm), pm);
         }
-        if (want_feat) {
-            for (int q = t; q < 6; q += TPF) {                          // the six interpolation end-point bins
-                const int k = p.pick[q];
-                const int kk = (k <= M / 2) ? k : M - k;
-                Cx<T> Xlo, Xhi;
-                post_twiddle(buf[padi<4>(kk)], buf[padi<4>(kk == 0 ? 0 : M - kk)], ldg_cx(&p.twN[kk]), Xlo, Xhi);
-                const Cx<T> X = (k <= M / 2) ? Xlo : Xhi;
-                picks[q] = X.x * X.x + X.y * X.y;
-            }
-        }
+        if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp);
         fence_proxy_async();                                            // generic accesses to buf before the next TMA write
-        group_sync<TPF, C::BLOCK>(grp);                                 // buf free for the next frame; picks visible
-        if (want_feat) frame_features<T, LOG2N>(plo, phi, pmid, acc, picks, scratch, p, g, active, t, grp);
         group_sync<TPF, C::BLOCK>(grp);
     }
 }
 
 // K3: analyzer over caller-supplied magnitude rows (analysis/analyzer.rs:41-81, the loop at :99-104 / mp.rs:86-88)
 template <typename T, int LOG2N>
-__global__ void __launch_bounds__(256, 2) analyzer_kernel(const StftParams<T> p) {
+__global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) analyzer_kernel(const StftParams<T> p) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
-    double *scratch = reinterpret_cast<double *>(smem_raw) + (size_t)grp * C::SCR;
-    T *picks = reinterpret_cast<T *>(scratch + 16 * C::NW);
+    Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
+    double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
+    double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
+    if (threadIdx.x < LOG2_TAB) logtab[threadIdx.x] = p.log2tab[threadIdx.x];
+    __syncthreads();
     const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
     const unsigned long long iters = (p.total_frames + stride - 1) / stride;
+#pragma unroll 1
     for (unsigned long long it = 0; it < iters; ++it) {
         const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
         const bool active = g < p.total_frames;
         const T *row = p.mags + (active ? g : 0ull) * (unsigned long long)K;
-        T plo[16], phi[16], pmid = (T)0;
         FeatAcc<T> acc;
-#pragma unroll
+#pragma unroll 2
         for (int i = 0; i < 16; ++i) {
             const int k = 16 * t + i;
             const T ml = active ? row[k] : (T)0, mh = active ? row[M - k] : (T)0;
-            plo[i] = ml * ml;                                           // make_power_spectrum, s_a_t.rs:273-279
-            phi[i] = mh * mh;
-            acc.template add<true>(k, ml, plo[i], p.r_lo, p.r_hi);
-            acc.template add<true>(M - k, mh, phi[i], p.r_lo, p.r_hi);
+            const T plo = ml * ml, phi = mh * mh;                       // make_power_spectrum, s_a_t.rs:273-279
+            buf[zslot(k)].x = plo;
+            buf[zslot(M - k)].x = phi;
+            acc.lo_sum += plo;
+            acc.hi_sum += phi;
+            acc.add((T)k, ml, plo);
+            acc.add((T)(M - k), mh, phi);
         }
         if (t == TPF - 1) {
             const T mm = active ? row[M / 2] : (T)0;
-            pmid = mm * mm;
-            acc.template add<true>(M / 2, mm, pmid, p.r_lo, p.r_hi);
+            const T pm = mm * mm;
+            buf[zslot(M / 2)].x = pm;
+            acc.mid = pm;
+            acc.add((T)(M / 2), mm, pm);
         }
-        for (int q = t; q < 6; q += TPF) {
-            const T mm = active ? row[p.pick[q]] : (T)0;
-            picks[q] = mm * mm;
-        }
-        group_sync<TPF, C::BLOCK>(grp);
-        frame_features<T, LOG2N>(plo, phi, pmid, acc, picks, scratch, p, g, active, t, grp);
+        frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp);
         group_sync<TPF, C::BLOCK>(grp);
     }
 }

@@ -1,8 +1,12 @@
 """Import shim: the package directory is ``aus-rust_b200/`` (not a valid Python identifier), so this module
-turns itself into that package.  ``import aus_rust_b200`` then behaves like importing the directory."""
+replaces itself in ``sys.modules`` with that directory loaded as the package ``aus_rust_b200``."""
+import importlib.util as _ilu
 import os as _os
+import sys as _sys
 
-__path__ = [_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "aus-rust_b200")]
-with open(_os.path.join(__path__[0], "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))
-del _f
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "aus-rust_b200")
+_spec = _ilu.spec_from_file_location("aus_rust_b200", _os.path.join(_dir, "__init__.py"),
+                                     submodule_search_locations=[_dir])
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules["aus_rust_b200"] = _mod
+_spec.loader.exec_module(_mod)

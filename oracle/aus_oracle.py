@@ -130,8 +130,9 @@ def overlap_add(chunks: np.ndarray, fft_size: int, hop_size: int) -> np.ndarray:
     return out
 
 
-def irstft(spectrogram, fft_size: int, hop_size: int, window_type: int) -> np.ndarray:
-    """fft.rs:204-268 including the -6 dBFS peak normalisation and its NaN/inf quirks."""
+def irstft(spectrogram, fft_size: int, hop_size: int, window_type: int, normalize: bool = True) -> np.ndarray:
+    """fft.rs:204-268 including the -6 dBFS peak normalisation and its NaN/inf quirks.
+    ``normalize=False`` (not in the reference) stops after the window-norm division (fft.rs:250-252)."""
     S = np.asarray(spectrogram, dtype=np.complex128)
     if S.ndim != 2 or S.shape[0] == 0:
         raise SpectrumError("empty spectrogram (the reference underflows at fft.rs:208)")
@@ -150,6 +151,8 @@ def irstft(spectrogram, fft_size: int, hop_size: int, window_type: int) -> np.nd
     audio = overlap_add(chunks, fft_size, hop_size)                           # fft.rs:247
     with np.errstate(divide="ignore", invalid="ignore"):
         audio = audio / norm                                                  # fft.rs:250-252
+        if not normalize:
+            return audio
         maxval = 0.0
         m = np.fmax.reduce(audio, initial=0.0) if audio.size else 0.0         # f64::max ignores NaN, fft.rs:255-258
         maxval = float(m)

@@ -3,7 +3,7 @@ relative 1e-9 for f64 features and spectra, 1e-4 for f32."""
 import numpy as np
 import pytest
 
-from helpers import ROLL, assert_features, assert_spectra, rel_err
+from helpers import ROLL, assert_features, assert_spectra, cancellation_scales, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -68,7 +68,9 @@ def test_ragged_lengths_and_short_last_frame(ctx, orc, n):
         assert_spectra(np.nan_to_num(got_s), np.nan_to_num(ref_s), RTOL64, f"n={n}")
         ref = orc.stft_features(x, 2048, 512, window, SR)
         got = ctx.stft_features(x, 2048, 512, window, SR)
-        assert_features(got, ref, RTOL64, f"n={n} w={window}")
+        # a 1- or 2-sample frame has a flat spectrum: its slopes are pure cancellation (see cancellation_scales)
+        sc = cancellation_scales(np.abs(np.nan_to_num(ref_s)), 2048, SR)
+        assert_features(got, ref, RTOL64, f"n={n} w={window}", scales=sc)
 
 
 def test_silent_frames_nan_pattern(ctx, orc):
@@ -107,8 +109,8 @@ def test_analyzer_batch(ctx, orc, fft_size):
     assert_features(got, ref, RTOL64, "analyzer_batch")
 
 
-@pytest.mark.parametrize("fft_size,hop,window", [(2048, 1024, 3), (4096, 1024, 2), (1024, 256, 1), (256, 128, 0),
-                                                 (16384, 4096, 3), (512, 512, 4)])
+@pytest.mark.parametrize("fft_size,hop,window", [(2048, 1024, 3), (4096, 1024, 2), (1024, 256, 3), (256, 128, 0),
+                                                 (16384, 4096, 3), (512, 512, 4), (64, 16, 3), (8192, 4096, 2)])
 def test_irstft(ctx, orc, fft_size, hop, window):
     x = orc.synth_signal(20 * fft_size + 123, SR, seed=8, file_id=fft_size)
     S = orc.rstft(x, fft_size, hop, window)
@@ -119,6 +121,24 @@ def test_irstft(ctx, orc, fft_size, hop, window):
     fin = np.isfinite(ref)
     scale = np.max(np.abs(ref[fin]))
     assert np.max(np.abs(got[fin] - ref[fin])) <= RTOL64 * scale
+
+
+def test_irstft_blackman_unnormalised(ctx, orc):
+    """Blackman's w[0] is a rounding residue (~ -1.4e-17), so out[0] = (FFT rounding noise) / 1e-17 is arbitrary in
+    ANY implementation and may even become the normalisation peak.  Parity is therefore checked before the peak
+    normalisation and away from samples whose window norm is ~0."""
+    fft_size, hop = 1024, 256
+    x = orc.synth_signal(20 * fft_size + 123, SR, seed=8, file_id=1)
+    S = orc.rstft(x, fft_size, hop, orc.BLACKMAN)
+    ref = orc.irstft(S, fft_size, hop, orc.BLACKMAN, normalize=False)
+    got = ctx.irstft(S, fft_size, hop, orc.BLACKMAN, normalize=False)
+    w2 = orc.generate_window(orc.BLACKMAN, fft_size) ** 2
+    norm = np.zeros(ref.size)
+    for h in range(S.shape[0]):
+        norm[h * hop:h * hop + fft_size] += w2
+    ok = norm > 1e-12
+    assert ok.sum() >= ref.size - 2
+    assert np.max(np.abs(got[ok] - ref[ok])) <= RTOL64 * np.max(np.abs(ref[ok]))
 
 
 def test_rfft_irfft(ctx, orc):
