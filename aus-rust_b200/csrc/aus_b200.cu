@@ -62,7 +62,7 @@ struct DevBuf {
 };
 
 struct Tables {
-    void *twM = nullptr, *twN = nullptr;
+    void *tw2 = nullptr, *tw3 = nullptr, *twNt = nullptr, *twN = nullptr;
     void *win2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -191,7 +191,9 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->tables) {
-        cudaFree(kv.second.twM);
+        cudaFree(kv.second.tw2);
+        cudaFree(kv.second.tw3);
+        cudaFree(kv.second.twNt);
         cudaFree(kv.second.twN);
         for (void *w : kv.second.win2) cudaFree(w);
     }
@@ -233,14 +235,31 @@ template <typename T> static int get_tables(aus_ctx *c, int lg, int wtype, Table
     Tables &tb = c->tables[key];
     const size_t N = (size_t)1 << lg, Mh = N / 2;
     const long double TWO_PI = 6.283185307179586476925286766559005768L;
-    if (!tb.twM) {
-        std::vector<Cx<T>> h(Mh);
-        for (size_t k = 0; k < Mh; ++k) {
-            const long double a = TWO_PI * (long double)k / (long double)Mh;
-            h[k].x = (T)cosl(a);
-            h[k].y = (T)(-sinl(a));
-        }
-        AUS_TRY(upload<T>(&tb.twM, h, c->stream));
+    const size_t tpf = Mh / 32, c2 = std::min<size_t>(tpf, 32), r3 = Mh > 1024 ? Mh / 1024 : 1;
+    auto wm = [&](size_t e) {                      // exp(-2 pi i e / M), e reduced mod M first (exact)
+        const long double a = TWO_PI * (long double)(e % Mh) / (long double)Mh;
+        return Cx<T>{(T)cosl(a), (T)(-sinl(a))};
+    };
+    if (!tb.tw2 && tpf >= 2) {                     // pass-2 twiddles in consumption order: [r][c] = W_M^(c R3 r)
+        std::vector<Cx<T>> h(32 * c2);
+        for (size_t r = 0; r < 32; ++r)
+            for (size_t cc = 0; cc < c2; ++cc) h[r * c2 + cc] = wm(cc * r3 * r);
+        AUS_TRY(upload<T>(&tb.tw2, h, c->stream));
+    }
+    if (!tb.tw3 && r3 > 1) {                       // pass-3 twiddles: [r][j] = W_M^(j r), j < 1024
+        std::vector<Cx<T>> h(r3 * 1024);
+        for (size_t r = 0; r < r3; ++r)
+            for (size_t j = 0; j < 1024; ++j) h[r * 1024 + j] = wm(j * r);
+        AUS_TRY(upload<T>(&tb.tw3, h, c->stream));
+    }
+    if (!tb.twNt) {                                // post-twiddles in consumption order: [i][t] = (cos, sin)(2 pi (16 t + i) / N)
+        std::vector<Cx<T>> h(16 * tpf);
+        for (size_t i = 0; i < 16; ++i)
+            for (size_t t = 0; t < tpf; ++t) {
+                const long double a = TWO_PI * (long double)(16 * t + i) / (long double)N;
+                h[i * tpf + t] = Cx<T>{(T)cosl(a), (T)sinl(a)};
+            }
+        AUS_TRY(upload<T>(&tb.twNt, h, c->stream));
     }
     if (!tb.twN) {
         std::vector<Cx<T>> h(Mh / 2 + 1);
@@ -506,7 +525,9 @@ static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t
     p.wtype = wtype;
     p.tma_ok = ((reinterpret_cast<uintptr_t>(d_audio) & 15) == 0) ? 1 : 0;
     p.win2 = (const Cx<T> *)tb->win2[wtype];
-    p.twM = (const Cx<T> *)tb->twM;
+    p.tw2 = (const Cx<T> *)tb->tw2;
+    p.tw3 = (const Cx<T> *)tb->tw3;
+    p.twNt = (const Cx<T> *)tb->twNt;
     p.twN = (const Cx<T> *)tb->twN;
     p.log2tab = (const double2 *)c->log2tab;
     p.npass = 2;
@@ -734,7 +755,9 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     p.apply_window = apply_window;
     p.tma_ok = ((reinterpret_cast<uintptr_t>(d_spec) & 15) == 0) ? 1 : 0;
     p.fwd.win2 = (const Cx<T> *)tb->win2[wtype];
-    p.fwd.twM = (const Cx<T> *)tb->twM;
+    p.fwd.tw2 = (const Cx<T> *)tb->tw2;
+    p.fwd.tw3 = (const Cx<T> *)tb->tw3;
+    p.fwd.twNt = (const Cx<T> *)tb->twNt;
     p.fwd.twN = (const Cx<T> *)tb->twN;
     p.fwd.npass = 2;
     AUS_TRY(launch_istft<T>(c, lg, p));

@@ -28,7 +28,7 @@ template <typename T> struct IstftParams {
     int halo;                                // ceil(N / hop) - 1
     int apply_window;                        // 0: irfft (plain inverse, no window / norm)
     int tma_ok;
-    StftParams<T> fwd;                       // tables (win2, twM, twN) for frame_fft
+    StftParams<T> fwd;                       // tables (win2, tw2, tw3, twN) for frame_fft
 };
 
 template <typename T, int LOG2N>

@@ -57,8 +57,11 @@ template <typename T> struct StftParams {
     int tma_ok;                        // audio base is 16-byte aligned
     int npass;                         // always 2; a runtime value so the shared radix-32 body stays one rolled loop
     const Cx<T> *win2;                 // [M] (0.5 w[2n], 0.5 w[2n+1]) -- the 1/2 of the real-FFT split is folded in
-    const Cx<T> *twM;                  // [M] exp(-2 pi i k / M)
-    const Cx<T> *twN;                  // [M/2 + 1] (cos, sin)(2 pi k / N)
+    // twiddles are stored in CONSUMPTION order, so the 32 lanes of a warp always read 32 consecutive entries:
+    const Cx<T> *tw2;                  // [32][C2] pass-2 twiddles  W_M^(c R3 r) at [r][c], C2 = min(TPF, 32)
+    const Cx<T> *tw3;                  // [R3][1024] pass-3 twiddles W_M^(j r) at [r][j]           (M > 1024 only)
+    const Cx<T> *twNt;                 // [16][TPF] post-twiddles (cos, sin)(2 pi (16 t + i) / N) at [i][t]
+    const Cx<T> *twN;                  // [M/2 + 1] (cos, sin)(2 pi k / N), natural order (inverse pre-twiddle)
     const double2 *log2tab;            // [LOG2_TAB] (1/c_i, -log2(1/c_i))
     double *raw;                       // [frames][RAW_N] per-frame sums for finalize_kernel, or nullptr (no features)
     T *feat;                           // [frames][14] (written by finalize_kernel)
@@ -117,7 +120,7 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
         // ---- passes 1 and 2 are both radix 32 with one butterfly per thread (j = t): one rolled loop whose
         //      loads / table reads / stores are linear in r:  address = base + r * stride.
         //      pass 1 (Ns = 1):  in  = buf[j + r TPF] (raw samples)   x win2[j + r TPF]      out = X[33 j + r]
-        //      pass 2 (Ns = 32): in  = X[pad5(j + r TPF)]             x twM[jm r]            out = Z or X layout
+        //      pass 2 (Ns = 32): in  = X[pad5(j + r TPF)]             x tw2[r][j mod 32]     out = Z or X layout
         const int j = t;
         int lbase = j, lstride = TPF;
         const Cx<T> *tab = p.win2 + j;
@@ -152,13 +155,12 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
             // address generators of pass 2
             lbase = j + (j >> 5);
             lstride = TPF + TPF / 32;
-            tab = p.twM;
+            tab = p.tw2 + (j & 31);                            // W_M^((j mod 32) R3 r) at tw2[r][j mod 32]
+            tstride = 32;
             if constexpr (!C::THREE) {
-                tstride = j;                                   // W_M^(j r)
                 sbase = j + (j >> 4);                          // Z layout: pad4(j + 32 r) = j + (j >> 4) + 34 r
                 sstride = 34;
             } else {
-                tstride = (j & 31) * R3;                       // W_M^((j mod 32) R3 r)
                 const int b = (j >> 5) * 1024 + (j & 31);      // exchange layout: pad5(b + 32 r) = b + (b >> 5) + 33 r
                 sbase = b + (b >> 5);
                 sstride = 33;
@@ -197,7 +199,7 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
             static_for<0, 32>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
                 Cx<T> z = buf[padi<XS>(j + r * TPF)];
-                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.twM[j * r]));
+                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.tw2[r * TPF + j]));
                 v[r] = z;
             });
             group_sync<TPF, C::BLOCK>(grp);
@@ -219,7 +221,7 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
             static_for<0, R3>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
                 Cx<T> z = buf[padi<XS>(j + r * 1024)];
-                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.twM[j * r]));
+                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.tw3[r * 1024 + j]));
                 v[b * R3 + r] = z;
             });
         });
@@ -264,6 +266,20 @@ template <typename T> struct FeatAcc {
 // Slot of bin b in the group buffer ("Z layout").
 __device__ __forceinline__ int zslot(int b) { return b + (b >> 4); }
 
+// During the feature passes a slot holds two scalars: the bin's power and the running sum up to it.  Lanes 8
+// (f64) / 16 (f32) apart map to the same banks (slot stride 17), so which half holds the power alternates with
+// bit 3 (4) of the owning thread: half = hpar(owner) for the power, 1 - hpar(owner) for the running sum.
+template <typename T> __device__ __forceinline__ int hpar(int owner) { return (owner >> (sizeof(T) == 8 ? 3 : 4)) & 1; }
+template <int M, int TPF> __device__ __forceinline__ int bin_owner(int b) {
+    return b < M / 2 ? (b >> 4) : (b == M / 2 ? TPF - 1 : ((M - b) >> 4));
+}
+template <typename T, int M, int TPF> __device__ __forceinline__ T &pow_of(Cx<T> *buf, int b) {
+    return reinterpret_cast<T *>(buf)[2 * zslot(b) + hpar<T>(bin_owner<M, TPF>(b))];
+}
+template <typename T, int M, int TPF> __device__ __forceinline__ T &cum_of(Cx<T> *buf, int b) {
+    return reinterpret_cast<T *>(buf)[2 * zslot(b) + 1 - hpar<T>(bin_owner<M, TPF>(b))];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Feature passes over one frame.  On entry slot(b).x = |X[b]|^2 for every bin b = 0..M (written by the owning
 // threads, not yet synchronised).  Thread t owns the bins [16 t, 16 t + 16) ("low") and (M - 16 t - 16, M - 16 t]
@@ -285,7 +301,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
         for (int u = 0; u < 33; ++u) {
             const int b = u < 16 ? 16 * t + u : (u < 32 ? hb + (u - 16) : M / 2);
             if (u == 32 && t != TPF - 1) break;
-            const T m = Mth<T>::sqrt_exact(buf[zslot(b)].x);
+            const T m = Mth<T>::sqrt_exact(pow_of<T, M, TPF>(buf, b));
             acc.s_m += m;
             acc.s_mk += m * (T)b;
         }
@@ -296,7 +312,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
 #pragma unroll 1
     for (int b = p.r_lo[0] + t; b < p.r_hi[1]; b += TPF) {
-        const T pw = buf[zslot(b)].x;
+        const T pw = pow_of<T, M, TPF>(buf, b);
         const T pk = pw * (T)b;
         if (b < p.r_hi[0]) { b1p += pw; b1pk += pk; }
         if (b >= p.r_lo[1]) { b2p += pw; b2pk += pk; }
@@ -321,40 +337,60 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     const T inv_p = (T)(1.0 / P);
     T d2s = 0, d3s = 0, d4s = 0, ent = 0, slq = 0;
     bool badq = false;
-    auto bin = [&](int b, T d, T &cum) {
-        Cx<T> *s = buf + zslot(b);
-        const T pw = s->x;
-        const T dd = d * d;
-        const T w2 = dd * pw;
-        d2s += w2;
-        d3s += w2 * d;
-        d4s += w2 * dd;
-        const T q = pw * inv_p;                       // make_spectrum_pmf, s_a_t.rs:284-290
-        badq |= abnormal(q);
-        const T l = Mth<T>::log2_(q, logtab);
-        ent += q * l;
-        slq += l;
-        cum += pw;
-        s->y = cum;
+    // four bins at a time: all shared-memory loads first, then four independent sqrt-free math chains, so the
+    // load-to-use latency is paid once per block.  s0 = slot of the first bin, the 4th bin sits at s0 + 3 + skip.
+    T *const bufT = reinterpret_cast<T *>(buf);
+    const int hp = hpar<T>(t);                        // this thread's power half; running sum in the other one
+    auto block4 = [&](int s0, int skip, T d0, T &cum) {
+        T pw[4], q[4], l[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pw[c] = bufT[2 * (s0 + c + (c == 3 ? skip : 0)) + hp];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const T d = d0 + (T)c;
+            const T dd = d * d;
+            const T w2 = dd * pw[c];
+            d2s += w2;
+            d3s += w2 * d;
+            d4s += w2 * dd;
+            q[c] = pw[c] * inv_p;                     // make_spectrum_pmf, s_a_t.rs:284-290
+            badq |= abnormal(q[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], logtab);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            ent += q[c] * l[c];
+            slq += l[c];
+            cum += pw[c];
+            bufT[2 * (s0 + c + (c == 3 ? skip : 0)) + 1 - hp] = cum;
+        }
     };
     {
         T cum = base_lo;
-        T d = (T)(16 * t) - kappa;
-#pragma unroll 2
-        for (int i = 0; i < 16; ++i) {
-            bin(16 * t + i, d, cum);
-            if constexpr (sizeof(T) == 8) d += (T)1; else d = (T)(16 * t + i + 1) - kappa;   // f64: no I2F per bin
-        }
+        const T dlo = (T)(16 * t) - kappa;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 4) block4(17 * t + i0, 0, dlo + (T)i0, cum);       // zslot(16 t + i) = 17 t + i
+        // high chunk, ascending bins hb .. hb + 15: slots hs .. hs + 14 and hs + 16 (hs + 15 is the pad slot)
         cum = base_hi;
-        d = (T)hb - kappa;
-#pragma unroll 2
-        for (int u = 0; u < 16; ++u) {
-            bin(hb + u, d, cum);
-            if constexpr (sizeof(T) == 8) d += (T)1; else d = (T)(hb + u + 1) - kappa;
-        }
-        if (t == TPF - 1) {
-            T cum_mid = (T)tot_lo;
-            bin(M / 2, (T)(M / 2) - kappa, cum_mid);
+        const int hs = zslot(hb);
+        const T dhi = (T)hb - kappa;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 4) block4(hs + i0, i0 == 12 ? 1 : 0, dhi + (T)i0, cum);
+        if (t == TPF - 1) {                            // bin M/2 sits between the low and the high chunks
+            const T pw = bufT[2 * zslot(M / 2) + hp];
+            const T d = (T)(M / 2) - kappa;
+            const T dd = d * d;
+            const T w2 = dd * pw;
+            d2s += w2;
+            d3s += w2 * d;
+            d4s += w2 * dd;
+            const T q = pw * inv_p;
+            badq |= abnormal(q);
+            const T l = Mth<T>::log2_(q, logtab);
+            ent += q * l;
+            slq += l;
+            bufT[2 * zslot(M / 2) + 1 - hp] = (T)tot_lo + pw;
         }
     }
     // zero / subnormal / non-finite q somewhere: redo the two log sums with the library log2 (0 * -inf = NaN and
@@ -366,7 +402,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
         for (int u = 0; u < 33; ++u) {
             const int b = u < 16 ? 16 * t + u : (u < 32 ? hb + (u - 16) : M / 2);
             if (u == 32 && t != TPF - 1) break;
-            const T q = buf[zslot(b)].x * inv_p;
+            const T q = pow_of<T, M, TPF>(buf, b) * inv_p;
             const T l = Mth<T>::log2_exact(q);
             ent += q * l;
             slq += l;
@@ -387,12 +423,12 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
 #pragma unroll 1
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (buf[zslot(mid)].y < th) lo = mid + 1; else hi = mid;
+                if (cum_of<T, M, TPF>(buf, mid) < th) lo = mid + 1; else hi = mid;
             }
             rec[RAW_ROLL0 + qq] = (double)lo;
         }
 #pragma unroll 1
-        for (int qq = t; qq < 6; qq += TPF) rec[RAW_PICK0 + qq] = (double)buf[zslot(p.pick[qq])].x;
+        for (int qq = t; qq < 6; qq += TPF) rec[RAW_PICK0 + qq] = (double)pow_of<T, M, TPF>(buf, p.pick[qq]);
         if (t == 0) {
             rec[RAW_SM] = r[0]; rec[RAW_SMK] = r[1]; rec[RAW_SPK] = r[2];
             rec[RAW_B1P] = r[3]; rec[RAW_B1PK] = r[4]; rec[RAW_B2P] = r[5]; rec[RAW_B2PK] = r[6];
@@ -510,29 +546,53 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
         // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)
         FeatAcc<T> acc;
         Cx<T> *spec = (p.spec != nullptr && active) ? p.spec + g * (unsigned long long)K : nullptr;
-        T klo = (T)(16 * t), khi = (T)(M - 16 * t);
-#pragma unroll 2
-        for (int i = 0; i < 16; ++i) {
-            const int k = 16 * t + i;
-            const int sa = 17 * t + i, sb = zslot(M - k);               // zslot(16 t + i) = 17 t + i
-            const Cx<T> A = buf[sa];
-            const Cx<T> B = (k == 0) ? A : buf[sb];
-            const Cx<T> W = ldg_cx(&p.twN[k]);
-            Cx<T> Xlo, Xhi;
-            post_twiddle(A, B, W, Xlo, Xhi);
-            if (spec) { spec[k] = Xlo; spec[M - k] = Xhi; }
-            const T plo = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
-            const T phi = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
-            buf[sa].x = plo;
-            buf[sb].x = phi;
+        // four pairs (k, M - k) at a time: loads first, then eight independent post-twiddle / sqrt chains.
+        // slots: zslot(16 t + i) = 17 t + i;  zslot(M - 16 t - i) = h0 - 1 - i for i >= 1 and h0 for i = 0.
+        const int h0 = zslot(M - 16 * t);
+        T *const bufT = reinterpret_cast<T *>(buf);
+        const int hp = hpar<T>(t);
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 4) {
+            Cx<T> A[4], B[4], W[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i0 + c;
+                A[c] = buf[17 * t + i];
+                B[c] = buf[(c == 0 && i0 == 0) ? (t == 0 ? 0 : h0) : h0 - 1 - i];      // k = 0 pairs with itself
+                W[c] = ldg_cx(&p.twNt[i * TPF + t]);
+            }
+            T plo[4], phi[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = 16 * t + i0 + c;
+                Cx<T> Xlo, Xhi;
+                post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
+                if (spec) { spec[k] = Xlo; spec[M - k] = Xhi; }
+                plo[c] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
+                phi[c] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i0 + c;
+                bufT[2 * (17 * t + i) + hp] = plo[c];
+                bufT[2 * ((c == 0 && i0 == 0) ? h0 : h0 - 1 - i) + hp] = phi[c];
+            }
             if (want_feat) {
-                acc.lo_sum += plo;
-                acc.hi_sum += phi;
-                acc.bad |= abnormal(plo) | abnormal(phi);
-                acc.add(klo, Mth<T>::sqrt_(plo), plo);
-                acc.add(khi, Mth<T>::sqrt_(phi), phi);
-                klo += (T)1;
-                khi -= (T)1;
+                T mlo[4], mhi[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc.bad |= abnormal(plo[c]) | abnormal(phi[c]);
+                    mlo[c] = Mth<T>::sqrt_(plo[c]);
+                    mhi[c] = Mth<T>::sqrt_(phi[c]);
+                }
+                const T klo = (T)(16 * t + i0), khi = (T)(M - 16 * t - i0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc.lo_sum += plo[c];
+                    acc.hi_sum += phi[c];
+                    acc.add(klo + (T)c, mlo[c], plo[c]);
+                    acc.add(khi - (T)c, mhi[c], phi[c]);
+                }
             }
         }
         if (t == TPF - 1) {
@@ -540,7 +600,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
             const Cx<T> X = Cx<T>{A.x + A.x, -(A.y + A.y)};             // X[M/2] = conj(Z[M/2])
             if (spec) spec[M / 2] = X;
             const T pm = X.x * X.x + X.y * X.y;
-            buf[zslot(M / 2)].x = pm;
+            bufT[2 * zslot(M / 2) + hp] = pm;
             acc.mid = pm;
             acc.bad |= abnormal(pm);
             if (want_feat) acc.add((T)(M / 2), Mth<T>::sqrt_(pm), pm);
@@ -576,8 +636,8 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ana
             const int k = 16 * t + i;
             const T ml = active ? row[k] : (T)0, mh = active ? row[M - k] : (T)0;
             const T plo = ml * ml, phi = mh * mh;                       // make_power_spectrum, s_a_t.rs:273-279
-            buf[zslot(k)].x = plo;
-            buf[zslot(M - k)].x = phi;
+            pow_of<T, M, TPF>(buf, k) = plo;
+            pow_of<T, M, TPF>(buf, M - k) = phi;
             acc.lo_sum += plo;
             acc.hi_sum += phi;
             acc.add((T)k, ml, plo);
@@ -586,7 +646,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ana
         if (t == TPF - 1) {
             const T mm = active ? row[M / 2] : (T)0;
             const T pm = mm * mm;
-            buf[zslot(M / 2)].x = pm;
+            pow_of<T, M, TPF>(buf, M / 2) = pm;
             acc.mid = pm;
             acc.add((T)(M / 2), mm, pm);
         }
