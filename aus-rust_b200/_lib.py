@@ -67,6 +67,8 @@ SIGNATURES = {
     "aus_batch_num_frames": (c_uint64, [_p_u64, c_size_t, c_size_t, c_size_t]),
     "aus_stft_features_multi": (c_int, [POINTER(c_int), c_int, _p_d, _p_u64, _p_u64, c_size_t, c_size_t, c_size_t,
                                         c_int, c_uint32, c_int, _p_d]),
+    "aus_plan_shards": (c_int, [_p_u64, _p_u64, c_size_t, c_size_t, c_size_t, c_int, _p_u64, _p_u64, _p_u64,
+                                POINTER(c_int), c_size_t, POINTER(c_size_t)]),
     "aus_rstft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_size_t, c_int, c_int, _p_d]),
     "aus_rstft_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, c_void_p]),
     "aus_rfft": (c_int, [c_void_p, _p_d, c_size_t, c_int, _p_d]),

@@ -238,6 +238,21 @@ def stft_features_multi(devices, audio, offsets, lengths, fft_size: int, hop: in
     return out
 
 
+def plan_shards(offsets, lengths, fft_size: int, hop: int, n_devices: int):
+    """The shard plan of aus_stft_features_multi as numpy arrays (vf_off, vf_len, vf_row, vf_dev); pure host."""
+    lib = _lib.load_library()
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    cap = ln.size * max(int(n_devices), 1) + 1
+    vo, vl, vr = (np.empty(cap, dtype=np.uint64) for _ in range(3))
+    vd = np.empty(cap, dtype=np.int32)
+    n = ctypes.c_size_t(0)
+    _lib.check(lib.aus_plan_shards(_pu64(off), _pu64(ln), ln.size, int(fft_size), int(hop), int(n_devices), _pu64(vo),
+                                   _pu64(vl), _pu64(vr), vd.ctypes.data_as(ctypes.POINTER(c_int)), cap, ctypes.byref(n)))
+    k = n.value
+    return vo[:k].astype(np.int64), vl[:k].astype(np.int64), vr[:k].astype(np.int64), vd[:k].copy()
+
+
 _default = {}
 _default_lock = threading.Lock()
 

@@ -842,31 +842,29 @@ extern "C" int aus_synth_dev(aus_ctx *c, void *d_audio, uint64_t n, uint64_t n0,
 }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU sharding
-// No collective: frames and files are independent.  Each device gets a contiguous run of (virtual) files; a
-// single long file is cut into contiguous frame ranges whose sample spans overlap by fft_size - hop, and only the span
-// that ends at the true end of the file can produce the short last frame.  Host threads, ordered gather into `features`.
-static std::mutex g_multi_mu;
-static std::map<int, aus_ctx *> g_multi_ctx;
-
-extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
-                                       const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr,
-                                       int precision, double *features) {
+// Pure host: the shard plan.  Virtual file v covers samples [vf_off, vf_off + vf_len) of the caller's buffer, produces
+// frames that land at feature rows [vf_row, vf_row + frames) and runs on device slot vf_dev (0 .. n_devices-1).
+extern "C" int aus_plan_shards(const uint64_t *offsets, const uint64_t *lengths, size_t n_files, size_t N, size_t hop,
+                               int n_devices, uint64_t *vf_off, uint64_t *vf_len, uint64_t *vf_row, int *vf_dev,
+                               size_t cap, size_t *n_out) {
     if (n_devices < 1) return fail(AUS_ERR_INVALID, "n_devices must be >= 1");
     AUS_TRY(check_fft_args(N, hop));
-    if (!lengths || !features) return fail(AUS_ERR_INVALID, "null argument");
-    // virtual files: (offset, length, first output row)
+    if (!lengths || !n_out) return fail(AUS_ERR_INVALID, "null argument");
     struct VF { uint64_t off, len, row, frames; };
     std::vector<VF> vf;
     uint64_t row = 0;
     for (size_t i = 0; i < n_files; ++i) {
         const uint64_t off = offsets ? offsets[i] : 0, len = lengths[i];
         const uint64_t F = aus_num_frames((size_t)len, N, hop);
+        // enough files: whole files per device; otherwise cut each file into contiguous frame ranges
         const uint64_t parts = (n_files >= (size_t)n_devices) ? 1 : std::min<uint64_t>(F, (uint64_t)n_devices);
         for (uint64_t s = 0; s < parts; ++s) {
             const uint64_t a = F * s / parts, b = F * (s + 1) / parts;
             VF v;
             v.off = off + a * hop;
-            v.len = (b == F) ? len - std::min<uint64_t>(len, a * hop) : (b - a - 1) * hop + N;   // full frames only unless it holds the end
+            // a range that does not hold the file's last frame gets exactly (b-a-1)*hop + N samples, so all of its
+            // frames are full length; the last range keeps the true tail and with it the short-window rule
+            v.len = (b == F) ? len - std::min<uint64_t>(len, a * hop) : (b - a - 1) * hop + N;
             v.row = row + a;
             v.frames = b - a;
             vf.push_back(v);
@@ -874,23 +872,45 @@ extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const 
         row += F;
     }
     const uint64_t total = row;
+    *n_out = vf.size();
+    if (vf.size() > cap) return fail(AUS_ERR_INVALID, "shard plan does not fit the caller's arrays");
     // contiguous split of the virtual files over devices, balanced by frame count
-    std::vector<size_t> cut(n_devices + 1, vf.size());
-    cut[0] = 0;
-    {
-        uint64_t acc = 0;
-        int d = 1;
-        for (size_t i = 0; i < vf.size() && d < n_devices; ++i) {
-            acc += vf[i].frames;
-            while (d < n_devices && acc * (uint64_t)n_devices >= total * (uint64_t)d) cut[d++] = i + 1;
-        }
+    uint64_t acc = 0;
+    for (size_t i = 0; i < vf.size(); ++i) {
+        // device of the shard's midpoint on the cumulative-frame axis (monotone, so each device gets a contiguous run)
+        const uint64_t mid2 = 2 * acc + vf[i].frames;
+        const int d = total ? (int)std::min<uint64_t>((uint64_t)n_devices - 1, mid2 * (uint64_t)n_devices / (2 * total)) : 0;
+        if (vf_off) vf_off[i] = vf[i].off;
+        if (vf_len) vf_len[i] = vf[i].len;
+        if (vf_row) vf_row[i] = vf[i].row;
+        if (vf_dev) vf_dev[i] = d;
+        acc += vf[i].frames;
     }
+    return AUS_OK;
+}
+
+// No collective: frames and files are independent.  Host threads, one per device, each running the batch
+// entry point on its run of virtual files; the ordered gather is the row offsets of the plan (like mp.rs:100-116).
+static std::mutex g_multi_mu;
+static std::map<int, aus_ctx *> g_multi_ctx;
+
+extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
+                                       const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr,
+                                       int precision, double *features) {
+    if (!features) return fail(AUS_ERR_INVALID, "null features");
+    const size_t cap = n_files * (size_t)std::max(n_devices, 1) + 1;
+    std::vector<uint64_t> vo(cap), vl(cap), vr(cap);
+    std::vector<int> vd(cap);
+    size_t nv = 0;
+    AUS_TRY(aus_plan_shards(offsets, lengths, n_files, N, hop, n_devices, vo.data(), vl.data(), vr.data(), vd.data(), cap, &nv));
     std::vector<int> rc(n_devices, AUS_OK);
     std::vector<std::string> msg(n_devices);
     std::vector<std::thread> th;
     for (int d = 0; d < n_devices; ++d) {
         th.emplace_back([&, d]() {
-            const size_t lo = cut[d], hi = cut[d + 1];
+            size_t lo = nv, hi = 0;
+            for (size_t i = 0; i < nv; ++i)
+                if (vd[i] == d) { lo = std::min(lo, i); hi = std::max(hi, i + 1); }
             if (lo >= hi) return;
             const int dev = devices ? devices[d] : d;
             aus_ctx *ctx = nullptr;
@@ -903,13 +923,12 @@ extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const 
                     g_multi_ctx[dev] = ctx;
                 } else ctx = it->second;
             }
-            // the device's sample span, re-based to its first sample
-            uint64_t s0 = UINT64_MAX, s1 = 0;
-            for (size_t i = lo; i < hi; ++i) { s0 = std::min(s0, vf[i].off); s1 = std::max(s1, vf[i].off + vf[i].len); }
+            uint64_t s0 = UINT64_MAX;                 // re-base the device's span to its first sample
+            for (size_t i = lo; i < hi; ++i) s0 = std::min(s0, vo[i]);
             std::vector<uint64_t> o(hi - lo), l(hi - lo);
-            for (size_t i = lo; i < hi; ++i) { o[i - lo] = vf[i].off - s0; l[i - lo] = vf[i].len; }
+            for (size_t i = lo; i < hi; ++i) { o[i - lo] = vo[i] - s0; l[i - lo] = vl[i]; }
             rc[d] = aus_stft_features_batch(ctx, audio + s0, o.data(), l.data(), hi - lo, N, hop, wtype, sr, precision,
-                                            features + vf[lo].row * 14, nullptr);
+                                            features + vr[lo] * 14, nullptr);
             if (rc[d] != AUS_OK) msg[d] = g_err;
         });
     }

@@ -127,6 +127,15 @@ int aus_stft_features_multi(const int *devices, int n_devices, const double *aud
                             const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop, int window_type,
                             uint32_t sample_rate, int precision, double *features);
 
+/* pure host: the shard plan aus_stft_features_multi uses (also for callers that drive the devices themselves, e.g. one
+ * process per GPU).  Virtual file v = samples [vf_off[v], vf_off[v]+vf_len[v]) of the caller's buffer; its frames are
+ * rows [vf_row[v], ...) of the whole batch; vf_dev[v] in 0..n_devices-1.  A single long file is cut into contiguous
+ * frame ranges overlapping by fft_size-hop samples; only the range ending at the true end of the file can produce the
+ * short last frame (fft.rs:148-159).  *n_out = number of virtual files (<= n_files * n_devices). */
+int aus_plan_shards(const uint64_t *offsets, const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop,
+                    int n_devices, uint64_t *vf_off, uint64_t *vf_len, uint64_t *vf_row, int *vf_dev, size_t cap,
+                    size_t *n_out);
+
 /* ---- STFT with spectra written out (kernel K2) ------------------------------------------------------- */
 /* spectrum/fft.rs:119 `rstft` */
 int aus_rstft(aus_ctx *ctx, const double *audio, size_t n_samples, size_t fft_size, size_t hop, int window_type,
