@@ -892,7 +892,7 @@ extern "C" int aus_plan_shards(const uint64_t *offsets, const uint64_t *lengths,
 // No collective: frames and files are independent.  Host threads, one per device, each running the batch
 // entry point on its run of virtual files; the ordered gather is the row offsets of the plan (like mp.rs:100-116).
 static std::mutex g_multi_mu;
-static std::map<int, aus_ctx *> g_multi_ctx;
+static std::map<std::pair<int, int>, aus_ctx *> g_multi_ctx;   // (device, slot): one context per host thread
 
 extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
                                        const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr,
@@ -916,11 +916,11 @@ extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const 
             aus_ctx *ctx = nullptr;
             {
                 std::lock_guard<std::mutex> lk(g_multi_mu);
-                auto it = g_multi_ctx.find(dev);
+                auto it = g_multi_ctx.find({dev, d});
                 if (it == g_multi_ctx.end()) {
                     rc[d] = aus_ctx_create(dev, &ctx);
                     if (rc[d] != AUS_OK) { msg[d] = g_err; return; }
-                    g_multi_ctx[dev] = ctx;
+                    g_multi_ctx[{dev, d}] = ctx;
                 } else ctx = it->second;
             }
             uint64_t s0 = UINT64_MAX;                 // re-base the device's span to its first sample

@@ -195,3 +195,124 @@ def test_error_codes(ctx, aus, orc):
     assert "incorrect length" in e.value.error_msg and "1025" in e.value.error_msg
     with pytest.raises(aus.SpectrumError):
         ctx.irfft(S[0, :-2], 2048)
+
+
+# ------------------------------------------------------------------------------------------------ golden fixtures
+def test_golden_fixtures(ctx, orc):
+    """CUDA path vs the committed oracle outputs (tests/golden/golden_v1.npz, made by tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+    assert_features(ctx.stft_features(g["c1_x"], 2048, 512, orc.HANNING, SR), g["c1_feat"], RTOL64, "golden c1")
+    assert_spectra(ctx.rstft(g["c1_x"], 2048, 512, orc.HANNING)[[0, 7, -1]], g["c1_spec"], RTOL64, "golden c1 spectra")
+    assert_features(ctx.stft_analysis(g["mp_x"], 2048, SR, 8), g["mp_feat"], RTOL64, "golden mp")
+    for ch in range(2):
+        S = ctx.rstft(g[f"c2_x{ch}"], 4096, 1024, orc.HAMMING)
+        assert_spectra(S[0], g[f"c2_spec{ch}_first"], RTOL64, "golden c2 spectrum")
+        y = ctx.irstft(S, 4096, 1024, orc.HAMMING)
+        assert np.max(np.abs(y - g[f"c2_audio{ch}"])) <= RTOL64 * np.max(np.abs(g[f"c2_audio{ch}"]))
+    lens = g["c3_lens"]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    got, _ = ctx.stft_features_batch(g["c3_x"], offs, lens, 1024, 256, orc.HANNING, SR)
+    assert_features(got, g["c3_feat"], RTOL64, "golden c3")
+    assert_features(ctx.stft_features(g["c4_x"], 16384, 4096, orc.HANNING, SR), g["c4_feat"], RTOL64, "golden c4")
+    assert_features(ctx.analyzer_batch(g["an_mag"], 2048, SR), g["an_feat"], RTOL64, "golden analyzer")
+
+
+def test_reference_named_free_functions(aus, orc):
+    """The mirror modules (same names as the crate) run on the default context."""
+    x = orc.synth_signal(6000, SR, seed=13)
+    S = aus.spectrum.rstft(x, 1024, 512, aus.WindowType.Hamming)
+    assert_spectra(S, orc.rstft(x, 1024, 512, orc.HAMMING), RTOL64, "spectrum.rstft")
+    mag, ph = aus.spectrum.complex_to_polar_rstft(S)
+    a = aus.analysis.analyzer(mag[2], 1024, SR)
+    ref = orc.analyzer(np.abs(S[2]), 1024, SR)
+    assert_features(a.as_array()[None], ref.as_array()[None], RTOL64, "analysis.analyzer")
+    f = aus.spectrum.rfftfreq(1024, SR)
+    assert aus.analysis.spectral_centroid(mag[2], f) == pytest.approx(ref.spectral_centroid, rel=RTOL64)
+    assert aus.analysis.spectral_roll_off_point(mag[2], f, 0.9) == ref.spectral_roll_off_90
+    assert aus.analysis.spectral_slope_region(mag[2], f, 1000.0, 5000.0, SR) == pytest.approx(ref.spectral_slope_1_5_khz, rel=RTOL64)
+    res = aus.mp.stft_analysis(x, 1024, SR, 4)
+    assert len(res) == orc.num_frames(x.size, 1024, 512)
+    assert res[1].spectral_entropy == pytest.approx(orc.stft_analysis(x, 1024, SR)[1, 4], rel=RTOL64)
+    back = aus.spectrum.irstft(aus.spectrum.polar_to_complex_rstft(mag, ph), 1024, 512, aus.WindowType.Hamming)
+    assert np.max(np.abs(back - orc.irstft(S, 1024, 512, orc.HAMMING))) <= 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ sharded path
+@pytest.mark.parametrize("n_dev", [2, 3])
+def test_multi_device_entry_point(aus, orc, n_dev):
+    """aus_stft_features_multi: host threads + shard plan.  On a 1-GPU box every slot maps to device 0."""
+    import torch
+    have = torch.cuda.device_count()
+    devices = [i % have for i in range(n_dev)]
+    x = orc.synth_signal(70000, SR, seed=14)
+    got = aus.stft_features_multi(devices, x, [0], [x.size], 2048, 512, orc.HANNING, SR)
+    assert_features(got, orc.stft_features(x, 2048, 512, orc.HANNING, SR), RTOL64, "multi single file")
+    lens = [5000, 0, 12000, 2048, 30000]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    audio = orc.synth_signal(sum(lens), SR, seed=15)
+    got = aus.stft_features_multi(devices, audio, offs, lens, 1024, 256, orc.HAMMING, SR)
+    ref = np.concatenate([orc.stft_features(audio[o:o + n], 1024, 256, orc.HAMMING, SR) for o, n in zip(offs, lens)])
+    assert_features(got, ref, RTOL64, "multi batch")
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_device_resident(ctx, orc):
+    """BASELINE-sized inputs, checked through size-independent properties plus oracle spot checks:
+    config 3 (1000 x 30 s, fft 1024 / hop 256) and config 2 (10 min, fft 4096 / hop 1024 round trip)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    ctx.use_torch_stream()          # torch ops below must be stream-ordered with the library's kernels
+    # ---- config 3: one launch for 1000 clips
+    n_clips, n = 1000, 30 * SR
+    d = torch.empty(n_clips * n, dtype=torch.float64, device=dev)
+    for i in range(n_clips):
+        ctx.synth_dev(d[i * n:(i + 1) * n], 0, SR, orc.file_freq(i), 0, i, "f64")
+    lens = np.full(n_clips, n, dtype=np.uint64)
+    offs = np.arange(n_clips, dtype=np.uint64) * np.uint64(n)
+    F1 = orc.num_frames(n, 1024, 256)
+    out = torch.empty((n_clips * F1, 14), dtype=torch.float64, device=dev)
+    ctx.stft_features_batch_dev(d, offs, lens, 1024, 256, orc.HANNING, SR, "f64", out)
+    out2 = torch.empty_like(out)
+    ctx.stft_features_batch_dev(d, offs, lens, 1024, 256, orc.HANNING, SR, "f64", out2)
+    torch.cuda.synchronize()
+    assert out.shape[0] == 5165000
+    assert torch.equal(out, out2)                                   # deterministic: no atomics, fixed reduction order
+    assert bool(torch.isfinite(out).all())
+    roll = out[:, 6:10]
+    assert bool((roll[:, 1:] >= roll[:, :-1]).all())                # roll-off points are ordered
+    bins = roll / (SR / 1024)
+    assert float((bins - bins.round()).abs().max()) < 1e-9          # ... and sit on the rfftfreq grid
+    assert bool((out[:, 5] > 0).all()) and bool((out[:, 5] <= 1 + 1e-12).all())     # flatness in (0, 1]
+    assert bool((out[:, 4] > 0).all()) and bool((out[:, 4] <= np.log2(513) + 1e-9).all())   # 0 < entropy <= log2 K
+    for clip in (0, 417, 999):                                      # spot checks against the oracle (device-made input)
+        x = d[clip * n:(clip + 1) * n].cpu().numpy()
+        ref = orc.stft_features(x, 1024, 256, orc.HANNING, SR)
+        assert_features(out[clip * F1:(clip + 1) * F1].cpu().numpy(), ref, RTOL64, f"clip {clip}")
+    del d, out, out2
+    # ---- config 2: linearity of the STFT and the round trip at full length
+    n, N, hop = 600 * SR, 4096, 1024
+    F, K = orc.num_frames(n, N, hop), N // 2 + 1
+    xa, xb = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(2))
+    ctx.synth_dev(xa, 0, SR, 440.0, 0, 100, "f64")
+    ctx.synth_dev(xb, 0, SR, 880.0, 0, 101, "f64")
+    l1, o1 = np.array([n], dtype=np.uint64), np.array([0], dtype=np.uint64)
+    Sa, Sb, Sc = (torch.empty((F, K, 2), dtype=torch.float64, device=dev) for _ in range(3))
+    ctx.stft_features_batch_dev(xa, o1, l1, N, hop, orc.HAMMING, SR, "f64", None, Sa)
+    ctx.stft_features_batch_dev(xb, o1, l1, N, hop, orc.HAMMING, SR, "f64", None, Sb)
+    xc = (0.75 * xa - 1.5 * xb).contiguous()
+    ctx.stft_features_batch_dev(xc, o1, l1, N, hop, orc.HAMMING, SR, "f64", None, Sc)
+    torch.cuda.synchronize()
+    peak = float(Sc.abs().max())
+    assert float((Sc - (0.75 * Sa - 1.5 * Sb)).abs().max()) <= 1e-12 * peak        # linearity
+    y = torch.empty(N + hop * (F - 1), dtype=torch.float64, device=dev)
+    ctx.irstft_dev(Sa, F, N, hop, orc.HAMMING, "f64", y, True)
+    torch.cuda.synchronize()
+    assert float(y.max()) == pytest.approx(10 ** (-6 / 20), rel=1e-12)               # peak-normalised to -6 dBFS
+    body = slice(N, n - 2 * N)
+    gain = float((y[body] * xa[body]).sum() / (xa[body] * xa[body]).sum())
+    err = float((y[body] / gain - xa[body]).abs().max())
+    assert 0.0 < err < 1e-9, err                                                     # reconstructs up to the gain
+    ref0 = orc.rstft(xa[:3 * N].cpu().numpy(), N, hop, orc.HAMMING)[:2]              # first frames against the oracle
+    got0 = torch.view_as_complex(Sa[:2].contiguous()).cpu().numpy()
+    assert_spectra(got0, ref0, RTOL64, "config 2 first frames")
