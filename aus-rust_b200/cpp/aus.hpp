@@ -1,0 +1,141 @@
+// aus.hpp -- C++ host mirror of the `aus` crate's public API for the STFT + spectral-feature path, header-only, over the
+// C ABI of include/aus_b200.h.  Same names, argument order and error behaviour as the Rust functions cited (paths
+// under the reference's src/): Vec<f64> <-> std::vector<double>, Vec<Vec<Complex<f64>>> <-> vector<vector<complex>>,
+// Result<_, SpectrumError> <-> throws aus::spectrum::SpectrumError, Rust panics <-> throws std::runtime_error.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/aus_b200.h"
+
+namespace aus {
+
+enum class WindowType { Bartlett = 0, Blackman, Hanning, Hamming, Rectangular };   // window.rs:9-15
+
+namespace detail {
+struct Ctx {
+    aus_ctx *h = nullptr;
+    Ctx() {
+        if (aus_ctx_create(0, &h) != AUS_OK) throw std::runtime_error(std::string("aus_b200: ") + aus_last_error());
+    }
+    ~Ctx() { aus_ctx_destroy(h); }
+};
+inline aus_ctx *ctx() {
+    thread_local Ctx c;            // one context per calling thread: the reference's functions are re-entrant
+    return c.h;
+}
+inline void ok(int rc) {
+    if (rc != AUS_OK) throw std::runtime_error(std::string("aus_b200: ") + aus_last_error());
+}
+}  // namespace detail
+
+inline std::vector<double> generate_window(WindowType t, size_t n) {               // window.rs:110
+    std::vector<double> w(n);
+    detail::ok(aus_generate_window((int)t, n, w.data()));
+    return w;
+}
+
+namespace spectrum {
+using cplx = std::complex<double>;
+struct SpectrumError : std::runtime_error {                                          // fft.rs:16-19
+    std::string error_msg;
+    explicit SpectrumError(const std::string &m) : std::runtime_error(m), error_msg(m) {}
+};
+inline void ok_or_spectrum_error(int rc) {
+    if (rc == AUS_ERR_SIZE) throw SpectrumError(aus_last_error());
+    detail::ok(rc);
+}
+
+inline std::vector<cplx> rfft(const std::vector<double> &audio, size_t fft_size) {    // fft.rs:37
+    if (audio.size() != fft_size) throw std::runtime_error("rfft: audio must have fft_size samples");
+    std::vector<cplx> out(fft_size / 2 + 1);
+    detail::ok(aus_rfft(detail::ctx(), audio.data(), fft_size, AUS_F64, reinterpret_cast<double *>(out.data())));
+    return out;
+}
+inline std::vector<double> irfft(const std::vector<cplx> &spectrum, size_t fft_size) {   // fft.rs:66
+    std::vector<double> out(fft_size);
+    ok_or_spectrum_error(aus_irfft(detail::ctx(), reinterpret_cast<const double *>(spectrum.data()), spectrum.size(),
+                                   fft_size, AUS_F64, out.data()));
+    return out;
+}
+inline std::vector<std::vector<cplx>> rstft(const std::vector<double> &audio, size_t fft_size, size_t hop_size,
+                                            WindowType window_type) {                 // fft.rs:119
+    const size_t K = fft_size / 2 + 1, F = aus_num_frames(audio.size(), fft_size, hop_size);
+    std::vector<cplx> flat(F * K);
+    detail::ok(aus_rstft(detail::ctx(), audio.data(), audio.size(), fft_size, hop_size, (int)window_type, AUS_F64,
+                         reinterpret_cast<double *>(flat.data())));
+    std::vector<std::vector<cplx>> out(F);
+    for (size_t f = 0; f < F; ++f) out[f].assign(flat.begin() + f * K, flat.begin() + (f + 1) * K);
+    return out;
+}
+inline std::vector<double> irstft(const std::vector<std::vector<cplx>> &spectrogram, size_t fft_size, size_t hop_size,
+                                  WindowType window_type) {                           // fft.rs:204
+    const size_t K = fft_size / 2 + 1;
+    for (size_t i = 0; i < spectrogram.size(); ++i)                                    // fft.rs:217-219
+        if (spectrogram[i].size() != K)
+            throw SpectrumError("The spectrum at frame " + std::to_string(i) + " has an incorrect length. It should be " +
+                                std::to_string(K) + ", but it is actually " + std::to_string(spectrogram[i].size()) + ".");
+    std::vector<cplx> flat;
+    flat.reserve(spectrogram.size() * K);
+    for (auto &r : spectrogram) flat.insert(flat.end(), r.begin(), r.end());
+    std::vector<double> out(aus_irstft_len(spectrogram.size(), fft_size, hop_size));
+    ok_or_spectrum_error(aus_irstft(detail::ctx(), reinterpret_cast<const double *>(flat.data()), spectrogram.size(), K,
+                                    fft_size, hop_size, (int)window_type, AUS_F64, 1, out.data()));
+    return out;
+}
+inline std::pair<std::vector<std::vector<double>>, std::vector<std::vector<double>>> complex_to_polar_rstft(
+    const std::vector<std::vector<cplx>> &spectrogram) {                              // fft_tools.rs:41
+    const size_t F = spectrogram.size(), K = F ? spectrogram[0].size() : 0;
+    std::vector<cplx> flat;
+    for (auto &r : spectrogram) flat.insert(flat.end(), r.begin(), r.end());
+    std::vector<double> m(F * K), p(F * K);
+    detail::ok(aus_complex_to_polar(detail::ctx(), reinterpret_cast<const double *>(flat.data()), F * K, m.data(), p.data()));
+    std::vector<std::vector<double>> mm(F), pp(F);
+    for (size_t f = 0; f < F; ++f) {
+        mm[f].assign(m.begin() + f * K, m.begin() + (f + 1) * K);
+        pp[f].assign(p.begin() + f * K, p.begin() + (f + 1) * K);
+    }
+    return {mm, pp};
+}
+inline std::vector<double> rfftfreq(size_t fft_size, uint32_t sample_rate) {          // fft_tools.rs:199
+    std::vector<double> f(fft_size / 2 + 1);
+    detail::ok(aus_rfftfreq(fft_size, sample_rate, f.data()));
+    return f;
+}
+}  // namespace spectrum
+
+namespace analysis {
+using Analysis = aus_analysis;                                                        // analyzer.rs:9-24
+inline Analysis analyzer(const std::vector<double> &magnitude_spectrum, size_t fft_size, uint32_t sample_rate) {   // analyzer.rs:41
+    if (magnitude_spectrum.size() != fft_size / 2 + 1) throw std::runtime_error("analyzer: wrong spectrum length");
+    Analysis a;
+    detail::ok(aus_analyzer_batch(detail::ctx(), magnitude_spectrum.data(), 1, fft_size, sample_rate, AUS_F64,
+                                  reinterpret_cast<double *>(&a)));
+    return a;
+}
+}  // namespace analysis
+
+namespace mp {
+// mp.rs:26 -- hop = fft_size/2, Hamming; max_num_threads accepted and ignored
+inline std::vector<analysis::Analysis> stft_analysis(std::vector<double> &audio, size_t fft_size, uint32_t sample_rate,
+                                                     std::optional<size_t> max_num_threads) {
+    std::vector<analysis::Analysis> out(aus_num_frames(audio.size(), fft_size, fft_size / 2));
+    detail::ok(aus_stft_analysis(detail::ctx(), audio.data(), audio.size(), fft_size, sample_rate,
+                                 max_num_threads.value_or(0), out.data()));
+    return out;
+}
+// general hop / window (new entry point)
+inline std::vector<analysis::Analysis> stft_features(const std::vector<double> &audio, size_t fft_size, size_t hop_size,
+                                                     WindowType window_type, uint32_t sample_rate) {
+    std::vector<analysis::Analysis> out(aus_num_frames(audio.size(), fft_size, hop_size));
+    detail::ok(aus_stft_features(detail::ctx(), audio.data(), audio.size(), fft_size, hop_size, (int)window_type,
+                                 sample_rate, AUS_F64, reinterpret_cast<double *>(out.data())));
+    return out;
+}
+}  // namespace mp
+
+}  // namespace aus

@@ -1,0 +1,315 @@
+//! Drop-in replacement for the STFT + spectral-feature path of `aus` (fleximeter/aus-rust 0.1.7) on B200.
+//!
+//! Every public function below has the *same signature* as the reference function it replaces (cited by
+//! `file:line` of the reference's `src/`), and forwards to the C ABI of `include/aus_b200.h`.  All arithmetic
+//! happens in the CUDA library; this file only reshapes `Vec`s.  There is no CPU fallback: if no B200 is present the
+//! functions panic with the library's error message (the reference's own failure mode on this path is a panic too).
+//!
+//! NOT compiled in the repository's build environment (no Rust toolchain there); kept deliberately thin.
+#![allow(clippy::needless_range_loop)]
+
+use num::Complex;
+use std::cell::RefCell;
+use std::ffi::CStr;
+use std::os::raw::{c_char, c_int, c_void};
+
+// ------------------------------------------------------------------------------------------------ FFI (include/aus_b200.h)
+#[repr(C)]
+pub struct AusCtx { _private: [u8; 0] }
+
+/// `#[repr(C)]` mirror of `aus_analysis`; `Analysis` itself has Rust-unspecified layout (analyzer.rs:9-24).
+#[repr(C)]
+#[derive(Copy, Clone, Default)]
+struct AusAnalysis { v: [f64; 14] }
+
+extern "C" {
+    fn aus_last_error() -> *const c_char;
+    fn aus_ctx_create(device: c_int, out: *mut *mut AusCtx) -> c_int;
+    fn aus_ctx_destroy(ctx: *mut AusCtx);
+    fn aus_num_frames(n_samples: usize, fft_size: usize, hop: usize) -> usize;
+    fn aus_irstft_len(n_frames: usize, fft_size: usize, hop: usize) -> usize;
+    fn aus_generate_window(window_type: c_int, window_length: usize, out: *mut f64) -> c_int;
+    fn aus_rfftfreq(fft_size: usize, sample_rate: u32, out: *mut f64) -> c_int;
+    fn aus_stft_analysis(ctx: *mut AusCtx, audio: *const f64, n: usize, fft_size: usize, sample_rate: u32,
+                         max_num_threads: usize, out: *mut AusAnalysis) -> c_int;
+    fn aus_stft_features(ctx: *mut AusCtx, audio: *const f64, n: usize, fft_size: usize, hop: usize, window: c_int,
+                         sample_rate: u32, precision: c_int, features: *mut f64) -> c_int;
+    fn aus_rstft(ctx: *mut AusCtx, audio: *const f64, n: usize, fft_size: usize, hop: usize, window: c_int,
+                 precision: c_int, spectra: *mut f64) -> c_int;
+    fn aus_rfft(ctx: *mut AusCtx, audio: *const f64, fft_size: usize, precision: c_int, spectrum: *mut f64) -> c_int;
+    fn aus_irstft(ctx: *mut AusCtx, spectra: *const f64, n_frames: usize, frame_len: usize, fft_size: usize, hop: usize,
+                  window: c_int, precision: c_int, normalize: c_int, audio: *mut f64) -> c_int;
+    fn aus_irfft(ctx: *mut AusCtx, spectrum: *const f64, spectrum_len: usize, fft_size: usize, precision: c_int,
+                 audio: *mut f64) -> c_int;
+    fn aus_complex_to_polar(ctx: *mut AusCtx, spectra: *const f64, n: usize, mag: *mut f64, ph: *mut f64) -> c_int;
+    fn aus_polar_to_complex(ctx: *mut AusCtx, mag: *const f64, ph: *const f64, n: usize, spectra: *mut f64) -> c_int;
+    fn aus_analyzer_batch(ctx: *mut AusCtx, mags: *const f64, n_frames: usize, fft_size: usize, sample_rate: u32,
+                          precision: c_int, features: *mut f64) -> c_int;
+}
+
+const AUS_ERR_SIZE: c_int = -4;
+const F64: c_int = 0;
+
+struct Ctx(*mut AusCtx);
+impl Drop for Ctx { fn drop(&mut self) { unsafe { aus_ctx_destroy(self.0) } } }
+thread_local! { static CTX: RefCell<Option<Ctx>> = RefCell::new(None); }
+
+fn last_error() -> String { unsafe { CStr::from_ptr(aus_last_error()).to_string_lossy().into_owned() } }
+
+/// One context per calling thread (the reference's functions are stateless and re-entrant).
+fn with_ctx<R>(f: impl FnOnce(*mut AusCtx) -> R) -> R {
+    CTX.with(|c| {
+        let mut c = c.borrow_mut();
+        if c.is_none() {
+            let dev = std::env::var("AUS_B200_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+            let mut h: *mut AusCtx = std::ptr::null_mut();
+            let rc = unsafe { aus_ctx_create(dev, &mut h) };
+            if rc != 0 { panic!("aus_b200: {}", last_error()); }
+            *c = Some(Ctx(h));
+        }
+        f(c.as_ref().unwrap().0)
+    })
+}
+fn ok(rc: c_int) { if rc != 0 { panic!("aus_b200: {}", last_error()); } }
+
+// ------------------------------------------------------------------------------------------------ window.rs
+/// window.rs:9-15
+#[derive(Copy, Clone)]
+pub enum WindowType { Bartlett, Blackman, Hanning, Hamming, Rectangular }
+fn wcode(w: WindowType) -> c_int { w as c_int }
+
+/// window.rs:110
+pub fn generate_window(window_type: WindowType, window_length: usize) -> Vec<f64> {
+    let mut w = vec![0.0; window_length];
+    ok(unsafe { aus_generate_window(wcode(window_type), window_length, w.as_mut_ptr()) });
+    w
+}
+pub fn generate_window_bartlett(n: usize) -> Vec<f64> { generate_window(WindowType::Bartlett, n) }       // window.rs:26
+pub fn generate_window_blackman(n: usize) -> Vec<f64> { generate_window(WindowType::Blackman, n) }       // window.rs:43
+pub fn generate_window_hanning(n: usize) -> Vec<f64> { generate_window(WindowType::Hanning, n) }         // window.rs:61
+pub fn generate_window_hamming(n: usize) -> Vec<f64> { generate_window(WindowType::Hamming, n) }         // window.rs:78
+pub fn generate_window_rectangular(n: usize) -> Vec<f64> { generate_window(WindowType::Rectangular, n) } // window.rs:95
+
+// ------------------------------------------------------------------------------------------------ spectrum
+pub mod spectrum {
+    use super::*;
+
+    /// spectrum/fft.rs:16-19
+    #[derive(Debug, Clone)]
+    pub struct SpectrumError { pub error_msg: String }
+
+    fn rows(flat: Vec<f64>, k: usize) -> Vec<Vec<Complex<f64>>> {
+        flat.chunks_exact(2 * k).map(|r| r.chunks_exact(2).map(|c| Complex::new(c[0], c[1])).collect()).collect()
+    }
+    fn flat(s: &[Vec<Complex<f64>>]) -> Vec<f64> {
+        let mut v = Vec::with_capacity(s.len() * s.first().map_or(0, |r| r.len()) * 2);
+        for r in s { for c in r { v.push(c.re); v.push(c.im); } }
+        v
+    }
+
+    /// spectrum/fft.rs:37
+    pub fn rfft(audio: &[f64], fft_size: usize) -> Vec<Complex<f64>> {
+        assert_eq!(audio.len(), fft_size, "rfft: zero-pad the audio to fft_size first (fft.rs:23-24)");
+        let k = fft_size / 2 + 1;
+        let mut out = vec![0.0; 2 * k];
+        with_ctx(|c| ok(unsafe { aus_rfft(c, audio.as_ptr(), fft_size, F64, out.as_mut_ptr()) }));
+        out.chunks_exact(2).map(|c| Complex::new(c[0], c[1])).collect()
+    }
+
+    /// spectrum/fft.rs:66
+    pub fn irfft(spectrum: &[Complex<f64>], fft_size: usize) -> Result<Vec<f64>, SpectrumError> {
+        let s: Vec<f64> = spectrum.iter().flat_map(|c| [c.re, c.im]).collect();
+        let mut out = vec![0.0; fft_size];
+        let rc = with_ctx(|c| unsafe { aus_irfft(c, s.as_ptr(), spectrum.len(), fft_size, F64, out.as_mut_ptr()) });
+        if rc == AUS_ERR_SIZE { return Err(SpectrumError { error_msg: last_error() }); }
+        ok(rc);
+        Ok(out)
+    }
+
+    /// spectrum/fft.rs:119
+    pub fn rstft(audio: &Vec<f64>, fft_size: usize, hop_size: usize, window_type: WindowType) -> Vec<Vec<Complex<f64>>> {
+        let k = fft_size / 2 + 1;
+        let f = unsafe { aus_num_frames(audio.len(), fft_size, hop_size) };
+        let mut out = vec![0.0; f * k * 2];
+        with_ctx(|c| ok(unsafe {
+            aus_rstft(c, audio.as_ptr(), audio.len(), fft_size, hop_size, wcode(window_type), F64, out.as_mut_ptr())
+        }));
+        rows(out, k)
+    }
+
+    /// spectrum/fft.rs:204
+    pub fn irstft(spectrogram: &Vec<Vec<Complex<f64>>>, fft_size: usize, hop_size: usize, window_type: WindowType)
+                  -> Result<Vec<f64>, SpectrumError> {
+        let k = fft_size / 2 + 1;
+        for (i, r) in spectrogram.iter().enumerate() {      // fft.rs:217-219: per-frame length check
+            if r.len() != k {
+                return Err(SpectrumError { error_msg: format!(
+                    "The spectrum at frame {} has an incorrect length. It should be {}, but it is actually {}.", i, k, r.len()) });
+            }
+        }
+        let s = flat(spectrogram);
+        let mut out = vec![0.0; unsafe { aus_irstft_len(spectrogram.len(), fft_size, hop_size) }];
+        let rc = with_ctx(|c| unsafe {
+            aus_irstft(c, s.as_ptr(), spectrogram.len(), k, fft_size, hop_size, wcode(window_type), F64, 1, out.as_mut_ptr())
+        });
+        if rc == AUS_ERR_SIZE { return Err(SpectrumError { error_msg: last_error() }); }
+        ok(rc);                                             // empty spectrogram: the reference panics too (fft.rs:208)
+        Ok(out)
+    }
+
+    /// spectrum/fft_tools.rs:21
+    pub fn complex_to_polar_rfft(spectrum: &Vec<Complex<f64>>) -> (Vec<f64>, Vec<f64>) {
+        let s: Vec<f64> = spectrum.iter().flat_map(|c| [c.re, c.im]).collect();
+        let (mut m, mut p) = (vec![0.0; spectrum.len()], vec![0.0; spectrum.len()]);
+        with_ctx(|c| ok(unsafe { aus_complex_to_polar(c, s.as_ptr(), spectrum.len(), m.as_mut_ptr(), p.as_mut_ptr()) }));
+        (m, p)
+    }
+
+    /// spectrum/fft_tools.rs:41
+    pub fn complex_to_polar_rstft(spectrogram: &Vec<Vec<Complex<f64>>>) -> (Vec<Vec<f64>>, Vec<Vec<f64>>) {
+        let k = spectrogram.first().map_or(0, |r| r.len());
+        let s = flat(spectrogram);
+        let n = s.len() / 2;
+        let (mut m, mut p) = (vec![0.0; n], vec![0.0; n]);
+        with_ctx(|c| ok(unsafe { aus_complex_to_polar(c, s.as_ptr(), n, m.as_mut_ptr(), p.as_mut_ptr()) }));
+        (m.chunks(k.max(1)).map(|r| r.to_vec()).collect(), p.chunks(k.max(1)).map(|r| r.to_vec()).collect())
+    }
+
+    /// spectrum/fft_tools.rs:131
+    pub fn polar_to_complex_rfft(magnitude_spectrum: &Vec<f64>, phase_spectrum: &Vec<f64>) -> Result<Vec<Complex<f64>>, SpectrumError> {
+        if magnitude_spectrum.len() != phase_spectrum.len() {
+            return Err(SpectrumError { error_msg: format!(
+                "The magnitude spectrum and phase spectrum do not have the same length. The magnitude spectrum has len {} and the phase spectrum has len {}.",
+                magnitude_spectrum.len(), phase_spectrum.len()) });
+        }
+        let mut out = vec![0.0; 2 * magnitude_spectrum.len()];
+        with_ctx(|c| ok(unsafe {
+            aus_polar_to_complex(c, magnitude_spectrum.as_ptr(), phase_spectrum.as_ptr(), magnitude_spectrum.len(), out.as_mut_ptr())
+        }));
+        Ok(out.chunks_exact(2).map(|c| Complex::new(c[0], c[1])).collect())
+    }
+
+    /// spectrum/fft_tools.rs:164
+    pub fn polar_to_complex_rstft(magnitude_spectrogram: &Vec<Vec<f64>>, phase_spectrogram: &Vec<Vec<f64>>)
+                                  -> Result<Vec<Vec<Complex<f64>>>, SpectrumError> {
+        if magnitude_spectrogram.len() != phase_spectrogram.len() {
+            return Err(SpectrumError { error_msg: format!(
+                "The magnitude spectrogram and phase spectrogram do not have the same length. The magnitude spectrogram has len {} and the phase spectrogram has len {}.",
+                magnitude_spectrogram.len(), phase_spectrogram.len()) });
+        }
+        magnitude_spectrogram.iter().zip(phase_spectrogram.iter()).map(|(m, p)| polar_to_complex_rfft(m, p)).collect()
+    }
+
+    /// spectrum/fft_tools.rs:199
+    pub fn rfftfreq(fft_size: usize, sample_rate: u32) -> Vec<f64> {
+        let mut f = vec![0.0; fft_size / 2 + 1];
+        ok(unsafe { aus_rfftfreq(fft_size, sample_rate, f.as_mut_ptr()) });
+        f
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ analysis
+pub mod analysis {
+    use super::*;
+
+    /// analysis/analyzer.rs:9-24
+    #[derive(Copy, Clone)]
+    pub struct Analysis {
+        pub spectral_centroid: f64,
+        pub spectral_variance: f64,
+        pub spectral_skewness: f64,
+        pub spectral_kurtosis: f64,
+        pub spectral_entropy: f64,
+        pub spectral_flatness: f64,
+        pub spectral_roll_off_50: f64,
+        pub spectral_roll_off_75: f64,
+        pub spectral_roll_off_90: f64,
+        pub spectral_roll_off_95: f64,
+        pub spectral_slope: f64,
+        pub spectral_slope_0_1_khz: f64,
+        pub spectral_slope_1_5_khz: f64,
+        pub spectral_slope_0_5_khz: f64,
+    }
+    pub(crate) fn from_row(v: &[f64]) -> Analysis {     // field-by-field copy from the repr(C) row
+        Analysis {
+            spectral_centroid: v[0], spectral_variance: v[1], spectral_skewness: v[2], spectral_kurtosis: v[3],
+            spectral_entropy: v[4], spectral_flatness: v[5], spectral_roll_off_50: v[6], spectral_roll_off_75: v[7],
+            spectral_roll_off_90: v[8], spectral_roll_off_95: v[9], spectral_slope: v[10],
+            spectral_slope_0_1_khz: v[11], spectral_slope_1_5_khz: v[12], spectral_slope_0_5_khz: v[13],
+        }
+    }
+
+    /// analysis/analyzer.rs:41
+    pub fn analyzer(magnitude_spectrum: &Vec<f64>, fft_size: usize, sample_rate: u32) -> Analysis {
+        assert_eq!(magnitude_spectrum.len(), fft_size / 2 + 1);
+        let mut out = [0.0f64; 14];
+        with_ctx(|c| ok(unsafe {
+            aus_analyzer_batch(c, magnitude_spectrum.as_ptr(), 1, fft_size, sample_rate, F64, out.as_mut_ptr())
+        }));
+        from_row(&out)
+    }
+
+    /// spectral_analysis_tools.rs:273
+    pub fn make_power_spectrum(magnitude_spectrum: &Vec<f64>) -> Vec<f64> {
+        magnitude_spectrum.iter().map(|m| m * m).collect()
+    }
+
+    // The single-feature wrappers (spectral_analysis_tools.rs:306-471) take the bin frequencies as an argument; the
+    // device path needs the rfftfreq grid the reference's own callers pass (analyzer.rs:46).
+    fn one(m: &Vec<f64>, freqs: Option<&Vec<f64>>, sample_rate: Option<u32>) -> Analysis {
+        let fft_size = 2 * (m.len() - 1);
+        let sr = sample_rate.unwrap_or_else(|| freqs.map_or(44100, |f| (f[1] * fft_size as f64).round() as u32));
+        analyzer(m, fft_size, sr)
+    }
+    pub fn spectral_centroid(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_centroid }   // :306
+    pub fn spectral_entropy(m: &Vec<f64>) -> f64 { one(m, None, None).spectral_entropy }                                       // :324
+    pub fn spectral_flatness(m: &Vec<f64>) -> f64 { one(m, None, None).spectral_flatness }                                     // :343
+    pub fn spectral_kurtosis(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_kurtosis }   // :362
+    pub fn spectral_skewness(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_skewness }   // :405
+    pub fn spectral_variance(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_variance }   // :466
+    pub fn spectral_slope(m: &Vec<f64>) -> f64 { one(m, None, None).spectral_slope }                                           // :426
+    /// :385 -- the analyzer's roll-off points 0.5 / 0.75 / 0.9 / 0.95 (analyzer.rs:53-56)
+    pub fn spectral_roll_off_point(m: &Vec<f64>, rfft_freqs: &Vec<f64>, n: f64) -> f64 {
+        let a = one(m, Some(rfft_freqs), None);
+        if n == 0.5 { a.spectral_roll_off_50 } else if n == 0.75 { a.spectral_roll_off_75 }
+        else if n == 0.9 { a.spectral_roll_off_90 } else if n == 0.95 { a.spectral_roll_off_95 }
+        else { panic!("aus_b200: roll-off point {} is not one of the analyzer's four", n) }
+    }
+    /// :447 -- the analyzer's bands 0-1k / 1-5k / 0-5k Hz (analyzer.rs:60-62)
+    pub fn spectral_slope_region(m: &Vec<f64>, rfft_freqs: &Vec<f64>, f_lower: f64, f_upper: f64, sample_rate: u32) -> f64 {
+        let a = one(m, Some(rfft_freqs), Some(sample_rate));
+        match (f_lower as i64, f_upper as i64) {
+            (0, 1000) => a.spectral_slope_0_1_khz, (1000, 5000) => a.spectral_slope_1_5_khz, (0, 5000) => a.spectral_slope_0_5_khz,
+            _ => panic!("aus_b200: slope band is not one of the analyzer's three"),
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ mp
+pub mod mp {
+    use super::*;
+    use crate::analysis::Analysis;
+
+    /// mp.rs:26 -- same signature; `audio` is never mutated (as in the reference), `max_num_threads` is ignored.
+    pub fn stft_analysis(audio: &mut Vec<f64>, fft_size: usize, sample_rate: u32, max_num_threads: Option<usize>) -> Vec<Analysis> {
+        let f = unsafe { aus_num_frames(audio.len(), fft_size, fft_size / 2) };
+        let mut rows = vec![AusAnalysis::default(); f];
+        with_ctx(|c| ok(unsafe {
+            aus_stft_analysis(c, audio.as_ptr(), audio.len(), fft_size, sample_rate, max_num_threads.unwrap_or(0), rows.as_mut_ptr())
+        }));
+        rows.iter().map(|r| analysis::from_row(&r.v)).collect()
+    }
+
+    /// New general entry point (hop and window are hard-coded inside mp.rs:42).
+    pub fn stft_features(audio: &[f64], fft_size: usize, hop_size: usize, window_type: WindowType, sample_rate: u32) -> Vec<Analysis> {
+        let f = unsafe { aus_num_frames(audio.len(), fft_size, hop_size) };
+        let mut out = vec![0.0f64; f * 14];
+        with_ctx(|c| ok(unsafe {
+            aus_stft_features(c, audio.as_ptr(), audio.len(), fft_size, hop_size, wcode(window_type), sample_rate, F64, out.as_mut_ptr())
+        }));
+        out.chunks_exact(14).map(analysis::from_row).collect()
+    }
+}
+
+#[allow(dead_code)]
+fn _unused(_: *mut c_void) {}
