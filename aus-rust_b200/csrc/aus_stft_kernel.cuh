@@ -562,12 +562,24 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
                 W[c] = ldg_cx(&p.twNt[i * TPF + t]);
             }
             T plo[4], phi[4];
+            if (!want_feat) {
+                // K2 (spectra only): X replaces Z in place, then the whole row leaves in coalesced stores below
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int i = i0 + c;
+                    Cx<T> Xlo, Xhi;
+                    post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
+                    buf[17 * t + i] = Xlo;
+                    buf[(c == 0 && i0 == 0) ? h0 : h0 - 1 - i] = Xhi;
+                }
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int k = 16 * t + i0 + c;
                 Cx<T> Xlo, Xhi;
                 post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
-                if (spec) { spec[k] = Xlo; spec[M - k] = Xhi; }
+                if (spec) { spec[k] = Xlo; spec[M - k] = Xhi; }      // features AND spectra requested: direct stores
                 plo[c] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
                 phi[c] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
             }
@@ -577,7 +589,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
                 bufT[2 * (17 * t + i) + hp] = plo[c];
                 bufT[2 * ((c == 0 && i0 == 0) ? h0 : h0 - 1 - i) + hp] = phi[c];
             }
-            if (want_feat) {
+            {
                 T mlo[4], mhi[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -595,7 +607,17 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
                 }
             }
         }
-        if (t == TPF - 1) {
+        if (!want_feat) {
+            if (t == TPF - 1) {
+                const Cx<T> A = buf[zslot(M / 2)];
+                buf[zslot(M / 2)] = Cx<T>{A.x + A.x, -(A.y + A.y)};     // X[M/2] = conj(Z[M/2])
+            }
+            group_sync<TPF, C::BLOCK>(grp);
+            if (spec) {
+#pragma unroll 4
+                for (int k = t; k <= M; k += TPF) spec[k] = buf[zslot(k)];   // consecutive lanes -> consecutive bins
+            }
+        } else if (t == TPF - 1) {
             const Cx<T> A = buf[zslot(M / 2)];
             const Cx<T> X = Cx<T>{A.x + A.x, -(A.y + A.y)};             // X[M/2] = conj(Z[M/2])
             if (spec) spec[M / 2] = X;

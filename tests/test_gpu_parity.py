@@ -316,3 +316,33 @@ def test_full_size_properties_device_resident(ctx, orc):
     ref0 = orc.rstft(xa[:3 * N].cpu().numpy(), N, hop, orc.HAMMING)[:2]              # first frames against the oracle
     got0 = torch.view_as_complex(Sa[:2].contiguous()).cpu().numpy()
     assert_spectra(got0, ref0, RTOL64, "config 2 first frames")
+
+
+def test_determinism_all_kernels(ctx, orc):
+    """No atomics on the data path and fixed reduction orders: repeated runs are bit-identical (also a race detector)."""
+    for N, hop in ((64, 16), (1024, 256), (2048, 512), (4096, 1024), (16384, 4096)):
+        x = orc.synth_signal(40 * hop + N + 7, SR, seed=17, file_id=N)
+        for prec in ("f64", "f32"):
+            f1, f2 = (ctx.stft_features(x, N, hop, orc.HAMMING, SR, prec) for _ in range(2))
+            assert np.array_equal(f1, f2, equal_nan=True)
+            S1, S2 = (ctx.rstft(x, N, hop, orc.HAMMING, prec) for _ in range(2))
+            assert np.array_equal(S1, S2)
+            y1, y2 = (ctx.irstft(S1, N, hop, orc.HAMMING, prec) for _ in range(2))
+            assert np.array_equal(y1, y2, equal_nan=True)
+            a1, a2 = (ctx.analyzer_batch(np.abs(S1), N, SR, prec) for _ in range(2))
+            assert np.array_equal(a1, a2, equal_nan=True)
+
+
+def test_features_and_spectra_in_one_call(ctx, orc):
+    """aus_stft_features_batch_dev with both outputs (the mixed path) agrees with the two single-output paths."""
+    import torch
+    ctx.use_torch_stream()
+    x = orc.synth_signal(30000, SR, seed=18)
+    d = torch.from_numpy(x).cuda()
+    F = orc.num_frames(x.size, 2048, 512)
+    feat = torch.empty((F, 14), dtype=torch.float64, device="cuda")
+    spec = torch.empty((F, 1025, 2), dtype=torch.float64, device="cuda")
+    ctx.stft_features_batch_dev(d, [0], [x.size], 2048, 512, orc.HANNING, SR, "f64", feat, spec)
+    torch.cuda.synchronize()
+    assert_features(feat.cpu().numpy(), orc.stft_features(x, 2048, 512, orc.HANNING, SR), RTOL64, "mixed features")
+    assert_spectra(torch.view_as_complex(spec).cpu().numpy(), orc.rstft(x, 2048, 512, orc.HANNING), RTOL64, "mixed spectra")

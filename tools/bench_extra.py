@@ -77,6 +77,20 @@ for prec in ("f64", "f32"):
     features_case("config4: 1 h, large window", 1, 3600 * SR, 16384, 4096, 2, prec)
     features_case("config5 shard: 4 x 1 h", 4, 3600 * SR, 2048, 512, 2, prec)
 
+# K2 at the headline shape: spectra written out (fft 2048 / hop 512), 1 h of audio
+for prec in ("f64", "f32"):
+    esz = 8 if prec == "f64" else 4
+    N, hop, n = 2048, 512, 3600 * SR
+    K, F = N // 2 + 1, frames_of(n, N, hop)
+    x = synth(1, n, prec)
+    spec = torch.empty((F, K, 2), dtype=x.dtype, device=dev)
+    lens, offs = np.array([n], dtype=np.uint64), np.array([0], dtype=np.uint64)
+    ms = timeit(lambda: ctx.stft_features_batch_dev(x, offs, lens, N, hop, 2, SR, prec, None, spec))
+    print(json.dumps({"case": "rstft only: 1 h mono", "kernel": "K2 stft_kernel (spectra out)", "dtype": prec, "fft": N, "hop": hop,
+                      "frames": F, "ms": ms, "frames_per_s": F / ms * 1e3,
+                      "hbm_frac": (n * esz + F * K * 2 * esz) / (ms * 1e-3) / 1e9 / peak}), flush=True)
+    del x, spec
+
 # config 2: rstft -> irstft round trip, 10 min stereo, fft 4096 hop 1024 (Hamming: finite at the ends)
 for prec in ("f64", "f32"):
     esz = 8 if prec == "f64" else 4

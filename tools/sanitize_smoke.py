@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Tiny invocations of every kernel (K1/K2/K3/K4/K5, f64 and f32, one size per FFT structure) for compute-sanitizer."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+import aus_oracle as orc
+import aus_rust_b200 as aus
+
+ctx = aus.Context(0)
+SR = 44100
+sizes = [int(a) for a in sys.argv[1:]] or [64, 512, 1024, 2048, 4096, 16384]
+for N in sizes:
+    hop = N // 4
+    x = orc.synth_signal(3 * N + 101, SR, seed=N)           # 10 frames, the last one short; odd length
+    for prec in ("f64", "f32"):
+        f = ctx.stft_features(x, N, hop, 2, SR, prec)
+        S = ctx.rstft(x, N, hop, 3, prec)
+        y = ctx.irstft(S, N, hop, 3, prec)
+        a = ctx.analyzer_batch(np.abs(S), N, SR, prec)
+        ctx.stft_features(x[1:], N, hop + 1 if hop + 1 <= N else hop, 1, SR, prec)   # odd hop / offset: non-TMA staging
+        print(N, prec, f.shape, S.shape, y.shape, a.shape, float(np.nanmax(np.abs(f))), flush=True)
+lens = [0, 5, 700, 3000]
+offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+print(ctx.stft_features_batch(orc.synth_signal(sum(lens)), offs, lens, 256, 64, 2, SR)[0].shape)
+print("sanitize smoke done")
