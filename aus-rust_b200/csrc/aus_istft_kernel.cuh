@@ -25,6 +25,7 @@ template <typename T> struct IstftParams {
     unsigned long long *file_max_bits;       // [n_files] bit pattern of max(out, 0.0) as f64 (fft.rs:255-258)
     unsigned long long n_seg;
     int hop;
+    unsigned hop_magic;                      // floor(2^32 / hop) + 1: x / hop == umulhi(x, hop_magic) for x < 2^15
     int halo;                                // ceil(N / hop) - 1
     int apply_window;                        // 0: irfft (plain inverse, no window / norm)
     int tma_ok;
@@ -117,36 +118,59 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
 
             frame_fft<T, LOG2N>(buf, p.fwd, t, grp, /*prewindowed=*/true);     // buf: conj(z) in the Z layout
 
-            // ---- window + overlap-add into the output (ascending frame order), finalise completed samples
+            // ---- window + overlap-add into the output (ascending frame order), finalise completed samples.
+            //      u = offset inside the frame.  Frames h - b (b >= 1) also cover the sample iff b <= (N-1-u)/hop, frames
+            //      h + a iff a <= u/hop; both quotients come from a 32-bit multiply-high (p.hop_magic), not a division.
             if (active) {
-                T *out = p.out + ooff;
-#pragma unroll 4
-                for (int i = 0; i < 32; ++i) {
-                    const int n = t + TPF * i;
-                    const Cx<T> z = buf[padi<4>(n)];
-                    const Cx<T> w = ldg_cx(&p.fwd.win2[n]);
+                T *outh = p.out + ooff + h * hop;
+                const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;
+                const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);
+                const bool first_frame = (h == 0), last_frame = (h == F - 1);
+#pragma unroll 1
+                for (int i0 = 0; i0 < 32; i0 += 8) {
+                    // eight butterfly outputs (16 samples) at a time: all partial sums are fetched from L2 first, so the
+                    // read-modify-write latency is paid once per batch instead of once per sample
+                    T prev[8][2];
+                    Cx<T> z[8], w[8];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const long long j = h * hop + 2 * n + e;
-                        if (j < own_lo || j >= own_hi) continue;
-                        T val = (e == 0) ? z.x : -z.y;
-                        if (!p.apply_window) { out[j] = val; continue; }
-                        val *= (T)2 * (e == 0 ? w.x : w.y);                                    // fft.rs:234-236
-                        const long long h_first = (j >= N) ? (j - N) / hop + 1 : 0;
-                        const long long h_last = (j / hop < F - 1) ? j / hop : F - 1;
-                        if (h > h_first) val += __ldcg(out + j);
-                        if (h == h_last) {
-                            T norm = (T)0;                                                     // fft.rs:239-243
-                            for (long long hh = h_first; hh <= h_last; ++hh) {
-                                const int idx = (int)(j - hh * hop);
-                                const Cx<T> ww = ldg_cx(&p.fwd.win2[idx >> 1]);
-                                const T wv = (T)2 * ((idx & 1) ? ww.y : ww.x);
-                                norm += wv * wv;
-                            }
-                            val /= norm;                                                       // fft.rs:250-252
-                            if (val > vmax) vmax = val;                                        // f64::max skips NaN
+                    for (int c = 0; c < 8; ++c) {
+                        const int n = t + TPF * (i0 + c);
+                        z[c] = buf[padi<4>(n)];
+                        w[c] = ldg_cx(&p.fwd.win2[n]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int u = 2 * n + e;
+                            const int back = p.hop == 1 ? N - 1 - u : (int)__umulhi((unsigned)(N - 1 - u), p.hop_magic);
+                            const bool need = p.apply_window && u >= ulo && u < uhi && back > 0 && !first_frame;
+                            prev[c][e] = need ? __ldcg(outh + u) : (T)0;                      // an earlier frame started it
                         }
-                        out[j] = val;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int n = t + TPF * (i0 + c);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int u = 2 * n + e;
+                            if (u < ulo || u >= uhi) continue;
+                            T val = (e == 0) ? z[c].x : -z[c].y;
+                            if (!p.apply_window) { outh[u] = val; continue; }
+                            val = val * ((T)2 * (e == 0 ? w[c].x : w[c].y)) + prev[c][e];      // fft.rs:234-236 + overlap-add
+                            const int fwd = p.hop == 1 ? u : (int)__umulhi((unsigned)u, p.hop_magic);   // u / hop
+                            if (fwd == 0 || last_frame) {                                      // no later frame reaches it
+                                const int back = p.hop == 1 ? N - 1 - u : (int)__umulhi((unsigned)(N - 1 - u), p.hop_magic);
+                                const long long nb = (long long)back < h ? back : h;          // frames h-nb .. h cover it
+                                T norm = (T)0;                                                 // fft.rs:239-243, ascending frames
+                                for (int b = (int)nb; b >= 0; --b) {
+                                    const int idx = u + b * p.hop;
+                                    const Cx<T> ww = ldg_cx(&p.fwd.win2[idx >> 1]);
+                                    const T wv = (T)2 * ((idx & 1) ? ww.y : ww.x);
+                                    norm += wv * wv;
+                                }
+                                val /= norm;                                                   // fft.rs:250-252
+                                if (val > vmax) vmax = val;                                    // f64::max skips NaN
+                            }
+                            outh[u] = val;
+                        }
                     }
                 }
             }
