@@ -301,4 +301,33 @@ __device__ __forceinline__ bool group_any(bool pred, double *scratch, int t, int
     }
 }
 
+// Order-preserving integer key of a non-negative power value (NaN sorts above everything): f64 -> high word,
+// f32 -> bit pattern >> 1 (so it fits the same unsigned compare); key >= *_MIN_NORMAL <=> positive normal or larger.
+__device__ __forceinline__ unsigned power_hi(double x) { return (unsigned)__double2hiint(x); }
+__device__ __forceinline__ unsigned power_hi(float x) { return __float_as_uint(x) >> 1; }
+template <typename T> __device__ __forceinline__ bool power_is_normal(unsigned key) {
+    if constexpr (sizeof(T) == 8) return key - 0x00100000u < 0x7fe00000u;          // [2^-1022, inf)
+    else return key - (0x00800000u >> 1) < ((0x7f800000u - 0x00800000u) >> 1);     // [2^-126, inf)
+}
+// a value with that key (low bits zero): a lower bound of the smallest power, good enough to test q = p / P
+template <typename T> __device__ __forceinline__ T power_from_hi(unsigned key) {
+    if constexpr (sizeof(T) == 8) return __hiloint2double((int)key, 0);
+    else return __uint_as_float(key << 1);
+}
+// min over the TPF threads of a frame group
+template <int TPF, int BLOCK>
+__device__ __forceinline__ unsigned group_min_u32(unsigned v, double *scratch, int t, int grp) {
+    constexpr int W = TPF < 32 ? TPF : 32;
+#pragma unroll
+    for (int off = W / 2; off >= 1; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if constexpr (TPF > 32) {
+        unsigned *s = reinterpret_cast<unsigned *>(scratch);
+        if ((t & 31) == 0) s[t >> 5] = v;
+        group_sync<TPF, BLOCK>(grp);
+        for (int w = 0; w < TPF / 32; ++w) v = min(v, s[w]);
+        group_sync<TPF, BLOCK>(grp);
+    }
+    return v;
+}
+
 }  // namespace aus

@@ -255,7 +255,7 @@ __device__ __forceinline__ void post_twiddle(Cx<T> A, Cx<T> B, Cx<T> W, Cx<T> &X
 // Per-thread running sums of the first feature pass (arithmetic type T; cross-thread combination is always double).
 template <typename T> struct FeatAcc {
     T s_m = 0, s_mk = 0, s_pk = 0, lo_sum = 0, hi_sum = 0, mid = 0;
-    bool bad = false;                                 // some bin is zero / subnormal / non-finite: redo sqrt exactly
+    unsigned pmin = 0x7ff00000u;                      // smallest power bin, as the high word of its f64 pattern (f32: bits >> 1)
     __device__ __forceinline__ void add(T kf, T m, T pw) {
         s_m += m;
         s_mk += m * kf;
@@ -288,13 +288,18 @@ template <typename T, int M, int TPF> __device__ __forceinline__ T &cum_of(Cx<T>
 template <typename T, int LOG2N>
 __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, double *scratch, const double2 *logtab,
                                                const StftParams<T> &p, unsigned long long g, bool active, int t,
-                                               int grp) {
+                                               int grp, bool mags_from_sqrt) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, K = C::K, TPF = C::TPF;
     const int hb = M - 16 * t - 15;                   // first (lowest) bin of this thread's high chunk
 
-    // a zero / subnormal / non-finite power bin somewhere in the frame: redo the magnitude sums with the exact sqrt
-    if (group_any<TPF, C::BLOCK>(acc.bad, scratch, t, grp)) {
+    // The fast sqrt / log2 need positive normal arguments.  Powers are >= 0, so one running minimum (an integer min
+    // per bin) plus the finiteness of the totals decides it for the whole frame: a zero / subnormal / non-finite power
+    // bin sends the frame through the exact library functions, which also reproduce the reference's NaN / -inf rules.
+    // (f32 uses sqrtf / log2f throughout, which handle every argument; K3 gets its magnitudes from the caller.)
+    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt &&
+                       (!power_is_normal<T>(acc.pmin) || !(acc.lo_sum + acc.hi_sum + acc.mid < (T)INFINITY));
+    if (group_any<TPF, C::BLOCK>(bad_p, scratch, t, grp)) {
         acc.s_m = 0;
         acc.s_mk = 0;
 #pragma unroll 1
@@ -336,7 +341,10 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     const T kappa = (T)(S_mk / S_m);
     const T inv_p = (T)(1.0 / P);
     T d2s = 0, d3s = 0, d4s = 0, ent = 0, slq = 0;
-    bool badq = false;
+    // q = p / P of the smallest bin must itself be a positive normal number (P finite and > 0 implied)
+    const unsigned gpmin = group_min_u32<TPF, C::BLOCK>(acc.pmin, scratch, t, grp);
+    const bool badq = sizeof(T) == 8 && (!power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) ||
+                                         abnormal((T)(power_from_hi<T>(gpmin) * inv_p)));
     // four bins at a time: all shared-memory loads first, then four independent sqrt-free math chains, so the
     // load-to-use latency is paid once per block.  s0 = slot of the first bin, the 4th bin sits at s0 + 3 + skip.
     T *const bufT = reinterpret_cast<T *>(buf);
@@ -354,7 +362,6 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
             d3s += w2 * d;
             d4s += w2 * dd;
             q[c] = pw[c] * inv_p;                     // make_spectrum_pmf, s_a_t.rs:284-290
-            badq |= abnormal(q[c]);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], logtab);
@@ -386,7 +393,6 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
             d3s += w2 * d;
             d4s += w2 * dd;
             const T q = pw * inv_p;
-            badq |= abnormal(q);
             const T l = Mth<T>::log2_(q, logtab);
             ent += q * l;
             slq += l;
@@ -395,7 +401,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     }
     // zero / subnormal / non-finite q somewhere: redo the two log sums with the library log2 (0 * -inf = NaN and
     // sum = -inf exactly like pmf * log2(pmf) and ln(m) in the reference, s_a_t.rs:93-114)
-    if (group_any<TPF, C::BLOCK>(badq, scratch, t, grp)) {
+    if (badq) {                                        // group-uniform
         ent = 0;
         slq = 0;
 #pragma unroll 1
@@ -593,7 +599,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
                 T mlo[4], mhi[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    acc.bad |= abnormal(plo[c]) | abnormal(phi[c]);
+                    acc.pmin = min(acc.pmin, min(power_hi(plo[c]), power_hi(phi[c])));
                     mlo[c] = Mth<T>::sqrt_(plo[c]);
                     mhi[c] = Mth<T>::sqrt_(phi[c]);
                 }
@@ -624,10 +630,10 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
             const T pm = X.x * X.x + X.y * X.y;
             bufT[2 * zslot(M / 2) + hp] = pm;
             acc.mid = pm;
-            acc.bad |= abnormal(pm);
+            acc.pmin = min(acc.pmin, power_hi(pm));
             if (want_feat) acc.add((T)(M / 2), Mth<T>::sqrt_(pm), pm);
         }
-        if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp);
+        if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, true);
         fence_proxy_async();                                            // generic accesses to buf before the next TMA write
         group_sync<TPF, C::BLOCK>(grp);
     }
@@ -662,6 +668,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ana
             pow_of<T, M, TPF>(buf, M - k) = phi;
             acc.lo_sum += plo;
             acc.hi_sum += phi;
+            acc.pmin = min(acc.pmin, min(power_hi(plo), power_hi(phi)));
             acc.add((T)k, ml, plo);
             acc.add((T)(M - k), mh, phi);
         }
@@ -670,9 +677,10 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ana
             const T pm = mm * mm;
             pow_of<T, M, TPF>(buf, M / 2) = pm;
             acc.mid = pm;
+            acc.pmin = min(acc.pmin, power_hi(pm));
             acc.add((T)(M / 2), mm, pm);
         }
-        frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp);
+        frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, false);
         group_sync<TPF, C::BLOCK>(grp);
     }
 }
