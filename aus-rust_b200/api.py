@@ -85,6 +85,10 @@ class Context:
         import torch
         self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_chunk_samples(self, n: int):
+        """Granularity of the copy/compute pipeline of the host-pointer feature calls (default 32 Mi samples)."""
+        _lib.check(self._lib.aus_ctx_set_chunk_samples(self._h, int(n)))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.aus_ctx_launch_count(self._h))

@@ -72,9 +72,13 @@ struct aus_ctx {
     bool own_stream = true;
     int sm_count = 148;
     uint64_t launches = 0;
+    uint64_t chunk_samples = 32ull << 20;     // host pipeline granularity: 32 Mi samples = 256 MB of f64
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
     DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw;
+    DevBuf pin64[2], pin32[2], pout64[2], pout32[2];     // double buffers of the chunked host pipeline
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 static int log2_exact(size_t n) {
@@ -198,7 +202,14 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
         for (void *w : kv.second.win2) cudaFree(w);
     }
     cudaFree(c->log2tab);
-    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw}) b->release();
+    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw,
+                      &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1]})
+        b->release();
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (int i = 0; i < 2; ++i)
+        for (cudaEvent_t e : {c->ev_in[i], c->ev_done[i], c->ev_out[i]})
+            if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -221,6 +232,11 @@ extern "C" int aus_ctx_synchronize(aus_ctx *c) {
     return AUS_OK;
 }
 extern "C" uint64_t aus_ctx_launch_count(const aus_ctx *c) { return c ? c->launches : 0; }
+extern "C" int aus_ctx_set_chunk_samples(aus_ctx *c, uint64_t n) {
+    if (!c || n == 0) return fail(AUS_ERR_INVALID, "bad argument");
+    c->chunk_samples = n;
+    return AUS_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ tables
 template <typename T> static int upload(void **dst, const std::vector<Cx<T>> &h, cudaStream_t s) {
@@ -564,6 +580,9 @@ extern "C" int aus_stft_features_batch_dev(aus_ctx *c, const void *d_audio, cons
     return stft_batch_dev_t<float>(c, (const float *)d_audio, b, N, hop, wtype, sr, (float *)d_features, (Cx<float> *)d_spectra);
 }
 
+static int stft_features_host_pipelined(aus_ctx *c, const double *audio, const struct Batch &b, size_t N, size_t hop,
+                                        int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples);
+
 // host-pointer core: upload f64, (convert), run, (convert), download f64
 static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offsets, const uint64_t *lengths, size_t n_files,
                            size_t N, size_t hop, int wtype, uint32_t sr, int precision, double *features, double *spectra,
@@ -575,6 +594,8 @@ static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offs
     if (frame_starts) for (size_t i = 0; i <= n_files; ++i) frame_starts[i] = b.first[i];
     if (b.total_frames == 0) return AUS_OK;
     if (!audio && b.span) return fail(AUS_ERR_INVALID, "null audio");
+    if (features && !spectra)      // the fused feature path: chunked, copy/compute overlapped
+        return stft_features_host_pipelined(c, audio, b, N, hop, wtype, sr, precision, features, c->chunk_samples);
     const size_t K = N / 2 + 1;
     const unsigned long long nfeat = b.total_frames * 14ull, nspec = b.total_frames * K * 2ull;
     AUS_TRY(c->in64.ensure(std::max<size_t>(b.span, 2) * sizeof(double)));
@@ -597,6 +618,108 @@ static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offs
     if (features) CUDA_TRY(cudaMemcpyAsync(features, c->out64.p, nfeat * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (spectra) CUDA_TRY(cudaMemcpyAsync(spectra, c->aux64.p, nspec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ chunked host pipeline
+// Features of a host-resident batch, pipelined in chunks of about `chunk_samples` samples: the H2D copy of chunk i+1
+// overlaps the kernels of chunk i and the D2H copy of chunk i-1 (three streams, double buffers).  Chunks are runs of
+// "virtual files" exactly like the multi-GPU shards: a long file is cut into contiguous frame ranges whose sample spans
+// overlap by fft_size - hop, and only the range that ends at the true end of the file can see the short last frame.
+struct VFile { uint64_t off, len, row, frames; };
+static void cut_file(uint64_t off, uint64_t len, size_t N, size_t hop, uint64_t parts, uint64_t row0, std::vector<VFile> &out) {
+    const uint64_t F = aus_num_frames((size_t)len, N, hop);
+    parts = std::max<uint64_t>(1, std::min<uint64_t>(parts, F));
+    for (uint64_t s = 0; s < parts; ++s) {
+        const uint64_t a = F * s / parts, b = F * (s + 1) / parts;
+        VFile v;
+        v.off = off + a * hop;
+        v.len = (b == F) ? len - std::min<uint64_t>(len, a * hop) : (b - a - 1) * hop + N;
+        v.row = row0 + a;
+        v.frames = b - a;
+        out.push_back(v);
+    }
+}
+
+static int ensure_pipeline(aus_ctx *c) {
+    if (c->s_in) return AUS_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    return AUS_OK;
+}
+
+static int stft_features_host_pipelined(aus_ctx *c, const double *audio, const Batch &b, size_t N, size_t hop, int wtype,
+                                        uint32_t sr, int precision, double *features, uint64_t chunk_samples) {
+    AUS_TRY(ensure_pipeline(c));
+    // virtual files no longer than a chunk
+    std::vector<VFile> vf;
+    for (size_t i = 0; i < b.off.size(); ++i) {
+        const uint64_t parts = (b.len[i] + chunk_samples - 1) / std::max<uint64_t>(chunk_samples, 1);
+        cut_file(b.off[i], b.len[i], N, hop, parts, b.first[i], vf);
+    }
+    // chunks: maximal runs of virtual files whose sample span stays within ~chunk_samples
+    struct Chunk { size_t lo, hi; uint64_t s0, span, frames; };
+    std::vector<Chunk> chunks;
+    for (size_t i = 0; i < vf.size();) {
+        Chunk ch{i, i, vf[i].off, 0, 0};
+        uint64_t s1 = vf[i].off;
+        while (ch.hi < vf.size()) {
+            const VFile &v = vf[ch.hi];
+            const uint64_t n0 = std::min(ch.s0, v.off), n1 = std::max(s1, v.off + v.len);
+            if (ch.hi > ch.lo && n1 - n0 > chunk_samples + N) break;
+            ch.s0 = n0; s1 = n1; ch.frames += v.frames; ++ch.hi;
+        }
+        ch.span = s1 - ch.s0;
+        chunks.push_back(ch);
+        i = ch.hi;
+    }
+    cudaStream_t st = c->stream;
+    // the copy streams must not start before work already queued on the caller's stream, nor the caller's later work
+    // before the copies finish: fence both ways with events
+    CUDA_TRY(cudaEventRecord(c->ev_done[0], st));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_done[0], 0));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_done[0], 0));
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk &ch = chunks[ci];
+        const int bb = (int)(ci & 1);
+        const size_t nfeat = (size_t)ch.frames * 14;
+        if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_done[bb], 0));       // kernels of chunk ci-2 released pin[bb]
+        AUS_TRY(c->pin64[bb].ensure(std::max<uint64_t>(ch.span, 2) * sizeof(double)));
+        AUS_TRY(c->pout64[bb].ensure(std::max<size_t>(nfeat, 1) * sizeof(double)));
+        if (ch.span)
+            CUDA_TRY(cudaMemcpyAsync(c->pin64[bb].p, audio + ch.s0, ch.span * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaEventRecord(c->ev_in[bb], c->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[bb], 0));
+        if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out[bb], 0));             // D2H of chunk ci-2 released pout[bb]
+        Batch cb;
+        cb.off.resize(ch.hi - ch.lo); cb.len.resize(ch.hi - ch.lo); cb.first.resize(ch.hi - ch.lo + 1);
+        uint64_t f = 0;
+        for (size_t i = ch.lo; i < ch.hi; ++i) {
+            cb.off[i - ch.lo] = vf[i].off - ch.s0; cb.len[i - ch.lo] = vf[i].len; cb.first[i - ch.lo] = f; f += vf[i].frames;
+        }
+        cb.first[ch.hi - ch.lo] = f; cb.total_frames = f; cb.span = ch.span;
+        if (precision == AUS_F64) {
+            AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->pin64[bb].p, cb, N, hop, wtype, sr, (double *)c->pout64[bb].p, nullptr));
+        } else {
+            AUS_TRY(c->pin32[bb].ensure(std::max<uint64_t>(ch.span, 4) * sizeof(float)));
+            AUS_TRY(c->pout32[bb].ensure(std::max<size_t>(nfeat, 1) * sizeof(float)));
+            AUS_TRY(cast_dev<double, float>(c, (const double *)c->pin64[bb].p, (float *)c->pin32[bb].p, ch.span));
+            AUS_TRY(stft_batch_dev_t<float>(c, (const float *)c->pin32[bb].p, cb, N, hop, wtype, sr, (float *)c->pout32[bb].p, nullptr));
+            AUS_TRY(cast_dev<float, double>(c, (const float *)c->pout32[bb].p, (double *)c->pout64[bb].p, nfeat));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_done[bb], st));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_done[bb], 0));
+        if (nfeat)
+            CUDA_TRY(cudaMemcpyAsync(features + vf[ch.lo].row * 14, c->pout64[bb].p, nfeat * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+        CUDA_TRY(cudaEventRecord(c->ev_out[bb], c->s_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->s_out));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return AUS_OK;
 }
 

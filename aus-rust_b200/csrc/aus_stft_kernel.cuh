@@ -658,27 +658,38 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ana
         const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
         const bool active = g < p.total_frames;
         const T *row = p.mags + (active ? g : 0ull) * (unsigned long long)K;
-        FeatAcc<T> acc;
-#pragma unroll 2
-        for (int i = 0; i < 16; ++i) {
-            const int k = 16 * t + i;
-            const T ml = active ? row[k] : (T)0, mh = active ? row[M - k] : (T)0;
-            const T plo = ml * ml, phi = mh * mh;                       // make_power_spectrum, s_a_t.rs:273-279
-            pow_of<T, M, TPF>(buf, k) = plo;
-            pow_of<T, M, TPF>(buf, M - k) = phi;
-            acc.lo_sum += plo;
-            acc.hi_sum += phi;
-            acc.pmin = min(acc.pmin, min(power_hi(plo), power_hi(phi)));
-            acc.add((T)k, ml, plo);
-            acc.add((T)(M - k), mh, phi);
+        // stage the row with coalesced loads (consecutive lanes -> consecutive bins): power in the power half of
+        // the owner's slot, the magnitude itself in the other half (overwritten by the running sum later)
+#pragma unroll 4
+        for (int b = t; b <= M; b += TPF) {
+            const T m = active ? row[b] : (T)0;
+            pow_of<T, M, TPF>(buf, b) = m * m;                          // make_power_spectrum, s_a_t.rs:273-279
+            cum_of<T, M, TPF>(buf, b) = m;
         }
-        if (t == TPF - 1) {
-            const T mm = active ? row[M / 2] : (T)0;
-            const T pm = mm * mm;
-            pow_of<T, M, TPF>(buf, M / 2) = pm;
-            acc.mid = pm;
-            acc.pmin = min(acc.pmin, power_hi(pm));
-            acc.add((T)(M / 2), mm, pm);
+        group_sync<TPF, C::BLOCK>(grp);
+        FeatAcc<T> acc;
+        {
+            T *const bufT = reinterpret_cast<T *>(buf);
+            const int hp = hpar<T>(t);
+            const int h0 = zslot(M - 16 * t);
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int sl = 17 * t + i, sh = (i == 0) ? h0 : h0 - 1 - i;
+                const T plo = bufT[2 * sl + hp], ml = bufT[2 * sl + 1 - hp];
+                const T phi = bufT[2 * sh + hp], mh = bufT[2 * sh + 1 - hp];
+                acc.lo_sum += plo;
+                acc.hi_sum += phi;
+                acc.pmin = min(acc.pmin, min(power_hi(plo), power_hi(phi)));
+                acc.add((T)(16 * t + i), ml, plo);
+                acc.add((T)(M - 16 * t - i), mh, phi);
+            }
+            if (t == TPF - 1) {
+                const int sm = zslot(M / 2);
+                const T pm = bufT[2 * sm + hp], mm = bufT[2 * sm + 1 - hp];
+                acc.mid = pm;
+                acc.pmin = min(acc.pmin, power_hi(pm));
+                acc.add((T)(M / 2), mm, pm);
+            }
         }
         frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, false);
         group_sync<TPF, C::BLOCK>(grp);

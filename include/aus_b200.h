@@ -87,6 +87,8 @@ int aus_ctx_set_stream(aus_ctx *ctx, void *cuda_stream);/* run on a caller-owned
 int aus_ctx_synchronize(aus_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t aus_ctx_launch_count(const aus_ctx *ctx);
+/* granularity (samples) of the host-pointer feature path's copy/compute pipeline; default 32 Mi samples (256 MB f64) */
+int aus_ctx_set_chunk_samples(aus_ctx *ctx, uint64_t n_samples);
 
 /* ---- pure host helpers ------------------------------------------------------------------------------- */
 /* frame count of the loop in spectrum/fft.rs:126-176 (strict `<` at :131; len <= fft_size -> 1 frame) */

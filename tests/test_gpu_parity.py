@@ -346,3 +346,25 @@ def test_features_and_spectra_in_one_call(ctx, orc):
     torch.cuda.synchronize()
     assert_features(feat.cpu().numpy(), orc.stft_features(x, 2048, 512, orc.HANNING, SR), RTOL64, "mixed features")
     assert_spectra(torch.view_as_complex(spec).cpu().numpy(), orc.rstft(x, 2048, 512, orc.HANNING), RTOL64, "mixed spectra")
+
+
+def test_host_pipeline_chunking(aus, orc):
+    """The host-pointer feature path cuts its input into chunks (copy/compute overlap).  With a tiny chunk size every
+    code path of the cut is exercised: long files split into frame ranges with halo, short files grouped, empty files."""
+    c = aus.Context(0)
+    x = orc.synth_signal(90000, SR, seed=19)
+    ref = orc.stft_features(x, 2048, 512, orc.HANNING, SR)
+    for chunk in (1000, 5000, 33333, 10 ** 9):
+        c.set_chunk_samples(chunk)
+        assert np.array_equal(c.stft_features(x, 2048, 512, orc.HANNING, SR), c.stft_features(x, 2048, 512, orc.HANNING, SR))
+        assert_features(c.stft_features(x, 2048, 512, orc.HANNING, SR), ref, RTOL64, f"chunk {chunk}")
+        assert_features(c.stft_features(x, 2048, 512, orc.HANNING, SR, "f32")[:, :6], ref[:, :6], RTOL32, f"chunk {chunk} f32")
+    lens = [0, 7000, 100, 0, 20000, 2048, 15000, 1]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    audio = orc.synth_signal(sum(lens), SR, seed=20)
+    refb = np.concatenate([orc.stft_features(audio[o:o + n], 1024, 256, orc.HAMMING, SR) for o, n in zip(offs, lens)])
+    for chunk in (3000, 9000, 10 ** 9):
+        c.set_chunk_samples(chunk)
+        got, starts = c.stft_features_batch(audio, offs, lens, 1024, 256, orc.HAMMING, SR)
+        assert_features(got, refb, RTOL64, f"batch chunk {chunk}")
+    c.close()
