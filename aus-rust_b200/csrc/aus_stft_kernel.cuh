@@ -431,6 +431,27 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
                 const int mid = (lo + hi) >> 1;
                 if (cum_of<T, M, TPF>(buf, mid) < th) lo = mid + 1; else hi = mid;
             }
+            if constexpr (sizeof(T) == 8) {
+                // Knife edge: the threshold sits within rounding distance of a running sum, where the reference's own
+                // arithmetic -- a sequential sum of p[i] / P compared with theta (s_a_t.rs:137-145) -- decides.  Redo it
+                // exactly that way (one thread, rare): identical result whenever the power values are identical, e.g.
+                // analyzer() on caller-supplied magnitudes with exact ties.
+                const double tol = 1e-12 * P;
+                const bool amb = (lo <= M && fabs((double)cum_of<T, M, TPF>(buf, lo) - (double)th) <= tol) ||
+                                 (lo >= 1 && fabs((double)th - (double)cum_of<T, M, TPF>(buf, lo - 1)) <= tol);
+                if (amb) {
+                    const double theta = qq == 0 ? 0.5 : qq == 1 ? 0.75 : qq == 2 ? 0.9 : 0.95;
+                    double pseq = 0.0;                     // power_spectrum.iter().sum(): sequential (analyzer.rs:44)
+                    for (int i = 0; i < K; ++i) pseq += (double)pow_of<T, M, TPF>(buf, i);
+                    double csum = 0.0;
+                    int i = -1;
+                    while (csum < theta && i < K - 1) {
+                        ++i;
+                        csum += (double)pow_of<T, M, TPF>(buf, i) / pseq;
+                    }
+                    lo = i;
+                }
+            }
             rec[RAW_ROLL0 + qq] = (double)lo;
         }
 #pragma unroll 1

@@ -368,3 +368,26 @@ def test_host_pipeline_chunking(aus, orc):
         got, starts = c.stft_features_batch(audio, offs, lens, 1024, 256, orc.HAMMING, SR)
         assert_features(got, refb, RTOL64, f"batch chunk {chunk}")
     c.close()
+
+
+def test_rolloff_knife_edges_match_reference_arithmetic(ctx, orc):
+    """Spectra built so that a roll-off threshold coincides with a running sum in exact arithmetic: the answer then
+    depends on how `cum += p[i] / P` rounds (s_a_t.rs:137-145).  The device path must reproduce that, not merely be
+    'close': e.g. 40 equal bins -> the 20th partial sum of 1/40 is 0.5000000000000001 or 0.49999999999999994."""
+    N, K = 2048, 1025
+    rows = []
+    rng = np.random.default_rng(5)
+    for nz in (2, 4, 10, 20, 40, 100, 200, 400, 1000):
+        for amp in (1.0, 3.0, 0.1):
+            m = np.zeros(K)
+            idx = np.sort(rng.choice(K, nz, replace=False))
+            m[idx] = amp
+            rows.append(m)
+    rows.append(np.full(K, 2.0))
+    m = np.zeros(K); m[::2] = 1.0; rows.append(m)
+    mags = np.array(rows)
+    ref = orc.analyze_spectrogram(mags, N, SR)
+    got = ctx.analyzer_batch(mags, N, SR)
+    assert np.array_equal(got[:, ROLL], ref[:, ROLL]), np.argwhere(got[:, ROLL] != ref[:, ROLL])
+    # the remaining features of these degenerate rows: zero bins -> entropy NaN, flatness 0 (same NaN pattern)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
