@@ -259,7 +259,7 @@ template <> struct Mth<double> {
     }
     static __device__ __forceinline__ double log2_(double x, const double2 *tab) {
         const unsigned hi = (unsigned)__double2hiint(x);
-        const double2 tc = tab[(hi >> 13) & (LOG2_TAB - 1)];
+        const double2 tc = tab[((hi >> 13) & (LOG2_TAB - 1)) * 8];     // 8 replicas per entry: see Cfg::LOGREP
         const double z = __hiloint2double((int)((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
         // exponent as a double without an I2F: 2^52 + 2^31 + (e ^ 0x80000000) trick
         const double ed = __hiloint2double(0x43300000, (int)(((hi >> 20) - 1023u) ^ 0x80000000u)) - 4503601774854144.0;

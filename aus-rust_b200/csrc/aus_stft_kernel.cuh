@@ -39,7 +39,10 @@ template <typename T, int LOG2N> struct Cfg {
     __host__ __device__ static constexpr size_t off_scratch() { return (size_t)FPB * BUF * sizeof(Cx<T>); }
     __host__ __device__ static constexpr size_t off_bar() { return off_scratch() + (size_t)FPB * SCR * sizeof(double); }
     __host__ __device__ static constexpr size_t off_log() { return (off_bar() + (size_t)FPB * sizeof(uint64_t) + 15) & ~(size_t)15; }
-    __host__ __device__ static constexpr size_t smem_bytes() { return off_log() + LOG2_TAB * sizeof(double2); }
+    // f64: the log2 table is replicated over the 8 sixteen-byte bank columns (lane l reads column l & 7), so a lookup
+    // with 32 random indices is conflict-free by construction; f32 uses log2f and needs no table
+    static constexpr int LOGREP = sizeof(T) == 8 ? 8 : 1;
+    __host__ __device__ static constexpr size_t smem_bytes() { return off_log() + (size_t)LOG2_TAB * LOGREP * sizeof(double2); }
     static_assert(LOG2N >= 6 && LOG2N <= 14, "fft_size must be 64..16384");
 };
 
@@ -349,6 +352,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     // load-to-use latency is paid once per block.  s0 = slot of the first bin, the 4th bin sits at s0 + 3 + skip.
     T *const bufT = reinterpret_cast<T *>(buf);
     const int hp = hpar<T>(t);                        // this thread's power half; running sum in the other one
+    const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);   // this lane's bank column
     auto block4 = [&](int s0, int skip, T d0, T &cum) {
         T pw[4], q[4], l[4];
 #pragma unroll
@@ -364,7 +368,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
             q[c] = pw[c] * inv_p;                     // make_spectrum_pmf, s_a_t.rs:284-290
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], logtab);
+        for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             ent += q[c] * l[c];
@@ -393,7 +397,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
             d3s += w2 * d;
             d4s += w2 * dd;
             const T q = pw * inv_p;
-            const T l = Mth<T>::log2_(q, logtab);
+            const T l = Mth<T>::log2_(q, ltab);
             ent += q * l;
             slq += l;
             bufT[2 * zslot(M / 2) + 1 - hp] = (T)tot_lo + pw;
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
     double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + C::off_bar()) + grp;
     double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
-    if (threadIdx.x < LOG2_TAB) logtab[threadIdx.x] = p.log2tab[threadIdx.x];
+    for (int i = threadIdx.x; i < LOG2_TAB * C::LOGREP; i += C::BLOCK) logtab[i] = p.log2tab[i / C::LOGREP];
     if (t == 0) mbar_init(bar, 1);
     fence_mbar_init();
     __syncthreads();
@@ -670,7 +674,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ana
     Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
     double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
     double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
-    if (threadIdx.x < LOG2_TAB) logtab[threadIdx.x] = p.log2tab[threadIdx.x];
+    for (int i = threadIdx.x; i < LOG2_TAB * C::LOGREP; i += C::BLOCK) logtab[i] = p.log2tab[i / C::LOGREP];
     __syncthreads();
     const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
     const unsigned long long iters = (p.total_frames + stride - 1) / stride;
