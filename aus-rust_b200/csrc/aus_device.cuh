@@ -274,8 +274,14 @@ template <> struct Mth<double> {
 template <> struct Mth<float> {
     static __device__ __forceinline__ float sqrt_exact(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float log2_exact(float x) { return log2f(x); }
-    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
-    static __device__ __forceinline__ float log2_(float x, const double2 *) { return log2f(x); }
+    // opt-in f32 mode (tolerance 1e-4): single-MUFU approximations.  sqrt.approx.ftz(0) = 0 and lg2.approx.ftz(0) = -inf,
+    // so zero bins keep the reference's NaN / -inf behaviour; max errors ~2^-22 (relative / absolute).
+    static __device__ __forceinline__ float sqrt_(float x) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    static __device__ __forceinline__ float log2_(float x, const double2 *) { return __log2f(x); }
 };
 
 // any-of over the TPF threads of a frame group (warp vote; cross-warp through shared scratch)
