@@ -10,8 +10,29 @@ namespace aus {
 // ------------------------------------------------------------------------------------------------ complex
 template <typename T> struct alignas(2 * sizeof(T)) Cx { T x, y; };
 
-template <typename T> __device__ __forceinline__ Cx<T> operator+(Cx<T> a, Cx<T> b) { return {a.x + b.x, a.y + b.y}; }
-template <typename T> __device__ __forceinline__ Cx<T> operator-(Cx<T> a, Cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ Cx<double> operator+(Cx<double> a, Cx<double> b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ Cx<double> operator-(Cx<double> a, Cx<double> b) { return {a.x - b.x, a.y - b.y}; }
+// f32: Blackwell's packed f32x2 ALU ops (SASS FADD2 / FMUL2) do a whole complex add / sub / scale in one issue slot;
+// the f32 kernel is issue-bound, and (re, im) already sits in an aligned register pair.
+__device__ __forceinline__ unsigned long long cx_bits(Cx<float> a) { return *reinterpret_cast<unsigned long long *>(&a); }
+__device__ __forceinline__ Cx<float> cx_from(unsigned long long u) { return *reinterpret_cast<Cx<float> *>(&u); }
+__device__ __forceinline__ Cx<float> operator+(Cx<float> a, Cx<float> b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+    return cx_from(r);
+}
+__device__ __forceinline__ Cx<float> operator-(Cx<float> a, Cx<float> b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+    return cx_from(r);
+}
+// element-wise product (x*x', y*y'): the window multiply of the packed real input
+__device__ __forceinline__ Cx<double> emul(Cx<double> a, Cx<double> b) { return {a.x * b.x, a.y * b.y}; }
+__device__ __forceinline__ Cx<float> emul(Cx<float> a, Cx<float> b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+    return cx_from(r);
+}
 template <typename T> __device__ __forceinline__ Cx<T> cmul(Cx<T> a, Cx<T> b) {
     return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
 }

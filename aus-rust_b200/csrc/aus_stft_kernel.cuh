@@ -138,9 +138,7 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
                 } else {
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const Cx<T> z = buf[lbase + r * lstride];
-                        const Cx<T> w = ldg_cx(tab + r * tstride);
-                        v[r] = Cx<T>{z.x * w.x, z.y * w.y};
+                        v[r] = emul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
                     }
                 }
             } else {
