@@ -63,6 +63,8 @@ SIGNATURES = {
     "aus_stft_analysis": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_uint32, c_size_t, c_void_p]),
     "aus_stft_features_batch": (c_int, [c_void_p, _p_d, _p_u64, _p_u64, c_size_t, c_size_t, c_size_t, c_int,
                                         c_uint32, c_int, _p_d, _p_u64]),
+    "aus_stft_features_batch_pcm": (c_int, [c_void_p, c_void_p, c_int, _p_u64, _p_u64, c_size_t, c_size_t, c_size_t, c_int,
+                                            c_uint32, c_int, _p_d, _p_u64]),
     "aus_stft_features_batch_dev": (c_int, [c_void_p, c_void_p, _p_u64, _p_u64, c_size_t, c_size_t, c_size_t, c_int,
                                             c_uint32, c_int, c_void_p, c_void_p]),
     "aus_batch_num_frames": (c_uint64, [_p_u64, c_size_t, c_size_t, c_size_t]),

@@ -128,6 +128,28 @@ class Context:
                                                      _pd(out), _pu64(starts)))
         return out, starts.astype(np.int64)
 
+    def stft_features_batch_pcm(self, pcm, offsets, lengths, fft_size: int, hop: int, window_type: int,
+                                sample_rate: int, precision="f64", sample_bits=None, out=None):
+        """Decoded integer PCM (int16, or int32 holding 24- or 32-bit samples) uploaded as-is and widened on the device
+        like the reference's reader: ``sample as f64 / INTMAX`` (audiofile.rs:296-329)."""
+        p = np.ascontiguousarray(pcm)
+        if p.dtype == np.int16:
+            bits = 16
+        elif p.dtype == np.int32:
+            bits = int(sample_bits or 32)
+        else:
+            raise ValueError("pcm must be int16 or int32")
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        total = batch_num_frames(ln, fft_size, hop)
+        if out is None:
+            out = np.empty((total, NUM_FEATURES), dtype=np.float64)
+        starts = np.empty(ln.size + 1, dtype=np.uint64)
+        _lib.check(self._lib.aus_stft_features_batch_pcm(self._h, p.ctypes.data_as(c_void_p), bits, _pu64(off), _pu64(ln),
+                                                         ln.size, int(fft_size), int(hop), int(window_type),
+                                                         int(sample_rate), _prec(precision), _pd(out), _pu64(starts)))
+        return out, starts.astype(np.int64)
+
     def rstft(self, audio, fft_size: int, hop: int, window_type: int, precision="f64") -> np.ndarray:
         """spectrum/fft.rs:119 -> complex128 [F, fft_size/2+1]."""
         a = _f64(audio)

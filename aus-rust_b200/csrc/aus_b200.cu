@@ -76,7 +76,7 @@ struct aus_ctx {
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
     DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw;
-    DevBuf pin64[2], pin32[2], pout64[2], pout32[2];     // double buffers of the chunked host pipeline
+    DevBuf pin64[2], pin32[2], pout64[2], pout32[2], ppcm[2];   // double buffers of the chunked host pipeline
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
@@ -203,7 +203,7 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
     }
     cudaFree(c->log2tab);
     for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw,
-                      &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1]})
+                      &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1], &c->ppcm[0], &c->ppcm[1]})
         b->release();
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -343,6 +343,12 @@ template <typename T> static int fill_feature_params(StftParams<T> &p, size_t N,
     return AUS_OK;
 }
 
+static int fill_feature_params_check(size_t N, uint32_t sr) {     // argument validation only (band vs Nyquist)
+    StftParams<double> tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    return fill_feature_params<double>(tmp, N, sr);
+}
+
 // ------------------------------------------------------------------------------------------------ launches
 template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
     using C = Cfg<T, LG>;
@@ -441,6 +447,21 @@ template <typename T> static int launch_finalize(aus_ctx *c, const StftParams<T>
     if (p.total_frames == 0) return AUS_OK;
     const unsigned int grid = (unsigned int)((p.total_frames + 255) / 256);
     finalize_kernel<T><<<grid, 256, 0, c->stream>>>(p, (int)(N / 2 + 1));
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+// audiofile.rs:296-329: decoded integer PCM -> f64 as `sample as f64 / INTMAX` (IEEE division, bit-identical)
+template <typename I, typename T>
+__global__ void pcm_kernel(const I *in, T *out, unsigned long long n, double intmax) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = (T)((double)in[i] / intmax);
+}
+template <typename I, typename T> static int pcm_dev(aus_ctx *c, const I *in, T *out, unsigned long long n, double intmax) {
+    if (n == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 16);
+    pcm_kernel<I, T><<<grid, 256, 0, c->stream>>>(in, out, n, intmax);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return AUS_OK;
@@ -580,8 +601,9 @@ extern "C" int aus_stft_features_batch_dev(aus_ctx *c, const void *d_audio, cons
     return stft_batch_dev_t<float>(c, (const float *)d_audio, b, N, hop, wtype, sr, (float *)d_features, (Cx<float> *)d_spectra);
 }
 
-static int stft_features_host_pipelined(aus_ctx *c, const double *audio, const struct Batch &b, size_t N, size_t hop,
-                                        int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples);
+static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_bits, const struct Batch &b, size_t N,
+                                        size_t hop, int wtype, uint32_t sr, int precision, double *features,
+                                        uint64_t chunk_samples);
 
 // host-pointer core: upload f64, (convert), run, (convert), download f64
 static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offsets, const uint64_t *lengths, size_t n_files,
@@ -595,7 +617,7 @@ static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offs
     if (b.total_frames == 0) return AUS_OK;
     if (!audio && b.span) return fail(AUS_ERR_INVALID, "null audio");
     if (features && !spectra)      // the fused feature path: chunked, copy/compute overlapped
-        return stft_features_host_pipelined(c, audio, b, N, hop, wtype, sr, precision, features, c->chunk_samples);
+        return stft_features_host_pipelined(c, audio, 0, b, N, hop, wtype, sr, precision, features, c->chunk_samples);
     const size_t K = N / 2 + 1;
     const unsigned long long nfeat = b.total_frames * 14ull, nspec = b.total_frames * K * 2ull;
     AUS_TRY(c->in64.ensure(std::max<size_t>(b.span, 2) * sizeof(double)));
@@ -653,9 +675,12 @@ static int ensure_pipeline(aus_ctx *c) {
     return AUS_OK;
 }
 
-static int stft_features_host_pipelined(aus_ctx *c, const double *audio, const Batch &b, size_t N, size_t hop, int wtype,
-                                        uint32_t sr, int precision, double *features, uint64_t chunk_samples) {
+// pcm_bits: 0 = the host buffer is f64 samples; 16 = int16_t PCM; 24 / 32 = int32_t PCM (24-bit samples in 32-bit words)
+static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
+                                        int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples) {
     AUS_TRY(ensure_pipeline(c));
+    const size_t in_bytes = pcm_bits == 0 ? sizeof(double) : (pcm_bits == 16 ? 2 : 4);
+    const double intmax = pcm_bits == 16 ? 32767.0 : (pcm_bits == 24 ? 8388607.0 : 2147483647.0);   // audiofile.rs:12-15
     // virtual files no longer than a chunk
     std::vector<VFile> vf;
     for (size_t i = 0; i < b.off.size(); ++i) {
@@ -691,8 +716,13 @@ static int stft_features_host_pipelined(aus_ctx *c, const double *audio, const B
         if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_done[bb], 0));       // kernels of chunk ci-2 released pin[bb]
         AUS_TRY(c->pin64[bb].ensure(std::max<uint64_t>(ch.span, 2) * sizeof(double)));
         AUS_TRY(c->pout64[bb].ensure(std::max<size_t>(nfeat, 1) * sizeof(double)));
+        void *h2d_dst = c->pin64[bb].p;
+        if (pcm_bits) {
+            AUS_TRY(c->ppcm[bb].ensure(std::max<uint64_t>(ch.span, 4) * in_bytes));
+            h2d_dst = c->ppcm[bb].p;
+        }
         if (ch.span)
-            CUDA_TRY(cudaMemcpyAsync(c->pin64[bb].p, audio + ch.s0, ch.span * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+            CUDA_TRY(cudaMemcpyAsync(h2d_dst, (const char *)audio + ch.s0 * in_bytes, ch.span * in_bytes, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaEventRecord(c->ev_in[bb], c->s_in));
         CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[bb], 0));
         if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out[bb], 0));             // D2H of chunk ci-2 released pout[bb]
@@ -703,6 +733,8 @@ static int stft_features_host_pipelined(aus_ctx *c, const double *audio, const B
             cb.off[i - ch.lo] = vf[i].off - ch.s0; cb.len[i - ch.lo] = vf[i].len; cb.first[i - ch.lo] = f; f += vf[i].frames;
         }
         cb.first[ch.hi - ch.lo] = f; cb.total_frames = f; cb.span = ch.span;
+        if (pcm_bits == 16) AUS_TRY(pcm_dev<int16_t, double>(c, (const int16_t *)c->ppcm[bb].p, (double *)c->pin64[bb].p, ch.span, intmax));
+        else if (pcm_bits) AUS_TRY(pcm_dev<int32_t, double>(c, (const int32_t *)c->ppcm[bb].p, (double *)c->pin64[bb].p, ch.span, intmax));
         if (precision == AUS_F64) {
             AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->pin64[bb].p, cb, N, hop, wtype, sr, (double *)c->pout64[bb].p, nullptr));
         } else {
@@ -728,6 +760,23 @@ extern "C" int aus_stft_features_batch(aus_ctx *c, const double *audio, const ui
                                        double *features, uint64_t *frame_starts) {
     if (!features) return fail(AUS_ERR_INVALID, "null features");
     return stft_batch_host(c, audio, offsets, lengths, n_files, N, hop, wtype, sr, precision, features, nullptr, frame_starts);
+}
+
+extern "C" int aus_stft_features_batch_pcm(aus_ctx *c, const void *pcm, int sample_bits, const uint64_t *offsets,
+                                           const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype,
+                                           uint32_t sr, int precision, double *features, uint64_t *frame_starts) {
+    AUS_TRY(check_common(c, N, hop, wtype, precision));
+    if (sample_bits != 16 && sample_bits != 24 && sample_bits != 32)
+        return fail(AUS_ERR_INVALID, "sample_bits must be 16 (int16_t), 24 or 32 (int32_t)");
+    if (!lengths || !features) return fail(AUS_ERR_INVALID, "null argument");
+    if (sample_bits != 16 && sample_bits != 24 && sample_bits != 32) return fail(AUS_ERR_INVALID, "bad sample_bits");
+    AUS_TRY(fill_feature_params_check(N, sr));
+    Batch b;
+    make_batch(b, offsets, lengths, n_files, N, hop);
+    if (frame_starts) for (size_t i = 0; i <= n_files; ++i) frame_starts[i] = b.first[i];
+    if (b.total_frames == 0) return AUS_OK;
+    if (!pcm && b.span) return fail(AUS_ERR_INVALID, "null pcm");
+    return stft_features_host_pipelined(c, pcm, sample_bits, b, N, hop, wtype, sr, precision, features, c->chunk_samples);
 }
 
 extern "C" int aus_stft_features(aus_ctx *c, const double *audio, size_t n, size_t N, size_t hop, int wtype, uint32_t sr,

@@ -120,6 +120,13 @@ int aus_stft_features_batch(aus_ctx *ctx, const double *audio, const uint64_t *o
 int aus_stft_features_batch_dev(aus_ctx *ctx, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
                                 size_t n_files, size_t fft_size, size_t hop, int window_type, uint32_t sample_rate,
                                 int precision, void *d_features, void *d_spectra);
+/* SURVEY 8(f) item 4 -- decoded integer PCM straight from the codec: the samples are uploaded as they are (2 or 4
+ * bytes each) and widened on the device exactly like the reader does, `sample as f64 / INTMAX` with INTMAX = 2^(bits-1)-1
+ * (audiofile.rs:12-15, :296-329).  sample_bits 16: `pcm` is int16_t[]; 24 or 32: int32_t[].  Same batch layout and
+ * output as aus_stft_features_batch. */
+int aus_stft_features_batch_pcm(aus_ctx *ctx, const void *pcm, int sample_bits, const uint64_t *offsets,
+                                const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop, int window_type,
+                                uint32_t sample_rate, int precision, double *features, uint64_t *frame_starts);
 /* total frames of a batch (sum of aus_num_frames over files) */
 uint64_t aus_batch_num_frames(const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop);
 

@@ -391,3 +391,20 @@ def test_rolloff_knife_edges_match_reference_arithmetic(ctx, orc):
     assert np.array_equal(got[:, ROLL], ref[:, ROLL]), np.argwhere(got[:, ROLL] != ref[:, ROLL])
     # the remaining features of these degenerate rows: zero bins -> entropy NaN, flatness 0 (same NaN pattern)
     assert np.array_equal(np.isnan(got), np.isnan(ref))
+
+
+def test_pcm_input_matches_reader_then_analyzer(ctx, orc):
+    """integer PCM widened on the device as `sample as f64 / INTMAX` (audiofile.rs:296-329)."""
+    rng = np.random.default_rng(21)
+    lens = [9000, 0, 30000, 2049]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    x = orc.synth_signal(sum(lens), SR, seed=22)
+    for dtype, bits, intmax in ((np.int16, 16, 2 ** 15 - 1), (np.int32, 24, 2 ** 23 - 1), (np.int32, 32, 2 ** 31 - 1)):
+        pcm = np.round(x * intmax).astype(dtype)
+        wide = pcm.astype(np.float64) / float(intmax)
+        ref = np.concatenate([orc.stft_features(wide[o:o + n], 2048, 512, orc.HANNING, SR) for o, n in zip(offs, lens)])
+        got, starts = ctx.stft_features_batch_pcm(pcm, offs, lens, 2048, 512, orc.HANNING, SR, sample_bits=bits)
+        assert_features(got, ref, RTOL64, f"pcm{bits}")
+        # identical to uploading the widened f64 samples (the conversion itself is bit-exact)
+        got64, _ = ctx.stft_features_batch(wide, offs, lens, 2048, 512, orc.HANNING, SR)
+        assert np.array_equal(got, got64, equal_nan=True)
