@@ -160,6 +160,15 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    try:        # run (and allocate the pinned host buffers) on the CPUs next to this rank's GPU: e2e is a PCIe / host-memory number
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda._get_nvml_device_index(local) if hasattr(torch.cuda, "_get_nvml_device_index") else local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        numa = len(os.sched_getaffinity(0))
+    except Exception:
+        numa = None
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON line
         # on stdout, so stdout points at stderr until the communicator exists
@@ -293,7 +302,7 @@ def run_ours(args):
             "audio_seconds_per_sec": value * HOP / SR,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": e2e_files * FILE_SAMPLES * 8,
                     "d2h_bytes_per_step": e2e_frames * 14 * 8, "files_per_step": e2e_files, "steps": e2e_steps,
-                    "host_dtype": "f64 (pinned)"},
+                    "host_dtype": "f64 (pinned)", "rank_cpu_affinity": numa},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": f"stft_kernel<{'double' if prec == 'f64' else 'float'}, 11>",
