@@ -574,6 +574,13 @@ static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t
         AUS_TRY(c->raw.ensure((size_t)b.total_frames * RAW_N * sizeof(double)));
         p.raw = (double *)c->raw.p;
     }
+    if (d_feat && d_spec) {           // both outputs: one spectra-only launch (coalesced stores) + one fused feature launch
+        StftParams<T> ps = p;
+        ps.raw = nullptr;
+        ps.feat = nullptr;
+        AUS_TRY(launch_stft<T>(c, lg, ps));
+        p.spec = nullptr;
+    }
     AUS_TRY(launch_stft<T>(c, lg, p));
     if (d_feat) AUS_TRY(launch_finalize<T>(c, p, N));
     return AUS_OK;

@@ -302,7 +302,11 @@ template <> struct Mth<float> {
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
         return r;
     }
-    static __device__ __forceinline__ float log2_(float x, const double2 *) { return __log2f(x); }
+    static __device__ __forceinline__ float log2_(float x, const double2 *) {
+        float r;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
 };
 
 // any-of over the TPF threads of a frame group (warp vote; cross-warp through shared scratch)

@@ -316,9 +316,10 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
 
     // sub-band sums for the three slope regions (s_a_t.rs:190-230): bins [r_lo, r_hi) of bands 1 and 2, all threads
     T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
+    const bool bands_low = p.r_hi[1] <= M / 2;        // every band bin in the lower half: owner = b >> 4, no selects
 #pragma unroll 1
     for (int b = p.r_lo[0] + t; b < p.r_hi[1]; b += TPF) {
-        const T pw = pow_of<T, M, TPF>(buf, b);
+        const T pw = bands_low ? reinterpret_cast<const T *>(buf)[2 * zslot(b) + hpar<T>(b >> 4)] : pow_of<T, M, TPF>(buf, b);
         const T pk = pw * (T)b;
         if (b < p.r_hi[0]) { b1p += pw; b1pk += pk; }
         if (b >= p.r_lo[1]) { b2p += pw; b2pk += pk; }
@@ -608,7 +609,6 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
                 const int k = 16 * t + i0 + c;
                 Cx<T> Xlo, Xhi;
                 post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
-                if (spec) { spec[k] = Xlo; spec[M - k] = Xhi; }      // features AND spectra requested: direct stores
                 plo[c] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
                 phi[c] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
             }
@@ -649,7 +649,6 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
         } else if (t == TPF - 1) {
             const Cx<T> A = buf[zslot(M / 2)];
             const Cx<T> X = Cx<T>{A.x + A.x, -(A.y + A.y)};             // X[M/2] = conj(Z[M/2])
-            if (spec) spec[M / 2] = X;
             const T pm = X.x * X.x + X.y * X.y;
             bufT[2 * zslot(M / 2) + hp] = pm;
             acc.mid = pm;
