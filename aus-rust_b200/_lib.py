@@ -82,6 +82,9 @@ SIGNATURES = {
     "aus_irstft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, _p_d]),
     "aus_irstft_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p]),
     "aus_irfft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_int, _p_d]),
+    "aus_autocorrelation": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d]),
+    "aus_autocorrelation_batch": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d]),
+    "aus_time_features_batch": (c_int, [c_void_p, _p_d, _p_u64, _p_u64, c_size_t, c_uint32, _p_d]),
     "aus_synth_dev": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_double, c_uint64, c_uint64, c_int]),
 }
 

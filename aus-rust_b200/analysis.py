@@ -114,3 +114,30 @@ def spectral_slope_region(magnitude_spectrum, rfft_freqs, f_lower: float, f_uppe
     if idx is None:
         raise ValueError("the device path provides the analyzer's three bands 0-1k / 1-5k / 0-5k Hz (analyzer.rs:60-62)")
     return float(_one(magnitude_spectrum, rfft_freqs, sample_rate)[idx])
+
+
+# ---- SURVEY 8(f) "next" rows: analysis::autocorrelation and the time-domain scalars of audio_analysis_tools.rs
+def autocorrelation(audio, fft_size: int) -> np.ndarray:
+    """spectral_analysis_tools.rs:31 -- raises SpectrumError when len(audio) != fft_size."""
+    return default_context().autocorrelation(np.asarray(audio, dtype=np.float64).reshape(-1), fft_size)
+
+
+def _time(audio, sample_rate=44100):
+    a = np.ascontiguousarray(audio, dtype=np.float64).reshape(-1)
+    return default_context().time_features_batch(a, [0], [a.size], sample_rate)[0]
+
+
+def dc_bias(audio) -> float:                          # audio_analysis_tools.rs:22
+    return float(_time(audio)[0])
+
+
+def dbfs_max(audio) -> float:                         # audio_analysis_tools.rs:55
+    return float(_time(audio)[1])
+
+
+def energy(audio) -> float:                           # audio_analysis_tools.rs:74
+    return float(_time(audio)[2])
+
+
+def zero_crossing_rate(audio, sample_rate: int) -> float:   # audio_analysis_tools.rs:98
+    return float(_time(audio, sample_rate)[3])

@@ -213,6 +213,28 @@ class Context:
                                                 _prec(precision), _pd(out)))
         return out
 
+    def autocorrelation(self, audio, fft_size: int) -> np.ndarray:
+        """analysis/spectral_analysis_tools.rs:31 (one chunk, or [n_chunks, fft_size] rows)."""
+        a = _f64(audio)
+        if a.ndim == 1:
+            out = np.empty(int(fft_size), dtype=np.float64)
+            _lib.check(self._lib.aus_autocorrelation(self._h, _pd(a), a.size, int(fft_size), _pd(out)))
+            return out
+        if a.shape[1] != fft_size:
+            raise _lib.SpectrumError(_lib.AUS_ERR_SIZE, "The audio length does not match the FFT size.")
+        out = np.empty(a.shape, dtype=np.float64)
+        _lib.check(self._lib.aus_autocorrelation_batch(self._h, _pd(a), a.shape[0], int(fft_size), _pd(out)))
+        return out
+
+    def time_features_batch(self, audio, offsets, lengths, sample_rate: int) -> np.ndarray:
+        """dc_bias, dbfs_max, energy, zero_crossing_rate per file (analysis/audio_analysis_tools.rs:22-108)."""
+        a = _f64(audio)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        out = np.empty((ln.size, 4), dtype=np.float64)
+        _lib.check(self._lib.aus_time_features_batch(self._h, _pd(a), _pu64(off), _pu64(ln), ln.size, int(sample_rate), _pd(out)))
+        return out
+
     # ---- device-pointer API (torch CUDA tensors; stream-ordered, no sync)
     def _check_dev(self, t, precision, name):
         import torch

@@ -466,6 +466,96 @@ template <typename I, typename T> static int pcm_dev(aus_ctx *c, const I *in, T 
     c->launches++;
     return AUS_OK;
 }
+// ---- SURVEY 8(f) "next" rows ------------------------------------------------------------------------------
+// autocorrelation (s_a_t.rs:43-53): N/2 zeros, the chunk, N/2 zeros -> one 2N-sample frame per chunk
+__global__ void acorr_pad_kernel(const double *in, double *out, unsigned long long n_chunks, int N) {
+    const unsigned long long total = n_chunks * 2ull * N;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = i / (2ull * N);
+        const int j = (int)(i - c * 2ull * N) - N / 2;
+        out[i] = (j >= 0 && j < N) ? in[c * N + j] : 0.0;
+    }
+}
+// spectrum[i] * conj(spectrum[i]) (s_a_t.rs:58-60)
+__global__ void acorr_power_kernel(double2 *s, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 v = s[i];
+        s[i] = make_double2(v.x * v.x + v.y * v.y, 0.0);
+    }
+}
+// auto[i] = spectrum[i + fft_size].re (s_a_t.rs:65-67)
+__global__ void acorr_slice_kernel(const double *y, double *out, unsigned long long n_chunks, int N) {
+    const unsigned long long total = n_chunks * (unsigned long long)N;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = i / N;
+        out[i] = y[c * 2ull * N + N + (i - c * N)];
+    }
+}
+// time-domain scalars of audio_analysis_tools.rs:22-108, two deterministic levels: per (file, 64 Ki-sample chunk)
+// partials {sum, sum of squares, max |x|, zero crossings}, then one warp per file combines them in chunk order
+constexpr int TF_CHUNK = 1 << 16;
+__global__ void __launch_bounds__(256) time_partial_kernel(const double *audio, const unsigned long long *off,
+                                                           const unsigned long long *len, const unsigned long long *chunk_first,
+                                                           int n_files, double *partials) {
+    __shared__ double sh[4][8];
+    const unsigned long long chunk = blockIdx.x;
+    int f = 0;
+    while (f + 1 < n_files && chunk >= chunk_first[f + 1]) ++f;         // few files per launch: linear is fine
+    const unsigned long long n = len[f], c0 = (chunk - chunk_first[f]) * (unsigned long long)TF_CHUNK;
+    const double *a = audio + off[f];
+    const unsigned long long c1 = c0 + TF_CHUNK < n ? c0 + TF_CHUNK : n;
+    double s = 0.0, s2 = 0.0, mx = 0.0, zc = 0.0;
+    for (unsigned long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const double x = a[i];
+        s += x;
+        s2 += x * x;
+        const double ax = fabs(x);
+        if (ax > mx) mx = ax;                                             // NaN never wins, like `sample_abs > maxval`
+        if (i >= 1) {                                                     // zero_crossing_rate's loop body, :100-106
+            if (a[i - 1] * x < 0.0) zc += 1.0;
+            else if (i + 1 < n && a[i + 1] < 0.0 && x == 0.0) zc += 1.0;
+        }
+    }
+    double v[4] = {s, s2, mx, zc};
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        v[1] += __shfl_xor_sync(0xffffffffu, v[1], o);
+        const double m2 = __shfl_xor_sync(0xffffffffu, v[2], o);
+        v[2] = m2 > v[2] ? m2 : v[2];
+        v[3] += __shfl_xor_sync(0xffffffffu, v[3], o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 4; ++k) sh[k][threadIdx.x >> 5] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 8; ++w) {
+            r[0] += sh[0][w]; r[1] += sh[1][w]; r[2] = sh[2][w] > r[2] ? sh[2][w] : r[2]; r[3] += sh[3][w];
+        }
+        for (int k = 0; k < 4; ++k) partials[chunk * 4 + k] = r[k];
+    }
+}
+__global__ void time_final_kernel(const double *partials, const unsigned long long *len, const unsigned long long *chunk_first,
+                                  int n_files, uint32_t sr, double *out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_files) return;
+    double s = 0.0, s2 = 0.0, mx = 0.0, zc = 0.0;
+    for (unsigned long long c = chunk_first[f]; c < chunk_first[f + 1]; ++c) {
+        s += partials[c * 4]; s2 += partials[c * 4 + 1];
+        mx = partials[c * 4 + 2] > mx ? partials[c * 4 + 2] : mx;
+        zc += partials[c * 4 + 3];
+    }
+    const double n = (double)len[f];
+    out[f * 4 + 0] = s / n;                                                   // dc_bias, :22-28
+    out[f * 4 + 1] = mx < 1e-20 ? -INFINITY : 20.0 * log10(mx);               // dbfs_max, :55-65 (DBFS_EPSILON = 1e-20)
+    out[f * 4 + 2] = len[f] < 1 ? 0.0 : sqrt(1.0 / n * s2);                   // energy, :74-84
+    out[f * 4 + 3] = zc * (double)sr / n;                                     // zero_crossing_rate, :98-108
+}
+
 // fft_tools.rs:41-55
 __global__ void to_polar_kernel(const double2 *s, double *mag, double *ph, unsigned long long n) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -1004,6 +1094,82 @@ extern "C" int aus_irfft(aus_ctx *c, const double *spectrum, size_t spectrum_len
     }
     if (!spectrum || !audio) return fail(AUS_ERR_INVALID, "null argument");
     return irstft_host(c, spectrum, 1, N, N, AUS_WINDOW_RECTANGULAR, precision, 0, 0, audio);
+}
+
+// ------------------------------------------------------------------------------------------------ SURVEY 8(f) entry points
+// analysis::autocorrelation (s_a_t.rs:31-70) over n_chunks consecutive chunks of fft_size samples, all on the device:
+// pad -> K2 at 2N (rectangular, hop 2N) -> |X|^2 -> K4 core as plain inverse -> slice [N, 2N).
+extern "C" int aus_autocorrelation_batch(aus_ctx *c, const double *audio, size_t n_chunks, size_t N, double *out) {
+    AUS_TRY(check_common(c, 2 * N, 2 * N, AUS_WINDOW_RECTANGULAR, AUS_F64));
+    if (!audio || !out) return fail(AUS_ERR_INVALID, "null argument");
+    if (n_chunks == 0) return AUS_OK;
+    const size_t N2 = 2 * N, K2 = N2 / 2 + 1, nin = n_chunks * N, npad = n_chunks * N2, nspec = n_chunks * K2 * 2;
+    AUS_TRY(c->in64.ensure(nin * sizeof(double)));
+    AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
+    AUS_TRY(c->out64.ensure(npad * sizeof(double)));
+    AUS_TRY(c->pin64[0].ensure(npad * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, nin * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const unsigned int grid = (unsigned int)std::min<size_t>((npad + 255) / 256, (size_t)c->sm_count * 16);
+    acorr_pad_kernel<<<grid, 256, 0, c->stream>>>((const double *)c->in64.p, (double *)c->pin64[0].p, n_chunks, (int)N);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    Batch b;
+    const uint64_t off0 = 0, len0 = npad;
+    make_batch(b, &off0, &len0, 1, N2, N2);                    // n_chunks frames of exactly 2N samples
+    AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->pin64[0].p, b, N2, N2, AUS_WINDOW_RECTANGULAR, 44100, nullptr,
+                                     (Cx<double> *)c->aux64.p));
+    acorr_power_kernel<<<grid, 256, 0, c->stream>>>((double2 *)c->aux64.p, n_chunks * K2);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    AUS_TRY(irstft_dev_t<double>(c, (const Cx<double> *)c->aux64.p, n_chunks, N2, N2, AUS_WINDOW_RECTANGULAR, 0, 0, (double *)c->out64.p));
+    acorr_slice_kernel<<<grid, 256, 0, c->stream>>>((const double *)c->out64.p, (double *)c->in64.p, n_chunks, (int)N);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, c->in64.p, nin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+extern "C" int aus_autocorrelation(aus_ctx *c, const double *audio, size_t audio_len, size_t N, double *out) {
+    if (audio_len != N) return fail(AUS_ERR_SIZE, "The audio length does not match the FFT size.");      // s_a_t.rs:33
+    return aus_autocorrelation_batch(c, audio, 1, N, out);
+}
+
+// dc_bias, dbfs_max, energy, zero_crossing_rate (audio_analysis_tools.rs:22-108) of every file of a batch: out[f][4]
+extern "C" int aus_time_features_batch(aus_ctx *c, const double *audio, const uint64_t *offsets, const uint64_t *lengths,
+                                       size_t n_files, uint32_t sr, double *out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (!lengths || !out || (!audio && n_files)) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_files == 0) return AUS_OK;
+    std::vector<unsigned long long> off(n_files), len(n_files), cf(n_files + 1);
+    unsigned long long span = 0, chunks = 0;
+    for (size_t i = 0; i < n_files; ++i) {
+        off[i] = offsets ? offsets[i] : 0;
+        len[i] = lengths[i];
+        cf[i] = chunks;
+        chunks += (len[i] + TF_CHUNK - 1) / TF_CHUNK;
+        span = std::max(span, off[i] + len[i]);
+    }
+    cf[n_files] = chunks;
+    AUS_TRY(c->in64.ensure(std::max<unsigned long long>(span, 1) * sizeof(double)));
+    AUS_TRY(c->aux64.ensure(std::max<unsigned long long>(chunks, 1) * 4 * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n_files * 4 * sizeof(double)));
+    if (span) CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, span * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    std::vector<const unsigned long long *> dp;
+    AUS_TRY(upload_desc(c, c->desc, {&off, &len, &cf}, dp));
+    if (chunks) {
+        time_partial_kernel<<<(unsigned int)chunks, 256, 0, c->stream>>>((const double *)c->in64.p, dp[0], dp[1], dp[2], (int)n_files,
+                                                                        (double *)c->aux64.p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    time_final_kernel<<<(unsigned int)((n_files + 127) / 128), 128, 0, c->stream>>>((const double *)c->aux64.p, dp[1], dp[2], (int)n_files, sr,
+                                                                                  (double *)c->out64.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, n_files * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ synthetic input

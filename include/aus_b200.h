@@ -177,6 +177,16 @@ int aus_irstft_dev(aus_ctx *ctx, const void *d_spectra, size_t n_frames, size_t 
 int aus_irfft(aus_ctx *ctx, const double *spectrum, size_t spectrum_len, size_t fft_size, int precision,
               double *audio /* fft_size */);
 
+/* ---- SURVEY 8(f) "next" rows ------------------------------------------------------------------------ */
+/* analysis/spectral_analysis_tools.rs:31-70 `autocorrelation` (audio_len != fft_size -> AUS_ERR_SIZE with the reference's
+ * message); the batch form takes n_chunks consecutive chunks of fft_size samples.  2*fft_size must be <= 16384. */
+int aus_autocorrelation(aus_ctx *ctx, const double *audio, size_t audio_len, size_t fft_size, double *out /* fft_size */);
+int aus_autocorrelation_batch(aus_ctx *ctx, const double *audio, size_t n_chunks, size_t fft_size, double *out);
+/* analysis/audio_analysis_tools.rs:22-108 over every file of a batch: out[f] = {dc_bias, dbfs_max, energy,
+ * zero_crossing_rate} */
+int aus_time_features_batch(aus_ctx *ctx, const double *audio, const uint64_t *offsets, const uint64_t *lengths,
+                            size_t n_files, uint32_t sample_rate, double *out /* n_files x 4 */);
+
 /* ---- synthetic input generator used by the benchmark (synthesis.rs:50-59 sine + counter noise) --- */
 int aus_synth_dev(aus_ctx *ctx, void *d_audio, uint64_t n_samples, uint64_t n0, uint32_t sample_rate, double freq,
                   uint64_t seed, uint64_t file_id, int precision);

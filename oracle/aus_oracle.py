@@ -402,6 +402,70 @@ def stft_analysis(audio, fft_size: int, sample_rate: int, max_num_threads=None) 
     return stft_features(audio, fft_size, fft_size // 2, HAMMING, sample_rate)
 
 
+# --------------------------------------------------------------------------- SURVEY 8(f) "next" rows
+def autocorrelation(audio, fft_size: int) -> np.ndarray:
+    """spectral_analysis_tools.rs:31-70: N/2 zeros left and right, 2N-point FFT, |X|^2, un-normalised inverse,
+    samples [N, 2N)."""
+    a = np.asarray(audio, dtype=np.float64)
+    if a.shape[0] != fft_size:
+        raise SpectrumError("The audio length does not match the FFT size.")
+    padded = np.concatenate([np.zeros(fft_size // 2), a, np.zeros(fft_size // 2)]).astype(np.complex128)
+    spec = np.fft.fft(padded)
+    spec = spec * np.conj(spec)
+    back = np.fft.ifft(spec) * (2 * fft_size)
+    return back[fft_size:2 * fft_size].real.copy()
+
+
+DBFS_EPSILON = 1e-20          # audio_analysis_tools.rs:10
+
+
+def dc_bias(audio) -> float:
+    """audio_analysis_tools.rs:22-28."""
+    a = np.asarray(audio, dtype=np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return float(np.float64(_seqsum(a)) / np.float64(a.size))
+
+
+def dbfs(val: float, epsilon: float = DBFS_EPSILON) -> float:
+    """audio_analysis_tools.rs:42-48 (note: log10 of the signed value, as written)."""
+    if abs(val) < epsilon:
+        return -math.inf
+    return 20.0 * math.log10(val) if val > 0 else math.nan
+
+
+def dbfs_max(audio) -> float:
+    """audio_analysis_tools.rs:55-65."""
+    a = np.asarray(audio, dtype=np.float64)
+    m = 0.0
+    if a.size:
+        ab = np.abs(a)
+        ab = ab[~np.isnan(ab)]          # `sample_abs > maxval` is false for NaN
+        m = float(ab.max()) if ab.size else 0.0
+    return dbfs(m, DBFS_EPSILON)
+
+
+def energy(audio) -> float:
+    """audio_analysis_tools.rs:74-84."""
+    a = np.asarray(audio, dtype=np.float64)
+    if a.size < 1:
+        return 0.0
+    return float(np.sqrt(1.0 / a.size * np.float64(_seqsum(a ** 2.0))))
+
+
+def zero_crossing_rate(audio, sample_rate: int) -> float:
+    """audio_analysis_tools.rs:98-108."""
+    a = np.asarray(audio, dtype=np.float64)
+    n = a.size
+    if n == 0:
+        return math.nan                  # 0 * sr / 0
+    prod_neg = a[:-1] * a[1:] < 0.0                      # i = 1 .. n-1
+    zero_then_neg = np.zeros(n - 1, dtype=bool)
+    if n > 2:
+        zero_then_neg[:-1] = (a[1:-1] == 0.0) & (a[2:] < 0.0)     # i < n-1 and a[i+1] < 0 and a[i] == 0
+    num = int(np.count_nonzero(prod_neg | (~prod_neg & zero_then_neg)))
+    return float(num) * float(sample_rate) / float(n)
+
+
 # --------------------------------------------------------------------------- synthetic inputs (SURVEY 8d)
 _M64 = (1 << 64) - 1
 

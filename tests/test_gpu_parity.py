@@ -408,3 +408,30 @@ def test_pcm_input_matches_reader_then_analyzer(ctx, orc):
         # identical to uploading the widened f64 samples (the conversion itself is bit-exact)
         got64, _ = ctx.stft_features_batch(wide, offs, lens, 2048, 512, orc.HANNING, SR)
         assert np.array_equal(got, got64, equal_nan=True)
+
+
+def test_next_rows_autocorrelation_and_time_features(ctx, aus, orc):
+    """SURVEY 8(f) items 2 and 3: analysis::autocorrelation and dc_bias / dbfs_max / energy / zero_crossing_rate."""
+    for N in (64, 1024, 2048, 8192):
+        x = orc.synth_signal(3 * N, SR, seed=23, file_id=N).reshape(3, N)
+        ref = np.stack([orc.autocorrelation(r, N) for r in x])
+        got = ctx.autocorrelation(x, N)
+        assert np.max(np.abs(got - ref)) <= RTOL64 * np.max(np.abs(ref))
+        assert np.max(np.abs(ctx.autocorrelation(x[1], N) - ref[1])) <= RTOL64 * np.max(np.abs(ref))
+    with pytest.raises(aus.SpectrumError) as e:
+        ctx.autocorrelation(np.zeros(100), 128)
+    assert e.value.error_msg == "The audio length does not match the FFT size."
+    lens = [70001, 1, 2, 3, 200000, 4097]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    a = orc.synth_signal(sum(lens), SR, seed=24)
+    a[offs[4] + 10:offs[4] + 20] = 0.0                    # exact zeros: the second zero-crossing rule
+    a[offs[4] + 20] = -0.3
+    a[offs[4] + 65535:offs[4] + 65538] = [0.2, 0.0, -0.1]    # ... across a partial-sum chunk boundary
+    got = ctx.time_features_batch(a, offs, lens, SR)
+    for i, (o, n) in enumerate(zip(offs, lens)):
+        seg = a[o:o + n]
+        ref = np.array([orc.dc_bias(seg), orc.dbfs_max(seg), orc.energy(seg), orc.zero_crossing_rate(seg, SR)])
+        assert got[i, 3] == ref[3], (i, got[i], ref)                      # a count: exact
+        assert np.all(np.abs(got[i, :3] - ref[:3]) <= RTOL64 * np.abs(ref[:3])), (i, got[i], ref)
+    assert aus.analysis.energy(a[:5000]) == pytest.approx(orc.energy(a[:5000]), rel=RTOL64)
+    assert aus.analysis.dbfs_max(np.zeros(10)) == -np.inf

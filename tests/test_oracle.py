@@ -266,3 +266,28 @@ def test_oracle_reproduces_golden_fixtures(orc):
     assert np.allclose(orc.analyze_spectrogram(g["an_mag"], 2048, SR), g["an_feat"], **tight)
     for w in range(5):
         assert np.array_equal(orc.generate_window(w, 16), g[f"win{w}_16"]) or np.allclose(orc.generate_window(w, 16), g[f"win{w}_16"], rtol=0, atol=1e-16)
+
+
+# ---------------------------------------------------------------------------------------------- SURVEY 8(f) rows
+def test_autocorrelation_is_reversed_scaled_linear_autocorrelation(orc):
+    """s_a_t.rs:31-70 returns samples [N, 2N) of the un-normalised inverse: 2N x the linear autocorrelation at lag N - i."""
+    N = 256
+    x = orc.synth_signal(N, seed=31)
+    ac = orc.autocorrelation(x, N)
+    full = np.correlate(x, x, "full")                      # lag l at index N - 1 + l
+    i = np.arange(1, N)
+    assert np.max(np.abs(ac[i] - 2 * N * full[N - 1 + (N - i)])) <= 1e-12 * np.max(np.abs(ac))
+    assert abs(ac[0]) <= 1e-9                              # lag N: no overlap
+    with pytest.raises(orc.SpectrumError):
+        orc.autocorrelation(x[:-1], N)
+
+
+def test_time_domain_scalars(orc):
+    a = np.array([0.5, -0.25, 0.0, -0.5, 0.0, 0.75, 0.0])
+    assert orc.dc_bias(a) == pytest.approx(0.5 / 7)
+    assert orc.energy(a) == pytest.approx(np.sqrt(np.mean(a ** 2)))
+    assert orc.dbfs_max(a) == pytest.approx(20 * np.log10(0.75))
+    assert orc.dbfs_max(np.zeros(4)) == -np.inf and orc.dbfs(1e-21) == -np.inf
+    # i=1: 0.5*-0.25<0 (+1); i=2: prod 0, a[3]<0 and a[2]==0 (+1); i=3: prod 0, a[4]<0? no; i=4: a[5]<0? no; i=5, 6: no
+    assert orc.zero_crossing_rate(a, 7) == 2.0
+    assert orc.energy(np.array([])) == 0.0
