@@ -55,6 +55,7 @@ SIGNATURES = {
     "aus_ctx_synchronize": (c_int, [c_void_p]),
     "aus_ctx_launch_count": (c_uint64, [c_void_p]),
     "aus_ctx_set_chunk_samples": (c_int, [c_void_p, c_uint64]),
+    "aus_ctx_set_direct_load": (c_int, [c_void_p, c_int]),
     "aus_num_frames": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "aus_irstft_len": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "aus_generate_window": (c_int, [c_int, c_size_t, _p_d]),

@@ -85,6 +85,10 @@ class Context:
         import torch
         self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_direct_load(self, on: bool):
+        """Input staging of full aligned frames: False = TMA bulk copy into shared memory, True = global -> registers."""
+        _lib.check(self._lib.aus_ctx_set_direct_load(self._h, 1 if on else 0))
+
     def set_chunk_samples(self, n: int):
         """Granularity of the copy/compute pipeline of the host-pointer feature calls (default 32 Mi samples)."""
         _lib.check(self._lib.aus_ctx_set_chunk_samples(self._h, int(n)))

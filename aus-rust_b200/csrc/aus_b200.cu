@@ -72,6 +72,7 @@ struct aus_ctx {
     bool own_stream = true;
     int sm_count = 148;
     uint64_t launches = 0;
+    int direct_load = 0;                      // experiment knob, see aus_ctx_set_direct_load
     uint64_t chunk_samples = 32ull << 20;     // host pipeline granularity: 32 Mi samples = 256 MB of f64
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
@@ -232,6 +233,11 @@ extern "C" int aus_ctx_synchronize(aus_ctx *c) {
     return AUS_OK;
 }
 extern "C" uint64_t aus_ctx_launch_count(const aus_ctx *c) { return c ? c->launches : 0; }
+extern "C" int aus_ctx_set_direct_load(aus_ctx *c, int on) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    c->direct_load = on ? 1 : 0;
+    return AUS_OK;
+}
 extern "C" int aus_ctx_set_chunk_samples(aus_ctx *c, uint64_t n) {
     if (!c || n == 0) return fail(AUS_ERR_INVALID, "bad argument");
     c->chunk_samples = n;
@@ -658,6 +664,7 @@ static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t
     p.twN = (const Cx<T> *)tb->twN;
     p.log2tab = (const double2 *)c->log2tab;
     p.npass = 2;
+    p.direct = c->direct_load;
     p.feat = d_feat;
     p.spec = d_spec;
     if (d_feat) {

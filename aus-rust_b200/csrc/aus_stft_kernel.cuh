@@ -59,6 +59,7 @@ template <typename T> struct StftParams {
     int wtype;
     int tma_ok;                        // audio base is 16-byte aligned
     int npass;                         // always 2; a runtime value so the shared radix-32 body stays one rolled loop
+    int direct;                        // 1: full aligned frames are read global -> registers (no shared staging); 0: TMA staging
     const Cx<T> *win2;                 // [M] (0.5 w[2n], 0.5 w[2n+1]) -- the 1/2 of the real-FFT split is folded in
     // twiddles are stored in CONSUMPTION order, so the 32 lanes of a warp always read 32 consecutive entries:
     const Cx<T> *tw2;                  // [32][C2] pass-2 twiddles  W_M^(c R3 r) at [r][c], C2 = min(TPF, 32)
@@ -100,7 +101,8 @@ template <int SHIFT> __device__ __forceinline__ int padi(int i) { return i + (i 
 // Forward packed FFT of the frame staged in buf (as N reals == M complex, unpadded).  On return buf holds
 // Z'[k] = FFT_M(z')[k] in the "Z layout" (index k + (k >> 4)), where z' = 0.5 * window * z.
 template <typename T, int LOG2N>
-__device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed) {
+__device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
+                                          const Cx<T> *gsrc = nullptr) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, R3 = C::R3, XS = C::XS;
     Cx<T> v[32];
@@ -132,7 +134,10 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
 #pragma unroll 1
         for (int pass = 0; pass < p.npass; ++pass) {
             if (pass == 0) {
-                if (prewindowed) {
+                if (gsrc != nullptr) {                        // samples straight from global memory (16-byte, coalesced)
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = emul(ldg_cx(gsrc + lbase + r * lstride), ldg_cx(tab + r * tstride));
+                } else if (prewindowed) {
 #pragma unroll
                     for (int r = 0; r < 32; ++r) v[r] = buf[lbase + r * lstride];
                 } else {
@@ -544,7 +549,9 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
             src = p.audio + p.file_off[f] + s;
         }
         const bool prewindowed = L < N;                                 // short last frame, fft.rs:148-159
-        const bool use_tma = active && !prewindowed && p.tma_ok && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        const bool aligned = active && !prewindowed && p.tma_ok && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        const bool direct = aligned && p.direct && C::R1 == 32;        // group-uniform
+        const bool use_tma = aligned && !direct;
         // ---- stage the frame's samples into the group buffer (TMA bulk copy when 16-byte aligned and full length;
         //      otherwise a cooperative copy that also applies the short last-frame window).  Groups sharing a warp
         //      may take different paths, so no barrier sits inside a branch.
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
                 mbar_arrive_expect_tx(bar, (uint32_t)(N * sizeof(T)));
                 tma_load_1d(buf, src, (uint32_t)(N * sizeof(T)), bar);
             }
-        } else {
+        } else if (!direct) {
             T *bufr = reinterpret_cast<T *>(buf);
 #pragma unroll 1
             for (int i = t; i < N; i += TPF) {
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
         }
         group_sync<TPF, C::BLOCK>(grp);
 
-        frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed);
+        frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr);
 
         // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)
         FeatAcc<T> acc;

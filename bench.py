@@ -189,6 +189,8 @@ def run_ours(args):
 
     ctx = aus.Context(local)
     ctx.use_torch_stream()
+    if args.direct_load is not None:
+        ctx.set_direct_load(bool(args.direct_load))
 
     files = args.files
     lens = np.full(files, FILE_SAMPLES, dtype=np.uint64)
@@ -325,6 +327,7 @@ def main():
     ap.add_argument("--files", type=int, default=4, help="1-hour files resident per GPU")
     ap.add_argument("--e2e-files", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--direct-load", type=int, default=None, help="experiment: 1 = global->register input loads, 0 = TMA staging")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

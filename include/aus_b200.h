@@ -87,6 +87,9 @@ int aus_ctx_set_stream(aus_ctx *ctx, void *cuda_stream);/* run on a caller-owned
 int aus_ctx_synchronize(aus_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t aus_ctx_launch_count(const aus_ctx *ctx);
+/* input staging of the forward kernels for full, 16-byte aligned frames: 0 (default) = TMA bulk copy into the frame
+ * group's shared buffer; 1 = coalesced 16-byte loads global -> registers (no shared staging).  Results are identical. */
+int aus_ctx_set_direct_load(aus_ctx *ctx, int on);
 /* granularity (samples) of the host-pointer feature path's copy/compute pipeline; default 32 Mi samples (256 MB f64) */
 int aus_ctx_set_chunk_samples(aus_ctx *ctx, uint64_t n_samples);
 

@@ -435,3 +435,31 @@ def test_next_rows_autocorrelation_and_time_features(ctx, aus, orc):
         assert np.all(np.abs(got[i, :3] - ref[:3]) <= RTOL64 * np.abs(ref[:3])), (i, got[i], ref)
     assert aus.analysis.energy(a[:5000]) == pytest.approx(orc.energy(a[:5000]), rel=RTOL64)
     assert aus.analysis.dbfs_max(np.zeros(10)) == -np.inf
+
+
+def test_randomised_parameter_sweep(ctx, orc):
+    """Random fft sizes, hops (odd, 1, = fft_size), windows and lengths, features + spectra + inverse, f64."""
+    rng = np.random.default_rng(2026)
+    sizes = [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
+    for trial in range(36):
+        N = int(sizes[trial % len(sizes)])
+        hop = int(rng.choice([1, 3, N // 4, N // 2, N, int(rng.integers(1, N + 1)), N // 3 + 1]))
+        if hop < 8 and N > 512:
+            hop = N // 8 + int(rng.integers(0, 5))          # keep the oracle's frame count small
+        window = int(rng.integers(0, 5))
+        n = int(rng.integers(0, 4 * N + 50)) if hop >= 8 else int(rng.integers(0, N + 40))
+        x = orc.synth_signal(n, SR, freq=float(rng.uniform(50, 8000)), seed=100 + trial, file_id=trial)
+        what = f"trial {trial}: N={N} hop={hop} w={window} n={n}"
+        Sref = orc.rstft(x, N, hop, window)
+        S = ctx.rstft(x, N, hop, window)
+        assert S.shape == Sref.shape, what
+        assert np.array_equal(np.isnan(S), np.isnan(Sref)), what
+        assert_spectra(np.nan_to_num(S), np.nan_to_num(Sref), RTOL64, what)
+        if not np.isnan(Sref).any():
+            sc = cancellation_scales(np.abs(Sref), N, SR)
+            assert_features(ctx.stft_features(x, N, hop, window, SR), orc.stft_features(x, N, hop, window, SR), RTOL64, what, scales=sc)
+            if window in (3, 4) and Sref.shape[0] * N < 400000:          # windows without (near-)zero end points
+                ref = orc.irstft(Sref, N, hop, window, normalize=False)
+                got = ctx.irstft(Sref, N, hop, window, normalize=False)
+                assert got.shape == ref.shape, what
+                assert np.max(np.abs(got - ref)) <= RTOL64 * max(np.max(np.abs(ref)), 1e-300), what
