@@ -34,7 +34,8 @@ class SpectrumError(AusError):
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libaus_b200.so")
+    # AUS_B200_LIB: load another build of the same C ABI (kernel experiments, tools/kbench.py); default = the in-tree build
+    return os.environ.get("AUS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libaus_b200.so")
 
 
 _LIB = None
@@ -56,6 +57,7 @@ SIGNATURES = {
     "aus_ctx_launch_count": (c_uint64, [c_void_p]),
     "aus_ctx_set_chunk_samples": (c_int, [c_void_p, c_uint64]),
     "aus_ctx_set_direct_load": (c_int, [c_void_p, c_int]),
+    "aus_ctx_set_forward_variant": (c_int, [c_void_p, c_int]),
     "aus_num_frames": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "aus_irstft_len": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "aus_generate_window": (c_int, [c_int, c_size_t, _p_d]),

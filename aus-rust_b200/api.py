@@ -89,6 +89,10 @@ class Context:
         """Input staging of full aligned frames: False = TMA bulk copy into shared memory, True = global -> registers."""
         _lib.check(self._lib.aus_ctx_set_direct_load(self._h, 1 if on else 0))
 
+    def set_forward_variant(self, mode: int):
+        """Forward kernel for fft_size <= 2048: -1 auto, 0 shared-memory tail, 1 register-resident tail."""
+        _lib.check(self._lib.aus_ctx_set_forward_variant(self._h, int(mode)))
+
     def set_chunk_samples(self, n: int):
         """Granularity of the copy/compute pipeline of the host-pointer feature calls (default 32 Mi samples)."""
         _lib.check(self._lib.aus_ctx_set_chunk_samples(self._h, int(n)))

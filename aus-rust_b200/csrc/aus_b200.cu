@@ -2,6 +2,7 @@
 // tables, feature-parameter derivation, kernel dispatch.  There is no CPU compute path in this file: every
 // entry point either launches the sm_100a kernels or returns an error.
 #include "../../include/aus_b200.h"
+#include <cstdlib>
 #include "aus_istft_kernel.cuh"
 
 #include <algorithm>
@@ -74,6 +75,7 @@ struct aus_ctx {
     uint64_t launches = 0;
     int direct_load = 0;                      // experiment knob, see aus_ctx_set_direct_load
     uint64_t chunk_samples = 32ull << 20;     // host pipeline granularity: 32 Mi samples = 256 MB of f64
+    int rr_mode = -1;                         // forward-kernel variant: -1 auto, 0 shared-memory tail, 1 register-resident tail
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
     DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw;
@@ -166,6 +168,7 @@ extern "C" int aus_ctx_create(int device, aus_ctx **out) {
     if (!c) return fail(AUS_ERR_ALLOC, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *rr = getenv("AUS_B200_RR")) c->rr_mode = (rr[0] == '0') ? 0 : (rr[0] == '1') ? 1 : -1;   // ablation knob
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -236,6 +239,11 @@ extern "C" uint64_t aus_ctx_launch_count(const aus_ctx *c) { return c ? c->launc
 extern "C" int aus_ctx_set_direct_load(aus_ctx *c, int on) {
     if (!c) return fail(AUS_ERR_INVALID, "null context");
     c->direct_load = on ? 1 : 0;
+    return AUS_OK;
+}
+extern "C" int aus_ctx_set_forward_variant(aus_ctx *c, int mode) {
+    if (!c || mode < -1 || mode > 1) return fail(AUS_ERR_INVALID, "bad argument");
+    c->rr_mode = mode;
     return AUS_OK;
 }
 extern "C" int aus_ctx_set_chunk_samples(aus_ctx *c, uint64_t n) {
@@ -356,10 +364,10 @@ static int fill_feature_params_check(size_t N, uint32_t sr) {     // argument va
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
-    using C = Cfg<T, LG>;
+template <typename T, int LG, bool RR> static int launch_stft_v(aus_ctx *c, const StftParams<T> &p) {
+    using C = Cfg<T, LG, RR>;
     static bool attr_done[64] = {false};
-    auto kern = stft_kernel<T, LG>;
+    auto kern = stft_kernel<T, LG, RR>;
     const size_t smem = C::smem_bytes();
     if (!attr_done[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -375,6 +383,16 @@ template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftPar
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return AUS_OK;
+}
+// Which forward kernel: the register-resident tail (aus_stft_r.cuh) exists for fft_size <= 2048.  Measured on B200 at
+// fft 2048 / hop 512: f32 +7 % (features) / +23 % (spectra), f64 spectra +17 %, f64 features -5 % (8 warps x 255 registers
+// against 12 x 168) -- so f64 features keep the shared-memory tail.  c->rr_mode (AUS_B200_RR=0|1) overrides for ablations.
+template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
+    if constexpr (LG <= 11) {
+        const bool auto_rr = sizeof(T) == 4 || p.raw == nullptr;
+        if (c->rr_mode == 1 || (c->rr_mode < 0 && auto_rr)) return launch_stft_v<T, LG, true>(c, p);
+    }
+    return launch_stft_v<T, LG, false>(c, p);
 }
 template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
     using C = Cfg<T, LG>;
@@ -417,6 +435,14 @@ template <typename T, int LG> static int launch_istft_t(aus_ctx *c, const IstftP
     return AUS_OK;
 }
 
+// AUS_DEV_LG (development builds only, e.g. -DAUS_DEV_LG=11): instantiate a single fft_size so one kernel iterates in seconds
+#ifdef AUS_DEV_LG
+#define AUS_DISPATCH_LG(lg, FN, ...)                                          \
+    switch (lg) {                                                             \
+    case AUS_DEV_LG: return FN<T, AUS_DEV_LG>(__VA_ARGS__);                   \
+    default: return fail(AUS_ERR_UNSUPPORTED, "development build: single fft_size"); \
+    }
+#else
 #define AUS_DISPATCH_LG(lg, FN, ...)                                          \
     switch (lg) {                                                             \
     case 6: return FN<T, 6>(__VA_ARGS__);                                     \
@@ -430,6 +456,7 @@ template <typename T, int LG> static int launch_istft_t(aus_ctx *c, const IstftP
     case 14: return FN<T, 14>(__VA_ARGS__);                                   \
     default: return fail(AUS_ERR_UNSUPPORTED, "fft_size must be in [64, 16384]"); \
     }
+#endif
 template <typename T> static int launch_stft(aus_ctx *c, int lg, const StftParams<T> &p) { AUS_DISPATCH_LG(lg, launch_stft_t, c, p) }
 template <typename T> static int launch_analyzer(aus_ctx *c, int lg, const StftParams<T> &p) { AUS_DISPATCH_LG(lg, launch_analyzer_t, c, p) }
 template <typename T> static int launch_istft(aus_ctx *c, int lg, const IstftParams<T> &p) { AUS_DISPATCH_LG(lg, launch_istft_t, c, p) }
@@ -671,7 +698,9 @@ static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t
         AUS_TRY(c->raw.ensure((size_t)b.total_frames * RAW_N * sizeof(double)));
         p.raw = (double *)c->raw.p;
     }
-    if (d_feat && d_spec) {           // both outputs: one spectra-only launch (coalesced stores) + one fused feature launch
+    const bool fused_both = lg <= 11 && (c->rr_mode == 1 || (c->rr_mode < 0 && sizeof(T) == 4));
+    if (d_feat && d_spec && !fused_both) {   // both outputs: one spectra-only launch + one feature launch, except where the
+                                             // register-resident kernel stores spectra and features from one pass
         StftParams<T> ps = p;
         ps.raw = nullptr;
         ps.feat = nullptr;

@@ -117,6 +117,37 @@ template <typename T, int IDX> __device__ __forceinline__ T tw32_sin() {
     else { constexpr T c = (T)w32_sin(IDX); return c; }
 }
 
+// Pass-2 input twiddles are the powers w^r, r = 1..31, of one per-thread root w = tab[stride].  The 31 table loads per
+// frame (124 L1 wavefronts in f64, and a 16 KB table that does not fit next to the window in what the shared-memory
+// carve-out leaves of L1) are replaced by four anchors w^1, w^8, w^16, w^24 and a running product in between: at most
+// seven multiplications deep (~1e-15 relative in f64).  f32 keeps the table (it is issue-bound, not L1-bound).
+#ifndef AUS_TW2_RECUR
+#define AUS_TW2_RECUR(T) (sizeof(T) == 8)
+#endif
+template <typename T, typename F> __device__ __forceinline__ void for_pass2_twiddles(const Cx<T> *tab, int stride, F &&f) {
+    if constexpr (AUS_TW2_RECUR(T)) {
+        const Cx<T> w1 = ldg_cx(tab + stride);
+        Cx<T> a8 = ldg_cx(tab + 8 * stride), a16 = ldg_cx(tab + 16 * stride), a24 = ldg_cx(tab + 24 * stride);
+        Cx<T> a0 = w1;
+        f(std::integral_constant<int, 1>{}, a0);
+        f(std::integral_constant<int, 8>{}, a8);
+        f(std::integral_constant<int, 16>{}, a16);
+        f(std::integral_constant<int, 24>{}, a24);
+        static_for<1, 8>([&](auto i_) {
+            constexpr int i = decltype(i_)::value;
+            if constexpr (i < 7) { a0 = cmul(a0, w1); f(std::integral_constant<int, 1 + i>{}, a0); }
+            a8 = cmul(a8, w1);
+            f(std::integral_constant<int, 8 + i>{}, a8);
+            a16 = cmul(a16, w1);
+            f(std::integral_constant<int, 16 + i>{}, a16);
+            a24 = cmul(a24, w1);
+            f(std::integral_constant<int, 24 + i>{}, a24);
+        });
+    } else {
+        static_for<1, 32>([&](auto r_) { f(r_, ldg_cx(tab + decltype(r_)::value * stride)); });
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ radix-R DFT
 // Forward DFT (sign -1) of v[0..R) held in registers: decimation-in-frequency radix-2 network, fully unrolled.
 // The result is left in bit-reversed order: natural output q is v[bitrev(q, log2 R)].  All indices are
@@ -180,6 +211,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// L2 prefetch of a byte range (16-byte aligned start, size multiple of 16)
+__device__ __forceinline__ void prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 // 1-D TMA bulk copy shared -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_1d(void *dst, const void *src, uint32_t bytes) {

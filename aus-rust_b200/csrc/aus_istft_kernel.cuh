@@ -12,6 +12,7 @@
 // recomputed instead of communicated.  A sample is divided by its window norm the moment its last frame lands.
 #pragma once
 #include "aus_stft_kernel.cuh"
+#include "aus_stft_r.cuh"
 
 namespace aus {
 

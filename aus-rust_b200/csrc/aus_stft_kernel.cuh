@@ -18,9 +18,19 @@
 #pragma once
 #include "aus_device.cuh"
 
+#ifndef AUS_F64_BLOCK_R
+#define AUS_F64_BLOCK_R 256      // f64 CTA size of the register-resident path; registers are allocated per 4 warps
+#endif
+#ifndef AUS_L2_PREFETCH
+#define AUS_L2_PREFETCH 1        // prefetch the next iteration's frame into L2 while this one is processed
+#endif
+
 namespace aus {
 
-template <typename T, int LOG2N> struct Cfg {
+// RR: register-resident tail (aus_stft_r.cuh), fft_size <= 2048 only.  It wants ~230 registers in f64, so those CTAs are
+// 8 warps x 255 registers instead of 12 x 168; that also shrinks the shared-memory carve-out enough for the window table
+// to stay in L1 (hit rate 68 % -> 99 %).
+template <typename T, int LOG2N, bool RR = false> struct Cfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int M = N / 2;
     static constexpr int K = M + 1;
@@ -29,9 +39,14 @@ template <typename T, int LOG2N> struct Cfg {
     static constexpr int R1 = THREE ? 32 : TPF;              // first radix (TPF == 1: single radix-32 pass)
     static constexpr int R3 = THREE ? M / 1024 : 1;
     // f64: 12 warps x 168 registers per SM (3 per scheduler) when the group buffers fit; f32: 2 CTAs x 8 warps x 128 regs
-    static constexpr int BLOCK = (sizeof(T) == 8 && TPF >= 16 && TPF <= 128) ? 384 : 256;
+    static constexpr int BLOCK = (sizeof(T) == 8 && RR) ? AUS_F64_BLOCK_R
+                                 : (sizeof(T) == 8 && TPF >= 16 && TPF <= 128) ? 384 : 256;
     static constexpr int MINB = (sizeof(T) == 4) ? 2 : 1;
     static constexpr int FPB = BLOCK / TPF;                  // frame groups per CTA
+    // register budget of the forward kernel: all 64 Ki registers of the SM split over the resident warps (allocation
+    // granularity: 8 registers per thread).  __maxnreg__ instead of __launch_bounds__, which rounds the CTA up to 128 threads.
+    static constexpr int MAXREG_RAW = (65536 / (BLOCK * MINB)) & ~7;
+    static constexpr int MAXREG = MAXREG_RAW > 255 ? 255 : MAXREG_RAW;
     static constexpr int XS = (R1 >= 16) ? ilog2(R1) : 5;    // exchange-layout pad shift
     static constexpr int BUF = M + M / 16 + 2;               // complex elements per group buffer: slots 0 .. zslot(M), even
     static constexpr int NW = TPF > 32 ? TPF / 32 : 1;
@@ -44,6 +59,7 @@ template <typename T, int LOG2N> struct Cfg {
     static constexpr int LOGREP = sizeof(T) == 8 ? 8 : 1;
     __host__ __device__ static constexpr size_t smem_bytes() { return off_log() + (size_t)LOG2_TAB * LOGREP * sizeof(double2); }
     static_assert(LOG2N >= 6 && LOG2N <= 14, "fft_size must be 64..16384");
+    static_assert(!RR || TPF <= 32, "register-resident tail: fft_size <= 2048");
 };
 
 // Everything the kernels need besides the template parameters.  Filled on the host (aus_b200.cu).
@@ -148,8 +164,10 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
                 }
             } else {
                 v[0] = buf[lbase];
-#pragma unroll
-                for (int r = 1; r < 32; ++r) v[r] = cmul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
+                for_pass2_twiddles<T>(tab, tstride, [&](auto r_, const Cx<T> &w) {
+                    constexpr int r = decltype(r_)::value;
+                    v[r] = cmul(buf[lbase + r * lstride], w);
+                });
             }
             group_sync<TPF, C::BLOCK>(grp);                   // every load done before buf is overwritten
             dft_dif<32>(v);
@@ -202,11 +220,10 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
         // ---- pass 2: radix 32, Ns = R1 = TPF, one butterfly per thread (j = t), natural-order output
         {
             const int j = t;
-            static_for<0, 32>([&](auto r_) {
+            v[0] = buf[padi<XS>(j)];
+            for_pass2_twiddles<T>(p.tw2 + j, TPF, [&](auto r_, const Cx<T> &w) {
                 constexpr int r = decltype(r_)::value;
-                Cx<T> z = buf[padi<XS>(j + r * TPF)];
-                if constexpr (r > 0) z = cmul(z, ldg_cx(&p.tw2[r * TPF + j]));
-                v[r] = z;
+                v[r] = cmul(buf[padi<XS>(j + r * TPF)], w);
             });
             group_sync<TPF, C::BLOCK>(grp);
             dft_dif<32>(v);
@@ -513,10 +530,18 @@ __global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, in
     for (int i = 0; i < 14; ++i) dst[i] = (T)out[i];
 }
 
+// register-resident variants for fft_size <= 2048, defined in aus_stft_r.cuh
+template <typename T, int LOG2N, typename C>
+__device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
+                                               const Cx<T> *gsrc, Cx<T> (&v)[32]);
+template <typename T, int LOG2N, typename C>
+__device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double *scratch, const double2 *logtab,
+                                             const StftParams<T> &p, unsigned long long g, bool active, int t, int grp);
+
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int LOG2N>
-__global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stft_kernel(const StftParams<T> p) {
-    using C = Cfg<T, LOG2N>;
+template <typename T, int LOG2N, bool RR>
+__global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftParams<T> p) {
+    using C = Cfg<T, LOG2N, RR>;
     constexpr int N = C::N, M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
@@ -548,6 +573,14 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
             L = rem < (unsigned long long)N ? (int)rem : N;             // fft.rs:130-144
             src = p.audio + p.file_off[f] + s;
         }
+#if AUS_L2_PREFETCH
+        if (active && t == 0 && g + stride < p.file_first[f + 1]) {     // same file: its next frame of this group, if full
+            const unsigned long long s2 = (g + stride - p.file_first[f]) * (unsigned long long)p.hop;
+            const T *src2 = p.audio + p.file_off[f] + s2;
+            if (s2 + N <= p.file_len[f] && (reinterpret_cast<uintptr_t>(src2) & 15) == 0)
+                prefetch_l2(src2, (uint32_t)(N * sizeof(T)));
+        }
+#endif
         const bool prewindowed = L < N;                                 // short last frame, fft.rs:148-159
         const bool aligned = active && !prewindowed && p.tma_ok && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
         const bool direct = aligned && p.direct && C::R1 == 32;        // group-uniform
@@ -578,6 +611,15 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) stf
         }
         group_sync<TPF, C::BLOCK>(grp);
 
+        if constexpr (RR) {
+            // the last pass, the real-FFT split and the first feature pass stay in registers (aus_stft_r.cuh)
+            Cx<T> v[32];
+            frame_fft_keep<T, LOG2N, C>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v);
+            frame_tail_r<T, LOG2N, C>(v, buf, scratch, logtab, p, g, active, t, grp);
+            fence_proxy_async();                                        // generic accesses to buf before the next TMA write
+            group_sync<TPF, C::BLOCK>(grp);
+            continue;
+        }
         frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr);
 
         // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)

@@ -1,0 +1,482 @@
+// aus_stft_r.cuh -- register-resident tail of the forward kernel for fft_size <= 2048 (TPF <= 32: one frame per
+// warp or less).  sm_100a.
+//
+// The L1/shared data pipe is the busiest unit of the fused kernel (ncu: 70 % of its wavefront peak at 18 % occupancy),
+// so this path removes shared-memory round trips instead of arithmetic:
+//   * the last radix-32 pass leaves Z[j + TPF s], s = 0..31, in the registers of thread j (no store);
+//   * the partner Z[M - k] of the real-FFT split (fft.rs:171-172 via the packed transform) lives in thread
+//     (TPF - j) mod TPF at s' = 31 - s, so half of the registers are swapped with it by warp shuffles (in place);
+//   * X[k], X[M-k] are formed in registers and, when the caller wants spectra (K2), stored straight to HBM
+//     (consecutive lanes -> consecutive bins, fully coalesced) -- no staging buffer, no second launch;
+//   * |X|^2 goes to shared memory once, transposed (bin b at slot b + b/32), so that each thread then walks 32
+//     consecutive bins for the order-dependent work (running sum -> roll-off) together with the second feature pass.
+#pragma once
+#include "aus_stft_kernel.cuh"
+
+#ifndef AUS_TAIL_BATCH
+#define AUS_TAIL_BATCH(T) 4
+#endif
+#ifndef AUS_PAIR_SHFL
+#define AUS_PAIR_SHFL(T) (sizeof(T) == 4)    // partner exchange by warp shuffles (f32) or through the group buffer (f64)
+#endif
+
+namespace aus {
+
+// Transposed power layout: bin b at T-slot b + b/32, so a thread's 32 consecutive bins [32 t, 32 t + 32) are 32
+// consecutive slots from 33 t (conflict-free both ways); bin M takes the pad slot that closes the last chunk.
+__device__ __forceinline__ int pslot_lt(int b) { return b + (b >> 5); }                          // b < M
+template <int M> __device__ __forceinline__ int pslot(int b) { return b + (b >> 5) - (b == M ? 1 : 0); }
+template <int M> struct RLay {
+    static constexpr int CO = (M + M / 32 + 2 + 1) & ~1;      // T-element offset of the running-sum region
+};
+
+// (cos, sin)(2 pi s / 64), s = 0..15: the post-twiddle of bin k = t + TPF s is W_N^t x W_64^s for every fft_size here
+// (N = 64 TPF), so a thread needs one table entry per frame and the rest are constant-bank operands (f64) / immediates.
+__constant__ double c_w64_cos[16] = {1.0, 0.99518472667219688624483695310947992, 0.98078528040323044912618223613423904, 0.95694033573220886493579788698026997, 0.92387953251128675612818318939678829, 0.88192126434835502971275686366038835, 0.83146961230254523707878837761790576, 0.7730104533627369608109066097584698, 0.70710678118654752440084436210484904, 0.63439328416364549821517161322549337, 0.55557023301960222474283081394853287, 0.47139673682599764855638762590525438, 0.38268343236508977172845998403039887, 0.29028467725446236763619237581739527, 0.19509032201612826784828486847702224, 0.098017140329560601994195563888641846};
+__constant__ double c_w64_sin[16] = {0.0, 0.098017140329560601994195563888641846, 0.19509032201612826784828486847702224, 0.29028467725446236763619237581739527, 0.38268343236508977172845998403039887, 0.47139673682599764855638762590525438, 0.55557023301960222474283081394853287, 0.63439328416364549821517161322549337, 0.70710678118654752440084436210484904, 0.7730104533627369608109066097584698, 0.83146961230254523707878837761790576, 0.88192126434835502971275686366038835, 0.92387953251128675612818318939678829, 0.95694033573220886493579788698026997, 0.98078528040323044912618223613423904, 0.99518472667219688624483695310947992};
+__host__ __device__ constexpr double w64_cos(int i) {
+    constexpr double t[16] = {1.0, 0.99518472667219688624483695310947992, 0.98078528040323044912618223613423904, 0.95694033573220886493579788698026997, 0.92387953251128675612818318939678829, 0.88192126434835502971275686366038835, 0.83146961230254523707878837761790576, 0.7730104533627369608109066097584698, 0.70710678118654752440084436210484904, 0.63439328416364549821517161322549337, 0.55557023301960222474283081394853287, 0.47139673682599764855638762590525438, 0.38268343236508977172845998403039887, 0.29028467725446236763619237581739527, 0.19509032201612826784828486847702224, 0.098017140329560601994195563888641846};
+    return t[i];
+}
+__host__ __device__ constexpr double w64_sin(int i) {
+    constexpr double t[16] = {0.0, 0.098017140329560601994195563888641846, 0.19509032201612826784828486847702224, 0.29028467725446236763619237581739527, 0.38268343236508977172845998403039887, 0.47139673682599764855638762590525438, 0.55557023301960222474283081394853287, 0.63439328416364549821517161322549337, 0.70710678118654752440084436210484904, 0.7730104533627369608109066097584698, 0.83146961230254523707878837761790576, 0.88192126434835502971275686366038835, 0.92387953251128675612818318939678829, 0.95694033573220886493579788698026997, 0.98078528040323044912618223613423904, 0.99518472667219688624483695310947992};
+    return t[i];
+}
+template <typename T, int S> __device__ __forceinline__ Cx<T> tw64() {
+    if constexpr (sizeof(T) == 8) return Cx<T>{c_w64_cos[S], c_w64_sin[S]};
+    else { constexpr T c = (T)w64_cos(S), sn = (T)w64_sin(S); return Cx<T>{c, sn}; }
+}
+
+template <int W> __device__ __forceinline__ Cx<double> shfl_cx(Cx<double> a, int src) {
+    return Cx<double>{__shfl_sync(0xffffffffu, a.x, src, W), __shfl_sync(0xffffffffu, a.y, src, W)};
+}
+template <int W> __device__ __forceinline__ Cx<float> shfl_cx(Cx<float> a, int src) {
+    return cx_from(__shfl_sync(0xffffffffu, cx_bits(a), src, W));
+}
+// first set bit of a group-wide vote among the TPF threads of this thread's frame group (32 if none)
+template <int TPF> __device__ __forceinline__ int group_first(bool pred) {
+    unsigned b = __ballot_sync(0xffffffffu, pred);
+    if constexpr (TPF < 32) {
+        const unsigned lane = threadIdx.x & 31u;
+        b = (b >> (lane & ~(unsigned)(TPF - 1))) & ((1u << TPF) - 1u);
+    }
+    return b ? __ffs((int)b) - 1 : 32;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Forward packed FFT like frame_fft(), but the last pass stays in registers: on return natural output s of
+// thread j's final radix-32 butterfly, Z'[j + TPF s], is v[bitrev(s, 5)], and every thread of the group has
+// finished reading buf (which may be overwritten).
+template <typename T, int LOG2N, typename C>
+__device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
+                                               const Cx<T> *gsrc, Cx<T> (&v)[32]) {
+    constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, XS = C::XS;
+    static_assert(TPF <= 32, "register-resident path: one frame per warp or less");
+
+    if constexpr (M == 32) {                                  // one thread per frame: a single radix-32 pass
+        static_for<0, 32>([&](auto r_) {
+            constexpr int r = decltype(r_)::value;
+            Cx<T> z = buf[r];
+            if (!prewindowed) { const Cx<T> w = ldg_cx(&p.win2[r]); z.x *= w.x; z.y *= w.y; }
+            v[r] = z;
+        });
+        dft_dif<32>(v);
+    } else if constexpr (R1 == 32) {
+        // same rolled two-trip loop as frame_fft(): one radix-32 butterfly body shared by both passes
+        const int j = t;
+        int lbase = j, lstride = TPF;
+        const Cx<T> *tab = p.win2 + j;
+        int tstride = TPF;
+#pragma unroll 1
+        for (int pass = 0; pass < p.npass; ++pass) {
+            if (pass == 0) {
+                if (gsrc != nullptr) {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = emul(ldg_cx(gsrc + lbase + r * lstride), ldg_cx(tab + r * tstride));
+                } else if (prewindowed) {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = buf[lbase + r * lstride];
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = emul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
+                }
+            } else {
+                v[0] = buf[lbase];
+                for_pass2_twiddles<T>(tab, tstride, [&](auto r_, const Cx<T> &w) {
+                    constexpr int r = decltype(r_)::value;
+                    v[r] = cmul(buf[lbase + r * lstride], w);
+                });
+            }
+            group_sync<TPF, C::BLOCK>(grp);                   // every load done before buf is overwritten
+            dft_dif<32>(v);
+            if (pass == 0) {
+                static_for<0, 32>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    buf[33 * j + r] = v[bitrev(r, 5)];
+                });
+                group_sync<TPF, C::BLOCK>(grp);
+                lbase = j + (j >> 5);
+                lstride = TPF + TPF / 32;
+                tab = p.tw2 + (j & 31);
+                tstride = 32;
+            }
+        }
+    } else {
+        constexpr int B1 = 32 / R1;
+        static_for<0, B1>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            const int j = t + TPF * b;
+            static_for<0, R1>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const int n = j + r * (M / R1);
+                Cx<T> z = buf[n];
+                if (!prewindowed) { const Cx<T> w = ldg_cx(&p.win2[n]); z.x *= w.x; z.y *= w.y; }
+                v[b * R1 + r] = z;
+            });
+        });
+        group_sync<TPF, C::BLOCK>(grp);
+        static_for<0, B1>([&](auto b_) {
+            constexpr int b = decltype(b_)::value;
+            const int j = t + TPF * b;
+            Cx<T> u[R1];
+            static_for<0, R1>([&](auto r_) { u[decltype(r_)::value] = v[b * R1 + decltype(r_)::value]; });
+            dft_dif<R1>(u);
+            static_for<0, R1>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                buf[padi<XS>(j * R1 + r)] = u[bitrev(r, ilog2(R1))];
+            });
+        });
+        group_sync<TPF, C::BLOCK>(grp);
+        {
+            const int j = t;
+            v[0] = buf[padi<XS>(j)];
+            for_pass2_twiddles<T>(p.tw2 + j, TPF, [&](auto r_, const Cx<T> &w) {
+                constexpr int r = decltype(r_)::value;
+                v[r] = cmul(buf[padi<XS>(j + r * TPF)], w);
+            });
+            group_sync<TPF, C::BLOCK>(grp);
+            dft_dif<32>(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Second half of the feature computation on the transposed layout.  On entry the power of every bin b = 0..M sits at
+// pw[pslot<M>(b)] (written by whichever thread produced it, not yet synchronised) and (s_m, s_mk, s_pk, p_part, pmin) are
+// this thread's partial sums over the bins it produced.  Thread t then owns the 32 consecutive bins [32 t, 32 t + 32)
+// (the last thread also bin M).  Writes the frame's raw record (see finalize_kernel).
+template <typename T, int LOG2N, typename C, bool STORE_CUM>
+__device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T s_pk, T p_part, unsigned pmin, double *scratch,
+                                                 const double2 *logtab, const StftParams<T> &p, unsigned long long g,
+                                                 bool active, int t, int grp, bool mags_from_sqrt) {
+    constexpr int M = C::M, K = C::K, TPF = C::TPF;
+    const int c0 = 33 * t;                              // slot of bin 32 t
+    const int cnt = (t == TPF - 1) ? 33 : 32;           // bins in this thread's chunk (bin M: slot c0 + 32)
+    group_sync<TPF, C::BLOCK>(grp);                     // every power bin visible to the whole group
+
+    // zero / subnormal / non-finite power somewhere: magnitudes again with the exact square root (cold)
+    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt && (!power_is_normal<T>(pmin) || !(p_part < (T)INFINITY));
+    if (group_any<TPF, C::BLOCK>(bad_p, scratch, t, grp)) {
+        s_m = 0;
+        s_mk = 0;
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) {
+            const T m = Mth<T>::sqrt_exact(pw[c0 + j]);
+            s_m += m;
+            s_mk += m * (T)(32 * t + j);
+        }
+    }
+
+    // sub-band sums for the three slope regions (s_a_t.rs:190-230): bins [r_lo, r_hi) of bands 1 and 2, all threads
+    T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
+#pragma unroll 1
+    for (int b = p.r_lo[0] + t; b < p.r_hi[1]; b += TPF) {
+        const T pv = pw[pslot<M>(b)];
+        const T pk = pv * (T)b;
+        if (b < p.r_hi[0]) { b1p += pv; b1pk += pk; }
+        if (b >= p.r_lo[1]) { b2p += pv; b2pk += pk; }
+    }
+    double r[8] = {(double)s_m, (double)s_mk, (double)s_pk, (double)b1p, (double)b1pk, (double)b2p, (double)b2pk,
+                   (double)p_part};
+    group_allreduce<TPF, C::BLOCK, 8>(r, scratch, t, grp);
+    const double S_m = r[0], S_mk = r[1], P = r[7];
+
+    // central moments about the (magnitude-weighted) centroid in bins; entropy and log-mean from q = p / P; the
+    // chunk-local running sum goes to the second region (global running sum = chunk base + local, see below)
+    const T kappa = (T)(S_mk / S_m);
+    const T inv_p = (T)(1.0 / P);
+    T d2s = 0, d3s = 0, d4s = 0, ent = 0, slq = 0;
+    const unsigned gpmin = group_min_u32<TPF, C::BLOCK>(pmin, scratch, t, grp);
+    const bool badq = sizeof(T) == 8 && (!power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) ||
+                                         abnormal((T)(power_from_hi<T>(gpmin) * inv_p)));
+    const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);
+    T cum = 0;
+    {
+        const T d0 = (T)(32 * t) - kappa;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += 4) {
+            T pv[4], q[4], l[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pv[c] = pw[c0 + j0 + c];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const T d = d0 + (T)(j0 + c);
+                const T dd = d * d;
+                const T w2 = dd * pv[c];
+                d2s += w2;
+                d3s += w2 * d;
+                d4s += w2 * dd;
+                q[c] = pv[c] * inv_p;                    // make_spectrum_pmf, s_a_t.rs:284-290
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ent += q[c] * l[c];
+                slq += l[c];
+                cum += pv[c];
+                if constexpr (STORE_CUM) cw[c0 + j0 + c] = cum;
+            }
+        }
+        if (t == TPF - 1) {                              // bin M closes the last chunk
+            const T pv = pw[c0 + 32];
+            const T d = (T)M - kappa;
+            const T dd = d * d;
+            const T w2 = dd * pv;
+            d2s += w2;
+            d3s += w2 * d;
+            d4s += w2 * dd;
+            const T q = pv * inv_p;
+            const T l = Mth<T>::log2_(q, ltab);
+            ent += q * l;
+            slq += l;
+            cum += pv;
+            if constexpr (STORE_CUM) cw[c0 + 32] = cum;
+        }
+    }
+    if (badq) {                                          // group-uniform, cold: library log2 (0 * -inf = NaN, sum = -inf)
+        ent = 0;
+        slq = 0;
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) {
+            const T q = pw[c0 + j] * inv_p;
+            const T l = Mth<T>::log2_exact(q);
+            ent += q * l;
+            slq += l;
+        }
+    }
+    double q[5] = {(double)d2s, (double)d3s, (double)d4s, (double)ent, (double)slq};
+    group_allreduce<TPF, C::BLOCK, 5>(q, scratch, t, grp);
+
+    // running sum at the end of each chunk (bin order), published in the chunk's pad slot of the power region (the last
+    // chunk's pad slot holds bin M; its end value is the total and never needed)
+    double inc = (double)cum, dummy = 0.0;
+    group_inclusive_scan2<TPF, C::BLOCK>(inc, dummy, scratch, t, grp);
+    if (t < TPF - 1) pw[c0 + 32] = (T)inc;
+    group_sync<TPF, C::BLOCK>(grp);                      // chunk ends and local running sums visible to the searching threads
+
+    if (active && p.raw != nullptr) {
+        double *rec = p.raw + g * (unsigned long long)RAW_N;
+        // roll-off (s_a_t.rs:137-145): index = number of bins whose inclusive running sum is below theta * P; one thread
+        // per threshold.  Level 1: binary search over the chunk ends for the chunk where the running sum first reaches
+        // the threshold; level 2: inside that chunk (global running sum = end of the previous chunk + local).
+#pragma unroll 1
+        for (int qq = t; qq < 4; qq += TPF) {
+            const double theta = qq == 0 ? 0.5 : qq == 1 ? 0.75 : qq == 2 ? 0.9 : 0.95;
+            const T th = (T)(theta * P);
+            int c = 0;
+            {
+                int lo = 0, hi = TPF - 1;                  // first chunk in [0, TPF - 1] whose end is not below th
+#pragma unroll 1
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (pw[33 * mid + 32] < th) lo = mid + 1; else hi = mid;
+                }
+                c = lo;
+            }
+            const T bs = c > 0 ? pw[33 * c - 1] : (T)0;    // end of chunk c - 1 = pad slot 33 (c - 1) + 32
+            const int n = (c == TPF - 1) ? 33 : 32;
+            int res;
+            bool amb = false;
+            T c_at = (T)0, c_prev = bs;
+            if constexpr (STORE_CUM) {
+                const T *cl = cw + 33 * c;
+                int lo = 0, hi = n;                        // first j in [0, n] with !(base + local[j] < th)
+#pragma unroll 1
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (bs + cl[mid] < th) lo = mid + 1; else hi = mid;
+                }
+                res = 32 * c + lo;                         // = K when even bin M stays below (then the reference answers K - 1)
+                if (lo < n) c_at = bs + cl[lo];
+                else amb = c < TPF - 1;                    // inside the spectrum this happens only by rounding of the scan
+                if (lo > 0) c_prev = bs + cl[lo - 1];      // running sum through bin res - 1
+            } else {
+                const T *pl = pw + 33 * c;                 // no stored running sums: walk the chunk's powers
+                T run = bs;
+                int j = 0;
+#pragma unroll 1
+                for (; j < n; ++j) {
+                    const T nx = run + pl[j];
+                    if (!(nx < th)) { c_at = nx; break; }
+                    run = nx;
+                }
+                res = 32 * c + j;
+                if (j == n) amb = c < TPF - 1;
+                c_prev = run;
+            }
+            if constexpr (sizeof(T) == 8) {
+                // Knife edge: the threshold sits within rounding distance of a running sum, where the reference's own
+                // arithmetic -- a sequential sum of p[i] / P compared with theta (s_a_t.rs:137-145) -- decides.  Redo it
+                // exactly that way (one thread, rare).
+                const double tol = 1e-12 * P;
+                if (!amb && res < K)
+                    amb = fabs((double)c_at - (double)th) <= tol || (res >= 1 && fabs((double)th - (double)c_prev) <= tol);
+                if (!amb && res == K) amb = fabs((double)th - (double)c_prev) <= tol;
+                if (amb) {
+                    double pseq = 0.0;                     // power_spectrum.iter().sum(): sequential (analyzer.rs:44)
+                    for (int i = 0; i < K; ++i) pseq += (double)pw[pslot<M>(i)];
+                    double csum = 0.0;
+                    int i = -1;
+                    while (csum < theta && i < K - 1) {
+                        ++i;
+                        csum += (double)pw[pslot<M>(i)] / pseq;
+                    }
+                    res = i;
+                }
+            }
+            rec[RAW_ROLL0 + qq] = (double)res;
+        }
+#pragma unroll 1
+        for (int qq = t; qq < 6; qq += TPF) rec[RAW_PICK0 + qq] = (double)pw[pslot<M>(p.pick[qq])];
+        if (t == 0) {
+            rec[RAW_SM] = r[0]; rec[RAW_SMK] = r[1]; rec[RAW_SPK] = r[2];
+            rec[RAW_B1P] = r[3]; rec[RAW_B1PK] = r[4]; rec[RAW_B2P] = r[5]; rec[RAW_B2PK] = r[6];
+            rec[RAW_P] = P;
+            rec[RAW_D2] = q[0]; rec[RAW_D3] = q[1]; rec[RAW_D4] = q[2]; rec[RAW_ENT] = q[3]; rec[RAW_SLQ] = q[4];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Real-FFT split + power + first feature pass straight from the registers left by frame_fft_keep().
+template <typename T, int LOG2N, typename C>
+__device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double *scratch, const double2 *logtab,
+                                             const StftParams<T> &p, unsigned long long g, bool active, int t, int grp) {
+    constexpr int M = C::M, K = C::K, TPF = C::TPF;
+    const bool want_feat = p.raw != nullptr;
+    Cx<T> *spec = (p.spec != nullptr && active) ? p.spec + g * (unsigned long long)K : nullptr;
+    T *const pw = reinterpret_cast<T *>(buf);
+
+    // sums over the bins this thread produces: low bins k = t + TPF s and high bins M - k, s = 0..15.  With c_s = TPF s,
+    //   sum m k = t S_lo + C_lo + (M - t) S_hi - C_hi,   S = sum m, C = sum m c_s   (c_s: compile-time constants)
+    T s_lo = 0, s_hi = 0, c_lo = 0, c_hi = 0, p_lo = 0, p_hi = 0, pc_lo = 0, pc_hi = 0;
+    unsigned pmin = 0x7ff00000u;
+    // thread 0 also holds the self-paired bin M/2 = t + TPF 16: X[M/2] = conj(Z[M/2]) (x2: the halved window); it enters
+    // the sums as one more "low" bin, before the register that holds it is reused by the exchange below
+    if (t == 0) {
+        const Cx<T> zmid = v[bitrev(16, 5)];
+        const Cx<T> X = Cx<T>{zmid.x + zmid.x, -(zmid.y + zmid.y)};
+        if (spec != nullptr) spec[M / 2] = X;
+        if (want_feat) {
+            const T pm = X.x * X.x + X.y * X.y;
+            pw[pslot_lt(M / 2)] = pm;
+            pmin = power_hi(pm);
+            const T mm = Mth<T>::sqrt_(pm);
+            s_lo = mm;
+            c_lo = mm * (T)(M / 2);
+            p_lo = pm;
+            pc_lo = pm * (T)(M / 2);
+        }
+    }
+    // ---- the partner Z'[M - k] of k = t + TPF s is natural output 31 - s of thread (TPF - t) mod TPF (thread 0 pairs with
+    //      itself one step further: M - TPF s = TPF (32 - s), and its k = 0 with Z'[0] itself).
+    //      f64: the upper half of the registers goes through a [16][TPF] staging area in the (now free) upper part of the
+    //      group buffer -- row s' - 16, column j, plus Z'[0] in slot 16 TPF -- where the partner of pair s is slot
+    //      (16 - s) TPF - t for every thread, 0 included; the 64 registers are free right after the store, which is what
+    //      keeps this path inside the 168-register budget.  f32 has the registers to swap them by warp shuffles instead.
+    const Cx<T> wt = ldg_cx(&p.twN[t]);                  // (cos, sin)(2 pi t / N)
+    constexpr bool SHFL = AUS_PAIR_SHFL(T);
+    constexpr int PB = AUS_TAIL_BATCH(T);                // pairs per batch
+    Cx<T> *const xb = buf + (C::BUF - 16 * TPF - 2);
+    const int partner = (TPF - t) & (TPF - 1);
+    auto exchange = [&](auto s_) {                       // shuffle variant: in place, v[bitrev(31 - s)] <- Z'[M - k]
+        constexpr int s = decltype(s_)::value;
+        constexpr int dst = bitrev(31 - s, 5), alt = bitrev((32 - s) & 31, 5);
+        Cx<T> snd = v[dst];
+        if (t == 0) snd = v[alt];
+        if constexpr (TPF > 1) v[dst] = shfl_cx<TPF>(snd, partner);
+        else v[dst] = snd;
+    };
+    if constexpr (SHFL) {
+        // walking s downwards keeps thread 0's sources intact until they are sent; pairs are consumed in the same order
+        static_for<0, PB>([&](auto c_) { exchange(std::integral_constant<int, 15 - decltype(c_)::value>{}); });
+    } else {
+        static_for<16, 32>([&](auto s_) {
+            constexpr int s = decltype(s_)::value;
+            xb[(s - 16) * TPF + t] = v[bitrev(s, 5)];
+        });
+        if (t == 0) xb[16 * TPF] = v[0];
+        group_sync<TPF, C::BLOCK>(grp);
+    }
+    static_for<0, 16 / PB>([&](auto b_) {
+        constexpr int i0 = 16 - PB * (decltype(b_)::value + 1);           // batch = pairs i0 .. i0 + PB - 1, descending batches
+        Cx<T> B[PB];
+        if constexpr (SHFL) {
+            if constexpr (i0 > 0)
+                static_for<0, PB>([&](auto c_) { exchange(std::integral_constant<int, i0 - 1 - decltype(c_)::value>{}); });
+            static_for<0, PB>([&](auto c_) { B[decltype(c_)::value] = v[bitrev(31 - i0 - decltype(c_)::value, 5)]; });
+        } else {
+#pragma unroll
+            for (int c = 0; c < PB; ++c) B[c] = xb[(16 - i0 - c) * TPF - t];
+        }
+        Cx<T> Xlo[PB], Xhi[PB];
+        static_for<0, PB>([&](auto c_) {
+            constexpr int c = decltype(c_)::value, s = i0 + c;
+            const Cx<T> W = s == 0 ? wt : cmul(wt, tw64<T, s>());       // (cos, sin)(2 pi (t + TPF s) / N)
+            post_twiddle(v[bitrev(s, 5)], B[c], W, Xlo[c], Xhi[c]);
+        });
+        if (spec != nullptr) {
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                const int k = t + TPF * (i0 + c);
+                spec[k] = Xlo[c];                          // consecutive lanes -> consecutive bins
+                spec[M - k] = Xhi[c];
+            }
+        }
+        if (want_feat) {
+            T plo[PB], phi[PB], mlo[PB], mhi[PB];
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                const int k = t + TPF * (i0 + c);
+                plo[c] = Xlo[c].x * Xlo[c].x + Xlo[c].y * Xlo[c].y;
+                phi[c] = Xhi[c].x * Xhi[c].x + Xhi[c].y * Xhi[c].y;
+                pw[pslot_lt(k)] = plo[c];
+                pw[(i0 + c == 0) ? pslot<M>(M - k) : pslot_lt(M - k)] = phi[c];   // only k = 0 pairs with bin M
+                pmin = min(pmin, min(power_hi(plo[c]), power_hi(phi[c])));
+                mlo[c] = Mth<T>::sqrt_(plo[c]);
+                mhi[c] = Mth<T>::sqrt_(phi[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < PB; ++c) {
+                const T cs = (T)(TPF * (i0 + c));
+                s_lo += mlo[c];
+                s_hi += mhi[c];
+                c_lo += mlo[c] * cs;
+                c_hi += mhi[c] * cs;
+                p_lo += plo[c];
+                p_hi += phi[c];
+                pc_lo += plo[c] * cs;
+                pc_hi += phi[c] * cs;
+            }
+        }
+    });
+    const T tf = (T)t, mt = (T)(M - t);
+    const T s_m = s_lo + s_hi;
+    const T s_mk = (tf * s_lo + c_lo) + (mt * s_hi - c_hi);
+    const T s_pk = (tf * p_lo + pc_lo) + (mt * p_hi - pc_hi);
+    const T p_part = p_lo + p_hi;
+    if (want_feat) frame_features_r<T, LOG2N, C, true>(pw, pw + RLay<M>::CO, s_m, s_mk, s_pk, p_part, pmin, scratch, logtab, p, g, active, t, grp, true);
+}
+
+}  // namespace aus

@@ -463,3 +463,48 @@ def test_randomised_parameter_sweep(ctx, orc):
                 got = ctx.irstft(Sref, N, hop, window, normalize=False)
                 assert got.shape == ref.shape, what
                 assert np.max(np.abs(got - ref)) <= RTOL64 * max(np.max(np.abs(ref)), 1e-300), what
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("fft_size,hop", [(64, 16), (128, 32), (256, 64), (512, 128), (1024, 256), (2048, 512), (2048, 300)])
+def test_forward_kernel_variants(ctx, orc, variant, fft_size, hop):
+    """Both forward kernels for fft_size <= 2048 -- shared-memory tail (0) and register-resident tail (1, aus_stft_r.cuh)
+    -- against the oracle, f64 and f32, features + spectra in one call, ragged files incl. silence and a short last frame."""
+    import torch
+    ctx.use_torch_stream()
+    ctx.set_forward_variant(variant)
+    try:
+        lens = [5 * fft_size + 13, 0, fft_size, 3 * fft_size + hop + 1, 7]
+        sig = [orc.synth_signal(n, SR, seed=31, file_id=i) for i, n in enumerate(lens)]
+        sig[3][: 2 * fft_size] = 0.0                     # silent frames: NaN pattern of the reference
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        audio = np.concatenate(sig)
+        K = fft_size // 2 + 1
+        refs_f = [orc.stft_features(s, fft_size, hop, orc.HAMMING, SR) for s in sig]
+        refs_s = [orc.rstft(s, fft_size, hop, orc.HAMMING) for s in sig]
+        F = sum(r.shape[0] for r in refs_f)
+        for prec, tdt, tol in (("f64", torch.float64, RTOL64), ("f32", torch.float32, RTOL32)):
+            d = torch.from_numpy(audio).to(tdt).cuda()
+            feat = torch.empty((F, 14), dtype=tdt, device="cuda")
+            spec = torch.empty((F, K, 2), dtype=tdt, device="cuda")
+            ctx.stft_features_batch_dev(d, offs, lens, fft_size, hop, orc.HAMMING, SR, prec, feat, spec)
+            torch.cuda.synchronize()
+            got_f = feat.cpu().numpy().astype(np.float64)
+            got_s = torch.view_as_complex(spec).cpu().numpy().astype(np.complex128)
+            pos = 0
+            for i, (rf, rs) in enumerate(zip(refs_f, refs_s)):
+                gs, gf = got_s[pos:pos + rf.shape[0]], got_f[pos:pos + rf.shape[0]]
+                pos += rf.shape[0]
+                assert np.array_equal(np.isnan(gs), np.isnan(rs))
+                assert_spectra(np.nan_to_num(gs), np.nan_to_num(rs), tol, f"variant {variant} {prec} file {i}")
+                if prec == "f64":
+                    sc = cancellation_scales(np.abs(np.nan_to_num(rs)), fft_size, SR)
+                    assert_features(gf, rf, tol, f"variant {variant} f64 file {i}", scales=sc)
+                else:
+                    ok = np.isfinite(rf).all(axis=1)
+                    cols = [c for c in range(14) if c not in range(6, 10)]
+                    sc = cancellation_scales(np.abs(np.nan_to_num(rs)), fft_size, SR)
+                    assert_features(gf[ok][:, cols], rf[ok][:, cols], tol, f"variant {variant} f32 file {i}",
+                                    scales=sc[ok][:, cols])
+    finally:
+        ctx.set_forward_variant(-1)
