@@ -65,6 +65,7 @@ struct DevBuf {
 struct Tables {
     void *tw2 = nullptr, *tw3 = nullptr, *twNt = nullptr, *twN = nullptr;
     void *win2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *winf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // full-scale window pairs (inverse transform)
 };
 
 struct aus_ctx {
@@ -78,7 +79,8 @@ struct aus_ctx {
     int rr_mode = -1;                         // forward-kernel variant: -1 auto, 0 shared-memory tail, 1 register-resident tail
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
-    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw;
+    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw, normtab;
+    long long normtab_key = -1;            // (fft_size, hop, window, precision) the reciprocal-norm table was built for
     DevBuf pin64[2], pin32[2], pout64[2], pout32[2], ppcm[2];   // double buffers of the chunked host pipeline
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -204,9 +206,10 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
         cudaFree(kv.second.twNt);
         cudaFree(kv.second.twN);
         for (void *w : kv.second.win2) cudaFree(w);
+        for (void *w : kv.second.winf) cudaFree(w);
     }
     cudaFree(c->log2tab);
-    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw,
+    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw, &c->normtab,
                       &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1], &c->ppcm[0], &c->ppcm[1]})
         b->release();
     if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -309,6 +312,11 @@ template <typename T> static int get_tables(aus_ctx *c, int lg, int wtype, Table
             h[n].y = (T)(0.5 * w[2 * n + 1]);
         }
         AUS_TRY(upload<T>(&tb.win2[wtype], h, c->stream));
+        for (size_t n = 0; n < Mh; ++n) {
+            h[n].x = (T)w[2 * n];
+            h[n].y = (T)w[2 * n + 1];
+        }
+        AUS_TRY(upload<T>(&tb.winf[wtype], h, c->stream));
     }
     *out = &tb;
     return AUS_OK;
@@ -395,7 +403,7 @@ template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftPar
     return launch_stft_v<T, LG, false>(c, p);
 }
 template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
-    using C = Cfg<T, LG>;
+    using C = CfgA<T, LG>;
     static bool attr_done[64] = {false};
     auto kern = analyzer_kernel<T, LG>;
     const size_t smem = C::smem_bytes();
@@ -1060,6 +1068,33 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     p.halo = (int)halo;
     p.apply_window = apply_window;
     p.tma_ok = ((reinterpret_cast<uintptr_t>(d_spec) & 15) == 0) ? 1 : 0;
+    p.fast_ok = 0;
+    if (apply_window && hop % 2 == 0 && hop < N) {
+        // steady-state reciprocal window norm of the first `hop` samples of a frame (fft.rs:239-243, 250-252): frames
+        // h - back .. h cover sample u < hop, summed in ascending frame order in the kernel's own arithmetic (T) exactly
+        // like the generic path's loop, then inverted once -- the fast path multiplies instead of dividing
+        const long long key = (((long long)N * 65536 + (long long)hop) * 8 + wtype) * 2 + (sizeof(T) == 4 ? 1 : 0);
+        if (c->normtab_key != key) {
+            std::vector<double> w(N);
+            AUS_TRY(aus_generate_window(wtype, N, w.data()));
+            std::vector<T> rn(hop);
+            for (size_t u = 0; u < hop; ++u) {
+                T acc = (T)0;
+                for (long long b = (long long)((N - 1 - u) / hop); b >= 0; --b) {
+                    const T wv = (T)w[u + (size_t)b * hop];
+                    acc += wv * wv;
+                }
+                rn[u] = (T)1 / acc;
+            }
+            AUS_TRY(c->normtab.ensure(hop * sizeof(T)));
+            CUDA_TRY(cudaMemcpyAsync(c->normtab.p, rn.data(), hop * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));        // rn is a temporary
+            c->normtab_key = key;
+        }
+        p.rnorm = (const T *)c->normtab.p;
+        p.winf = (const Cx<T> *)tb->winf[wtype];
+        p.fast_ok = 1;
+    }
     p.fwd.win2 = (const Cx<T> *)tb->win2[wtype];
     p.fwd.tw2 = (const Cx<T> *)tb->tw2;
     p.fwd.tw3 = (const Cx<T> *)tb->tw3;

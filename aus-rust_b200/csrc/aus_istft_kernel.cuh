@@ -27,6 +27,9 @@ template <typename T> struct IstftParams {
     unsigned long long n_seg;
     int hop;
     unsigned hop_magic;                      // floor(2^32 / hop) + 1: x / hop == umulhi(x, hop_magic) for x < 2^15
+    const T *rnorm;                          // [hop] reciprocal steady-state window norm (fast path)
+    const Cx<T> *winf;                       // [M] (w[2n], w[2n+1]) full-scale window pairs (fast path)
+    int fast_ok;                             // windowed, even hop < N: frames with every covering frame present take the fast path
     int halo;                                // ceil(N / hop) - 1
     int apply_window;                        // 0: irfft (plain inverse, no window / norm)
     int tma_ok;
@@ -82,6 +85,10 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             const long long h = h_begin + st;
             const bool active = seg_ok && h < b;
             const Cx<T> *row = p.spec + (gfirst + (unsigned long long)(active ? h : 0)) * (unsigned long long)K;
+#if AUS_L2_PREFETCH
+            if (active && t == 0 && h + 1 < b && ((K * sizeof(Cx<T>)) % 16 == 0) && p.tma_ok)
+                prefetch_l2(row + K, (uint32_t)(K * sizeof(Cx<T>)));        // next frame of this segment -> L2
+#endif
             // ---- stage the K bins of this frame (TMA bulk copy when the row is 16-byte sized and aligned)
             const bool use_tma = active && p.tma_ok && ((K * sizeof(Cx<T>)) % 16 == 0) &&
                                  ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
@@ -122,7 +129,47 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             // ---- window + overlap-add into the output (ascending frame order), finalise completed samples.
             //      u = offset inside the frame.  Frames h - b (b >= 1) also cover the sample iff b <= (N-1-u)/hop, frames
             //      h + a iff a <= u/hop; both quotients come from a 32-bit multiply-high (p.hop_magic), not a division.
-            if (active) {
+            // Fast path (almost every frame): windowed, even hop, every frame that can cover this frame's samples exists
+            // (h >= halo) and a later frame follows.  Then both samples of a butterfly output share their class -- has a
+            // partial sum from earlier frames iff u < N - hop, complete after this frame iff u < hop -- so each pair is one
+            // 16-byte read-modify-write, the window norm is a table multiply, and nothing is computed per sample.
+            const bool fastf = active && p.fast_ok && h >= p.halo && h < F - 1 &&
+                               ((reinterpret_cast<uintptr_t>(p.out + ooff + h * hop) & (2 * sizeof(T) - 1)) == 0);
+            if (fastf) {
+                using V2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+                T *outh = p.out + ooff + h * hop;
+                const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;     // owned range, relative (even)
+                const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);
+                const int nprev = N - p.hop;
+#pragma unroll 1
+                for (int i0 = 0; i0 < 32; i0 += 8) {
+                    V2 prev[8];
+                    Cx<T> z[8], w[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int n = t + TPF * (i0 + c), u0 = 2 * n;
+                        prev[c] = V2{(T)0, (T)0};
+                        if (u0 >= ulo && u0 < uhi && u0 < nprev) prev[c] = __ldcg(reinterpret_cast<const V2 *>(outh + u0));
+                        z[c] = buf[padi<4>(n)];
+                        w[c] = ldg_cx(&p.winf[n]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int u0 = 2 * (t + TPF * (i0 + c));
+                        if (u0 < ulo || u0 >= uhi) continue;
+                        T v0 = z[c].x * w[c].x + prev[c].x;                 // fft.rs:234-236 + overlap-add (ascending frames)
+                        T v1 = -z[c].y * w[c].y + prev[c].y;
+                        if (u0 < p.hop) {                                   // no later frame reaches it: fft.rs:250-258
+                            const V2 rn = __ldg(reinterpret_cast<const V2 *>(p.rnorm + u0));
+                            v0 *= rn.x;
+                            v1 *= rn.y;
+                            if (v0 > vmax) vmax = v0;                       // f64::max skips NaN
+                            if (v1 > vmax) vmax = v1;
+                        }
+                        *reinterpret_cast<V2 *>(outh + u0) = V2{v0, v1};
+                    }
+                }
+            } else if (active) {
                 T *outh = p.out + ooff + h * hop;
                 const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;
                 const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);

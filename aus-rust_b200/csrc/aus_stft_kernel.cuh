@@ -710,61 +710,4 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
     }
 }
 
-// K3: analyzer over caller-supplied magnitude rows (analysis/analyzer.rs:41-81, the loop at :99-104 / mp.rs:86-88)
-template <typename T, int LOG2N>
-__global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) analyzer_kernel(const StftParams<T> p) {
-    using C = Cfg<T, LOG2N>;
-    constexpr int M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
-    Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
-    double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
-    double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
-    for (int i = threadIdx.x; i < LOG2_TAB * C::LOGREP; i += C::BLOCK) logtab[i] = p.log2tab[i / C::LOGREP];
-    __syncthreads();
-    const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
-    const unsigned long long iters = (p.total_frames + stride - 1) / stride;
-#pragma unroll 1
-    for (unsigned long long it = 0; it < iters; ++it) {
-        const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
-        const bool active = g < p.total_frames;
-        const T *row = p.mags + (active ? g : 0ull) * (unsigned long long)K;
-        // stage the row with coalesced loads (consecutive lanes -> consecutive bins): power in the power half of
-        // the owner's slot, the magnitude itself in the other half (overwritten by the running sum later)
-#pragma unroll 4
-        for (int b = t; b <= M; b += TPF) {
-            const T m = active ? row[b] : (T)0;
-            pow_of<T, M, TPF>(buf, b) = m * m;                          // make_power_spectrum, s_a_t.rs:273-279
-            cum_of<T, M, TPF>(buf, b) = m;
-        }
-        group_sync<TPF, C::BLOCK>(grp);
-        FeatAcc<T> acc;
-        {
-            T *const bufT = reinterpret_cast<T *>(buf);
-            const int hp = hpar<T>(t);
-            const int h0 = zslot(M - 16 * t);
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
-                const int sl = 17 * t + i, sh = (i == 0) ? h0 : h0 - 1 - i;
-                const T plo = bufT[2 * sl + hp], ml = bufT[2 * sl + 1 - hp];
-                const T phi = bufT[2 * sh + hp], mh = bufT[2 * sh + 1 - hp];
-                acc.lo_sum += plo;
-                acc.hi_sum += phi;
-                acc.pmin = min(acc.pmin, min(power_hi(plo), power_hi(phi)));
-                acc.add((T)(16 * t + i), ml, plo);
-                acc.add((T)(M - 16 * t - i), mh, phi);
-            }
-            if (t == TPF - 1) {
-                const int sm = zslot(M / 2);
-                const T pm = bufT[2 * sm + hp], mm = bufT[2 * sm + 1 - hp];
-                acc.mid = pm;
-                acc.pmin = min(acc.pmin, power_hi(pm));
-                acc.add((T)(M / 2), mm, pm);
-            }
-        }
-        frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, false);
-        group_sync<TPF, C::BLOCK>(grp);
-    }
-}
-
 }  // namespace aus

@@ -53,16 +53,6 @@ template <int W> __device__ __forceinline__ Cx<double> shfl_cx(Cx<double> a, int
 template <int W> __device__ __forceinline__ Cx<float> shfl_cx(Cx<float> a, int src) {
     return cx_from(__shfl_sync(0xffffffffu, cx_bits(a), src, W));
 }
-// first set bit of a group-wide vote among the TPF threads of this thread's frame group (32 if none)
-template <int TPF> __device__ __forceinline__ int group_first(bool pred) {
-    unsigned b = __ballot_sync(0xffffffffu, pred);
-    if constexpr (TPF < 32) {
-        const unsigned lane = threadIdx.x & 31u;
-        b = (b >> (lane & ~(unsigned)(TPF - 1))) & ((1u << TPF) - 1u);
-    }
-    return b ? __ffs((int)b) - 1 : 32;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Forward packed FFT like frame_fft(), but the last pass stays in registers: on return natural output s of
 // thread j's final radix-32 butterfly, Z'[j + TPF s], is v[bitrev(s, 5)], and every thread of the group has
@@ -275,26 +265,53 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
     if (t < TPF - 1) pw[c0 + 32] = (T)inc;
     group_sync<TPF, C::BLOCK>(grp);                      // chunk ends and local running sums visible to the searching threads
 
-    if (active && p.raw != nullptr) {
-        double *rec = p.raw + g * (unsigned long long)RAW_N;
-        // roll-off (s_a_t.rs:137-145): index = number of bins whose inclusive running sum is below theta * P; one thread
-        // per threshold.  Level 1: binary search over the chunk ends for the chunk where the running sum first reaches
-        // the threshold; level 2: inside that chunk (global running sum = end of the previous chunk + local).
+    // roll-off (s_a_t.rs:137-145): index = number of bins whose inclusive running sum is below theta * P; one thread per
+    // threshold.  Level 1: binary search over the chunk ends for the chunk where the running sum first reaches the
+    // threshold; level 2: inside that chunk (global running sum = end of the previous chunk + local).
+    auto theta_of = [](int qq) { return qq == 0 ? 0.5 : qq == 1 ? 0.75 : qq == 2 ? 0.9 : 0.95; };
+    auto level1 = [&](T th, int &c, T &bs) {
+        int lo = 0, hi = TPF - 1;                          // first chunk in [0, TPF - 1] whose end is not below th
+#pragma unroll 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (pw[33 * mid + 32] < th) lo = mid + 1; else hi = mid;
+        }
+        c = lo;
+        bs = c > 0 ? pw[33 * c - 1] : (T)0;                // end of chunk c - 1 = pad slot 33 (c - 1) + 32
+    };
+    // Knife edge: the threshold sits within rounding distance of a running sum, where the reference's own arithmetic -- a
+    // sequential sum of p[i] / P compared with theta (s_a_t.rs:137-145) -- decides.  Redo it exactly that way (one thread,
+    // rare): identical result whenever the power values are identical.
+    auto settle = [&](int qq, T th, int res, bool amb, T c_at, T c_prev) -> int {
+        if constexpr (sizeof(T) == 8) {
+            const double tol = 1e-12 * P;
+            if (!amb && res < K)
+                amb = fabs((double)c_at - (double)th) <= tol || (res >= 1 && fabs((double)th - (double)c_prev) <= tol);
+            if (!amb && res == K) amb = fabs((double)th - (double)c_prev) <= tol;
+            if (amb) {
+                const double theta = theta_of(qq);
+                double pseq = 0.0;                         // power_spectrum.iter().sum(): sequential (analyzer.rs:44)
+                for (int i = 0; i < K; ++i) pseq += (double)pw[pslot<M>(i)];
+                double csum = 0.0;
+                int i = -1;
+                while (csum < theta && i < K - 1) {
+                    ++i;
+                    csum += (double)pw[pslot<M>(i)] / pseq;
+                }
+                res = i;
+            }
+        }
+        return res;
+    };
+    double *rec = p.raw + g * (unsigned long long)RAW_N;
+    const bool wr = active && p.raw != nullptr;
+    {
 #pragma unroll 1
         for (int qq = t; qq < 4; qq += TPF) {
-            const double theta = qq == 0 ? 0.5 : qq == 1 ? 0.75 : qq == 2 ? 0.9 : 0.95;
-            const T th = (T)(theta * P);
-            int c = 0;
-            {
-                int lo = 0, hi = TPF - 1;                  // first chunk in [0, TPF - 1] whose end is not below th
-#pragma unroll 1
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (pw[33 * mid + 32] < th) lo = mid + 1; else hi = mid;
-                }
-                c = lo;
-            }
-            const T bs = c > 0 ? pw[33 * c - 1] : (T)0;    // end of chunk c - 1 = pad slot 33 (c - 1) + 32
+            const T th = (T)(theta_of(qq) * P);
+            int c;
+            T bs;
+            level1(th, c, bs);
             const int n = (c == TPF - 1) ? 33 : 32;
             int res;
             bool amb = false;
@@ -307,12 +324,13 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
                     const int mid = (lo + hi) >> 1;
                     if (bs + cl[mid] < th) lo = mid + 1; else hi = mid;
                 }
-                res = 32 * c + lo;                         // = K when even bin M stays below (then the reference answers K - 1)
+                res = 32 * c + lo;                         // = K when even bin M stays below (the reference then answers K - 1)
                 if (lo < n) c_at = bs + cl[lo];
                 else amb = c < TPF - 1;                    // inside the spectrum this happens only by rounding of the scan
                 if (lo > 0) c_prev = bs + cl[lo - 1];      // running sum through bin res - 1
             } else {
-                const T *pl = pw + 33 * c;                 // no stored running sums: walk the chunk's powers
+                const T *pl = pw + 33 * c;                 // no stored running sums: walk the chunk's powers (a warp-
+                                                           // cooperative scan of the chunk measured no faster)
                 T run = bs;
                 int j = 0;
 #pragma unroll 1
@@ -325,28 +343,12 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
                 if (j == n) amb = c < TPF - 1;
                 c_prev = run;
             }
-            if constexpr (sizeof(T) == 8) {
-                // Knife edge: the threshold sits within rounding distance of a running sum, where the reference's own
-                // arithmetic -- a sequential sum of p[i] / P compared with theta (s_a_t.rs:137-145) -- decides.  Redo it
-                // exactly that way (one thread, rare).
-                const double tol = 1e-12 * P;
-                if (!amb && res < K)
-                    amb = fabs((double)c_at - (double)th) <= tol || (res >= 1 && fabs((double)th - (double)c_prev) <= tol);
-                if (!amb && res == K) amb = fabs((double)th - (double)c_prev) <= tol;
-                if (amb) {
-                    double pseq = 0.0;                     // power_spectrum.iter().sum(): sequential (analyzer.rs:44)
-                    for (int i = 0; i < K; ++i) pseq += (double)pw[pslot<M>(i)];
-                    double csum = 0.0;
-                    int i = -1;
-                    while (csum < theta && i < K - 1) {
-                        ++i;
-                        csum += (double)pw[pslot<M>(i)] / pseq;
-                    }
-                    res = i;
-                }
-            }
-            rec[RAW_ROLL0 + qq] = (double)res;
+            res = settle(qq, th, res, amb, c_at, c_prev);
+            if (wr) rec[RAW_ROLL0 + qq] = (double)res;
         }
+    }
+
+    if (wr) {
 #pragma unroll 1
         for (int qq = t; qq < 6; qq += TPF) rec[RAW_PICK0 + qq] = (double)pw[pslot<M>(p.pick[qq])];
         if (t == 0) {
@@ -477,6 +479,92 @@ __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double 
     const T s_pk = (tf * p_lo + pc_lo) + (mt * p_hi - pc_hi);
     const T p_part = p_lo + p_hi;
     if (want_feat) frame_features_r<T, LOG2N, C, true>(pw, pw + RLay<M>::CO, s_m, s_mk, s_pk, p_part, pmin, scratch, logtab, p, g, active, t, grp, true);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: analyzer over caller-supplied magnitude rows (analysis/analyzer.rs:41-81, the loop at :99-104 / mp.rs:86-88).
+// HBM-bound by design (K * sizeof(T) bytes in, 14 values out, ~22 flops per bin), so the layout is chosen for memory-level
+// parallelism: no FFT buffer, only the transposed power row in shared memory (33 TPF + 1 slots per frame group), two
+// (f64) or three (f32) 256-thread CTAs per SM, and every thread issues its 32 coalesced row loads back to back.
+template <typename T, int LOG2N> struct CfgA {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int M = N / 2;
+    static constexpr int K = M + 1;
+    static constexpr int TPF = M / 32;
+    static constexpr int BLOCK = 256;
+    static constexpr int MINB = (sizeof(T) == 4) ? 3 : 2;
+    static constexpr int FPB = BLOCK / TPF;
+    static constexpr int PW = (33 * TPF + 1 + 1) & ~1;        // T slots per group: bins 0..M transposed (pslot), even
+    static constexpr int NW = TPF > 32 ? TPF / 32 : 1;
+    static constexpr int SCR = TPF > 32 ? 16 * NW : 2;
+    static constexpr int LOGREP = sizeof(T) == 8 ? 8 : 1;
+    static constexpr int MAXREG = (65536 / (BLOCK * MINB)) & ~7;
+    __host__ __device__ static constexpr size_t off_scratch() { return ((size_t)FPB * PW * sizeof(T) + 15) & ~(size_t)15; }
+    __host__ __device__ static constexpr size_t off_log() { return (off_scratch() + (size_t)FPB * SCR * sizeof(double) + 15) & ~(size_t)15; }
+    __host__ __device__ static constexpr size_t smem_bytes() {
+        return off_log() + (sizeof(T) == 8 ? (size_t)LOG2_TAB * LOGREP * sizeof(double2) : 0);
+    }
+};
+
+template <typename T, int LOG2N>
+__global__ void __maxnreg__((CfgA<T, LOG2N>::MAXREG)) analyzer_kernel(const StftParams<T> p) {
+    using C = CfgA<T, LOG2N>;
+    constexpr int M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
+    T *const pw = reinterpret_cast<T *>(smem_raw) + (size_t)grp * C::PW;
+    double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
+    double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
+    if constexpr (sizeof(T) == 8) {
+        for (int i = threadIdx.x; i < LOG2_TAB * C::LOGREP; i += C::BLOCK) logtab[i] = p.log2tab[i / C::LOGREP];
+    }
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
+    const unsigned long long iters = (p.total_frames + stride - 1) / stride;
+    const T tf = (T)t;
+#pragma unroll 1
+    for (unsigned long long it = 0; it < iters; ++it) {
+        const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
+        const bool active = g < p.total_frames;
+        const T *row = p.mags + (active ? g : 0ull) * (unsigned long long)K;
+#if AUS_L2_PREFETCH
+        if (t == 0 && g + stride + 1 < p.total_frames) {   // this group's next row -> L2 (16-byte aligned superset; the row after
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p.mags + (g + stride) * (unsigned long long)K);   // it exists, so in bounds)
+            prefetch_l2(reinterpret_cast<const void *>(a & ~(uintptr_t)15), (uint32_t)((K * sizeof(T) + 16 + 15) & ~(size_t)15));
+        }
+#endif
+        // thread t takes bins t + TPF s (consecutive lanes -> consecutive bins), thread 0 also bin M
+        T mv[32];
+#pragma unroll
+        for (int s = 0; s < 32; ++s) mv[s] = active ? __ldg(row + t + TPF * s) : (T)0;
+        const T m_last = (active && t == 0) ? __ldg(row + M) : (T)0;
+        T s_m = 0, c_m = 0, s_p = 0, c_p = 0;              // sum m, sum m (TPF s), sum p, sum p (TPF s)
+        unsigned pmin = 0x7ff00000u;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const T m = mv[s];
+            const T pv = m * m;                            // make_power_spectrum, s_a_t.rs:273-279
+            pw[pslot_lt(t + TPF * s)] = pv;
+            pmin = min(pmin, power_hi(pv));
+            const T cs = (T)(TPF * s);
+            s_m += m;
+            c_m += m * cs;
+            s_p += pv;
+            c_p += pv * cs;
+        }
+        T s_mk = tf * s_m + c_m, s_pk = tf * s_p + c_p;
+        if (t == 0) {
+            const T pv = m_last * m_last;
+            pw[33 * TPF - 1] = pv;                         // pslot<M>(M)
+            pmin = min(pmin, power_hi(pv));
+            s_m += m_last;
+            s_mk += m_last * (T)M;
+            s_p += pv;
+            s_pk += pv * (T)M;
+        }
+        frame_features_r<T, LOG2N, C, false>(pw, nullptr, s_m, s_mk, s_pk, s_p, pmin, scratch, logtab, p, g, active, t, grp, false);
+        group_sync<TPF, C::BLOCK>(grp);                    // the searches are done before the next row overwrites pw
+    }
 }
 
 }  // namespace aus

@@ -65,6 +65,29 @@ if args.check:
     sgot = np.asarray(ctx.rstft(x, args.n, args.hop, int(aus.WindowType.Hanning)))
     print("check f64 spectra max |d| / max|X|", float(np.abs(sgot - sref).max() / np.abs(sref).max()), flush=True)
 
+if args.check:
+    rng = np.random.default_rng(3)
+    mags = np.abs(rng.normal(size=(40, args.n // 2 + 1))) + 1e-3
+    mags[5, :] = 0.0
+    mags[6, 10] = 0.0
+    ref = orc.analyze_spectrogram(mags, args.n, SR)
+    got = ctx.analyzer_batch(mags, args.n, SR)
+    with np.errstate(all="ignore"):
+        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+    rel = np.where(np.isnan(got) & np.isnan(ref), 0.0, rel)
+    print("check k3 f64 max rel per feature", np.nanmax(rel, axis=0).tolist(), "nan pattern equal",
+          bool(np.array_equal(np.isnan(got), np.isnan(ref))), flush=True)
+
+if args.check:
+    xs = orc.synth_signal(40 * args.n + 123, SR, seed=8, file_id=args.n)
+    for wt in (orc.HAMMING, orc.HANNING):
+        S = orc.rstft(xs, args.n, args.hop, wt)
+        ref = orc.irstft(S, args.n, args.hop, wt)
+        got = ctx.irstft(S, args.n, args.hop, wt)
+        fin = np.isfinite(ref)
+        print("check k4 f64 window", wt, "max |d| / peak", float(np.max(np.abs(got[fin] - ref[fin])) / np.max(np.abs(ref[fin]))),
+              "nan pattern equal", bool(np.array_equal(np.isnan(got), np.isnan(ref))), flush=True)
+
 N, hop, n = args.n, args.hop, args.seconds * SR
 K = N // 2 + 1
 F = aus.num_frames(n, N, hop)
