@@ -372,11 +372,11 @@ static int fill_feature_params_check(size_t N, uint32_t sr) {     // argument va
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-template <typename T, int LG, bool RR> static int launch_stft_v(aus_ctx *c, const StftParams<T> &p) {
+template <typename T, int LG, bool RR, bool FEAT> static int launch_stft_v(aus_ctx *c, const StftParams<T> &p) {
     using C = Cfg<T, LG, RR>;
     static bool attr_done[64] = {false};
-    auto kern = stft_kernel<T, LG, RR>;
-    const size_t smem = C::smem_bytes();
+    auto kern = stft_kernel<T, LG, RR, FEAT>;
+    const size_t smem = FEAT ? C::smem_bytes() : C::off_log();          // the spectra-only build carries no log2 table
     if (!attr_done[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[c->device & 63] = true;
@@ -392,15 +392,24 @@ template <typename T, int LG, bool RR> static int launch_stft_v(aus_ctx *c, cons
     c->launches++;
     return AUS_OK;
 }
-// Which forward kernel: the register-resident tail (aus_stft_r.cuh) exists for fft_size <= 2048.  Measured on B200 at
-// fft 2048 / hop 512: f32 +7 % (features) / +23 % (spectra), f64 spectra +17 %, f64 features -5 % (8 warps x 255 registers
-// against 12 x 168) -- so f64 features keep the shared-memory tail.  c->rr_mode (AUS_B200_RR=0|1) overrides for ablations.
+// Which forward kernel: the register-resident tail (aus_stft_r.cuh) exists for fft_size <= 2048.  Measured on B200 over
+// fft_size 64..2048 x {f64, f32} x {features, spectra, both} on >= 15 min inputs (tools/kbench.py, AUS_B200_RR=0|1):
+//   f32: it wins everywhere (features +3..32 %, spectra +20..90 %, both outputs in one launch +17..110 %);
+//   f64: spectra +17..70 % and both outputs +15..35 %, but features alone lose 10..30 % (its CTAs are 8 warps x 255
+//        registers against 12 x 168, and the FP64 feature pass needs the resident warps) -> those keep the shared-memory tail.
+// c->rr_mode (aus_ctx_set_forward_variant / AUS_B200_RR) overrides the table for ablations.
+static bool use_rr(const aus_ctx *c, int lg, bool f32, bool feat, bool spec) {
+    if (lg > 11) return false;
+    if (c->rr_mode >= 0) return c->rr_mode == 1;
+    if (!f32 && feat && !spec) return false;
+    return true;
+}
 template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
     if constexpr (LG <= 11) {
-        const bool auto_rr = sizeof(T) == 4 || p.raw == nullptr;
-        if (c->rr_mode == 1 || (c->rr_mode < 0 && auto_rr)) return launch_stft_v<T, LG, true>(c, p);
+        if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
+            return p.raw != nullptr ? launch_stft_v<T, LG, true, true>(c, p) : launch_stft_v<T, LG, true, false>(c, p);
     }
-    return launch_stft_v<T, LG, false>(c, p);
+    return launch_stft_v<T, LG, false, true>(c, p);
 }
 template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
     using C = CfgA<T, LG>;
@@ -706,7 +715,7 @@ static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t
         AUS_TRY(c->raw.ensure((size_t)b.total_frames * RAW_N * sizeof(double)));
         p.raw = (double *)c->raw.p;
     }
-    const bool fused_both = lg <= 11 && (c->rr_mode == 1 || (c->rr_mode < 0 && sizeof(T) == 4));
+    const bool fused_both = use_rr(c, lg, sizeof(T) == 4, true, true);
     if (d_feat && d_spec && !fused_both) {   // both outputs: one spectra-only launch + one feature launch, except where the
                                              // register-resident kernel stores spectra and features from one pass
         StftParams<T> ps = p;

@@ -22,7 +22,9 @@
 #define AUS_F64_BLOCK_R 256      // f64 CTA size of the register-resident path; registers are allocated per 4 warps
 #endif
 #ifndef AUS_L2_PREFETCH
-#define AUS_L2_PREFETCH 1        // prefetch the next iteration's frame into L2 while this one is processed
+#define AUS_L2_PREFETCH 0        // experiment: cp.async.bulk.prefetch.L2 of the next frame / row while this one is processed.
+                                 // Measured on 2 h inputs: forward features -1..-6 %, spectra -4..-6 %, analyzer +1 %, irstft +-4 %
+                                 // (the neighbouring frames other warps are loading already keep L2 warm) -> off.
 #endif
 
 namespace aus {
@@ -534,14 +536,17 @@ __global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, in
 template <typename T, int LOG2N, typename C>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
                                                const Cx<T> *gsrc, Cx<T> (&v)[32]);
-template <typename T, int LOG2N, typename C>
+template <typename T, int LOG2N, typename C, bool SHFL, bool FEAT>
 __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double *scratch, const double2 *logtab,
                                              const StftParams<T> &p, unsigned long long g, bool active, int t, int grp);
 
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int LOG2N, bool RR>
+// FEAT = false (register-resident variant only): spectra-only build -- no feature code, no log2 table; the smaller
+// register footprint is worth +11 % on the spectra path (f64, fft 2048: 59 % -> 66 % of the HBM roofline).
+template <typename T, int LOG2N, bool RR, bool FEAT>
 __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftParams<T> p) {
     using C = Cfg<T, LOG2N, RR>;
+    static_assert(RR || FEAT, "the spectra-only build exists for the register-resident variant");
     constexpr int N = C::N, M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
@@ -549,7 +554,9 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
     double *scratch = reinterpret_cast<double *>(smem_raw + C::off_scratch()) + (size_t)grp * C::SCR;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + C::off_bar()) + grp;
     double2 *logtab = reinterpret_cast<double2 *>(smem_raw + C::off_log());
-    for (int i = threadIdx.x; i < LOG2_TAB * C::LOGREP; i += C::BLOCK) logtab[i] = p.log2tab[i / C::LOGREP];
+    if constexpr (FEAT) {
+        for (int i = threadIdx.x; i < LOG2_TAB * C::LOGREP; i += C::BLOCK) logtab[i] = p.log2tab[i / C::LOGREP];
+    }
     if (t == 0) mbar_init(bar, 1);
     fence_mbar_init();
     __syncthreads();
@@ -557,22 +564,28 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
 
     const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
     const unsigned long long iters = (p.total_frames + stride - 1) / stride;
-    const bool want_feat = p.raw != nullptr;
+    const bool want_feat = FEAT && p.raw != nullptr;
     int f = 0;
+    // frame g of the batch -> its samples: file (frames only move forward, so the search resumes at fq), start, length
+    auto locate = [&](unsigned long long gq, int &fq, const T *&srcq, int &Lq) -> bool {
+        srcq = p.audio;
+        Lq = 0;
+        if (gq >= p.total_frames) return false;
+        while (gq >= p.file_first[fq + 1]) ++fq;
+        const unsigned long long s = (gq - p.file_first[fq]) * (unsigned long long)p.hop;
+        const unsigned long long len = p.file_len[fq];
+        const unsigned long long rem = len > s ? len - s : 0ull;
+        Lq = rem < (unsigned long long)N ? (int)rem : N;                // fft.rs:130-144
+        srcq = p.audio + p.file_off[fq] + s;
+        return true;
+    };
+    bool staged = false;                                                // this iteration's bulk copy was issued early (below)
 #pragma unroll 1
     for (unsigned long long it = 0; it < iters; ++it) {
         const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
-        const bool active = g < p.total_frames;
-        const T *src = p.audio;
-        int L = 0;
-        if (active) {
-            while (g >= p.file_first[f + 1]) ++f;                       // frames only move forward
-            const unsigned long long s = (g - p.file_first[f]) * (unsigned long long)p.hop;
-            const unsigned long long len = p.file_len[f];
-            const unsigned long long rem = len > s ? len - s : 0ull;
-            L = rem < (unsigned long long)N ? (int)rem : N;             // fft.rs:130-144
-            src = p.audio + p.file_off[f] + s;
-        }
+        const T *src;
+        int L;
+        const bool active = locate(g, f, src, L);
 #if AUS_L2_PREFETCH
         if (active && t == 0 && g + stride < p.file_first[f + 1]) {     // same file: its next frame of this group, if full
             const unsigned long long s2 = (g + stride - p.file_first[f]) * (unsigned long long)p.hop;
@@ -589,7 +602,7 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
         //      otherwise a cooperative copy that also applies the short last-frame window).  Groups sharing a warp
         //      may take different paths, so no barrier sits inside a branch.
         if (use_tma) {
-            if (t == 0) {
+            if (t == 0 && !staged) {
                 mbar_arrive_expect_tx(bar, (uint32_t)(N * sizeof(T)));
                 tma_load_1d(buf, src, (uint32_t)(N * sizeof(T)), bar);
             }
@@ -615,7 +628,32 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
             // the last pass, the real-FFT split and the first feature pass stay in registers (aus_stft_r.cuh)
             Cx<T> v[32];
             frame_fft_keep<T, LOG2N, C>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v);
-            frame_tail_r<T, LOG2N, C>(v, buf, scratch, logtab, p, g, active, t, grp);
+            staged = false;
+            if (!want_feat) {
+                // spectra only: nothing below touches the group buffer, and every thread has read its last-pass inputs, so
+                // the next frame's bulk copy starts now and overlaps the butterflies, the real-FFT split and the stores
+                const T *src2;
+                int L2, f2 = f;
+                const bool act2 = it + 1 < iters && locate(g + stride, f2, src2, L2);
+                const bool tma2 = act2 && L2 == N && p.tma_ok && !(p.direct && C::R1 == 32) &&
+                                  ((reinterpret_cast<uintptr_t>(src2) & 15) == 0);      // = the next iteration's use_tma
+                fence_proxy_async();                                    // pass-1 stores (generic proxy) before the async write
+                group_sync<TPF, C::BLOCK>(grp);                         // (outside the branch: groups may share a warp)
+                if (tma2) {                                             // group-uniform
+                    if (t == 0) {
+                        mbar_arrive_expect_tx(bar, (uint32_t)(N * sizeof(T)));
+                        tma_load_1d(buf, src2, (uint32_t)(N * sizeof(T)), bar);
+                    }
+                    staged = true;
+                }
+            }
+            // partner exchange: by shuffles (f32; spectra-only builds, where the buffer now belongs to the next frame) or
+            // through the group buffer (f64 with features: frees registers for the feature pass)
+            if constexpr (!FEAT) {
+                frame_tail_r<T, LOG2N, C, true, false>(v, buf, scratch, logtab, p, g, active, t, grp);
+            } else {
+                frame_tail_r<T, LOG2N, C, sizeof(T) == 4, true>(v, buf, scratch, logtab, p, g, active, t, grp);
+            }
             fence_proxy_async();                                        // generic accesses to buf before the next TMA write
             group_sync<TPF, C::BLOCK>(grp);
             continue;

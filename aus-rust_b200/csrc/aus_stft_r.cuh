@@ -16,9 +16,7 @@
 #ifndef AUS_TAIL_BATCH
 #define AUS_TAIL_BATCH(T) 4
 #endif
-#ifndef AUS_PAIR_SHFL
-#define AUS_PAIR_SHFL(T) (sizeof(T) == 4)    // partner exchange by warp shuffles (f32) or through the group buffer (f64)
-#endif
+
 
 namespace aus {
 
@@ -362,11 +360,11 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
 
 // ---------------------------------------------------------------------------------------------------------
 // Real-FFT split + power + first feature pass straight from the registers left by frame_fft_keep().
-template <typename T, int LOG2N, typename C>
+template <typename T, int LOG2N, typename C, bool SHFL, bool FEAT>
 __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double *scratch, const double2 *logtab,
                                              const StftParams<T> &p, unsigned long long g, bool active, int t, int grp) {
     constexpr int M = C::M, K = C::K, TPF = C::TPF;
-    const bool want_feat = p.raw != nullptr;
+    const bool want_feat = FEAT && p.raw != nullptr;
     Cx<T> *spec = (p.spec != nullptr && active) ? p.spec + g * (unsigned long long)K : nullptr;
     T *const pw = reinterpret_cast<T *>(buf);
 
@@ -393,12 +391,12 @@ __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double 
     }
     // ---- the partner Z'[M - k] of k = t + TPF s is natural output 31 - s of thread (TPF - t) mod TPF (thread 0 pairs with
     //      itself one step further: M - TPF s = TPF (32 - s), and its k = 0 with Z'[0] itself).
-    //      f64: the upper half of the registers goes through a [16][TPF] staging area in the (now free) upper part of the
-    //      group buffer -- row s' - 16, column j, plus Z'[0] in slot 16 TPF -- where the partner of pair s is slot
-    //      (16 - s) TPF - t for every thread, 0 included; the 64 registers are free right after the store, which is what
-    //      keeps this path inside the 168-register budget.  f32 has the registers to swap them by warp shuffles instead.
+    //      SHFL: the upper half of the registers is swapped with the partner by warp shuffles, in place; nothing touches
+    //      the group buffer, so a spectra-only launch can already stream the next frame into it.
+    //      !SHFL: a [16][TPF] staging area in the free upper part of the group buffer -- row s' - 16, column j, plus Z'[0]
+    //      in slot 16 TPF -- where the partner of pair s is slot (16 - s) TPF - t for every thread; twice the shared-memory
+    //      traffic, but 64 registers are free right after the store, which the f64 feature pass needs (measured +4..12 %).
     const Cx<T> wt = ldg_cx(&p.twN[t]);                  // (cos, sin)(2 pi t / N)
-    constexpr bool SHFL = AUS_PAIR_SHFL(T);
     constexpr int PB = AUS_TAIL_BATCH(T);                // pairs per batch
     Cx<T> *const xb = buf + (C::BUF - 16 * TPF - 2);
     const int partner = (TPF - t) & (TPF - 1);

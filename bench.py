@@ -307,9 +307,10 @@ def run_ours(args):
                     "host_dtype": "f64 (pinned)", "rank_cpu_affinity": numa},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": f"stft_kernel<{'double' if prec == 'f64' else 'float'}, 11>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "stft_kernel<double, 11, 0>" if prec == "f64" else "stft_kernel<float, 11, 1>",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "f64 path is FP64-pipe bound (DESIGN.md); see profiles/ for pipe utilisation"},
+                         "note": "fused f64 path is co-limited by the FP64 pipe, issue slots and the L1/shared data pipe, not by HBM "
+                                 "(DESIGN.md section 5); the spectra-writing kernel of the same path runs at ~59 % (profiles/)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }))
