@@ -392,23 +392,26 @@ template <typename T, int LG, bool RR, bool FEAT> static int launch_stft_v(aus_c
     c->launches++;
     return AUS_OK;
 }
-// Which forward kernel: the register-resident tail (aus_stft_r.cuh) exists for fft_size <= 2048.  Measured on B200 over
-// fft_size 64..2048 x {f64, f32} x {features, spectra, both} on >= 15 min inputs (tools/kbench.py, AUS_B200_RR=0|1):
-//   f32: it wins everywhere (features +3..32 %, spectra +20..90 %, both outputs in one launch +17..110 %);
-//   f64: spectra +17..70 % and both outputs +15..35 %, but features alone lose 10..30 % (its CTAs are 8 warps x 255
-//        registers against 12 x 168, and the FP64 feature pass needs the resident warps) -> those keep the shared-memory tail.
+#ifndef AUS_RR_F64_FEAT_MIN_LG
+#define AUS_RR_F64_FEAT_MIN_LG 14
+#endif
+// Which forward kernel: shared-memory tail or register-resident tail (aus_stft_r.cuh).  Measured on B200 over
+// fft_size 64..16384 x {f64, f32} x {features, spectra, both} on >= 15 min inputs (tools/kbench.py, AUS_B200_RR=0|1):
+//   f32: the register-resident tail wins everywhere (features +3..32 %, spectra +18..90 %, both outputs in one launch
+//        +17..110 %);
+//   f64: both outputs +15..80 %; spectra alone +15..70 % except at fft_size 4096 / 8192 (-1..-4 %); features alone lose
+//        4..30 % up to fft_size 8192 (its CTAs are 8 warps x 255 registers against 12 x 168, and the FP64 feature pass
+//        needs the resident warps) and gain 8 % at 16384, where the shared-memory tail has 8 warps per SM as well.
 // c->rr_mode (aus_ctx_set_forward_variant / AUS_B200_RR) overrides the table for ablations.
 static bool use_rr(const aus_ctx *c, int lg, bool f32, bool feat, bool spec) {
-    if (lg > 11) return false;
     if (c->rr_mode >= 0) return c->rr_mode == 1;
-    if (!f32 && feat && !spec) return false;
-    return true;
+    if (f32 || (feat && spec)) return true;
+    if (feat) return lg >= AUS_RR_F64_FEAT_MIN_LG;       // f64 features alone
+    return lg <= 11 || lg >= 14;                         // f64 spectra alone
 }
 template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
-    if constexpr (LG <= 11) {
-        if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
-            return p.raw != nullptr ? launch_stft_v<T, LG, true, true>(c, p) : launch_stft_v<T, LG, true, false>(c, p);
-    }
+    if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
+        return p.raw != nullptr ? launch_stft_v<T, LG, true, true>(c, p) : launch_stft_v<T, LG, true, false>(c, p);
     return launch_stft_v<T, LG, false, true>(c, p);
 }
 template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
@@ -435,7 +438,7 @@ template <typename T, int LG> static int launch_istft_t(aus_ctx *c, const IstftP
     using C = Cfg<T, LG>;
     static bool attr_done[64] = {false};
     auto kern = istft_kernel<T, LG>;
-    const size_t smem = C::smem_bytes();
+    const size_t smem = C::off_log();                                     // no log2 table in the inverse kernel
     if (!attr_done[c->device & 63]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[c->device & 63] = true;

@@ -61,7 +61,6 @@ template <typename T, int LOG2N, bool RR = false> struct Cfg {
     static constexpr int LOGREP = sizeof(T) == 8 ? 8 : 1;
     __host__ __device__ static constexpr size_t smem_bytes() { return off_log() + (size_t)LOG2_TAB * LOGREP * sizeof(double2); }
     static_assert(LOG2N >= 6 && LOG2N <= 14, "fft_size must be 64..16384");
-    static_assert(!RR || TPF <= 32, "register-resident tail: fft_size <= 2048");
 };
 
 // Everything the kernels need besides the template parameters.  Filled on the host (aus_b200.cu).
@@ -532,6 +531,97 @@ __global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, in
     for (int i = 0; i < 14; ++i) dst[i] = (T)out[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory tail of the forward kernel (every fft_size): on entry buf holds Z' in the Z layout (frame_fft()).
+template <typename T, int LOG2N>
+__device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const double2 *logtab, const StftParams<T> &p,
+                                             unsigned long long g, bool active, int t, int grp, bool want_feat) {
+    using C = Cfg<T, LOG2N>;
+    constexpr int M = C::M, K = C::K, TPF = C::TPF;
+    // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)
+    FeatAcc<T> acc;
+    Cx<T> *spec = (p.spec != nullptr && active) ? p.spec + g * (unsigned long long)K : nullptr;
+    // four pairs (k, M - k) at a time: loads first, then eight independent post-twiddle / sqrt chains.
+    // slots: zslot(16 t + i) = 17 t + i;  zslot(M - 16 t - i) = h0 - 1 - i for i >= 1 and h0 for i = 0.
+    const int h0 = zslot(M - 16 * t);
+    T *const bufT = reinterpret_cast<T *>(buf);
+    const int hp = hpar<T>(t);
+#pragma unroll 1
+    for (int i0 = 0; i0 < 16; i0 += 4) {
+        Cx<T> A[4], B[4], W[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + c;
+            A[c] = buf[17 * t + i];
+            B[c] = buf[(c == 0 && i0 == 0) ? (t == 0 ? 0 : h0) : h0 - 1 - i];      // k = 0 pairs with itself
+            W[c] = ldg_cx(&p.twNt[i * TPF + t]);
+        }
+        T plo[4], phi[4];
+        if (!want_feat) {
+            // K2 (spectra only): X replaces Z in place, then the whole row leaves in coalesced stores below
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = i0 + c;
+                Cx<T> Xlo, Xhi;
+                post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
+                buf[17 * t + i] = Xlo;
+                buf[(c == 0 && i0 == 0) ? h0 : h0 - 1 - i] = Xhi;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            Cx<T> Xlo, Xhi;
+            post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
+            plo[c] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
+            phi[c] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + c;
+            bufT[2 * (17 * t + i) + hp] = plo[c];
+            bufT[2 * ((c == 0 && i0 == 0) ? h0 : h0 - 1 - i) + hp] = phi[c];
+        }
+        {
+            T mlo[4], mhi[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc.pmin = min(acc.pmin, min(power_hi(plo[c]), power_hi(phi[c])));
+                mlo[c] = Mth<T>::sqrt_(plo[c]);
+                mhi[c] = Mth<T>::sqrt_(phi[c]);
+            }
+            const T klo = (T)(16 * t + i0), khi = (T)(M - 16 * t - i0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc.lo_sum += plo[c];
+                acc.hi_sum += phi[c];
+                acc.add(klo + (T)c, mlo[c], plo[c]);
+                acc.add(khi - (T)c, mhi[c], phi[c]);
+            }
+        }
+    }
+    if (!want_feat) {
+        if (t == TPF - 1) {
+            const Cx<T> A = buf[zslot(M / 2)];
+            buf[zslot(M / 2)] = Cx<T>{A.x + A.x, -(A.y + A.y)};     // X[M/2] = conj(Z[M/2])
+        }
+        group_sync<TPF, C::BLOCK>(grp);
+        if (spec) {
+#pragma unroll 4
+            for (int k = t; k <= M; k += TPF) spec[k] = buf[zslot(k)];   // consecutive lanes -> consecutive bins
+        }
+    } else if (t == TPF - 1) {
+        const Cx<T> A = buf[zslot(M / 2)];
+        const Cx<T> X = Cx<T>{A.x + A.x, -(A.y + A.y)};             // X[M/2] = conj(Z[M/2])
+        const T pm = X.x * X.x + X.y * X.y;
+        bufT[2 * zslot(M / 2) + hp] = pm;
+        acc.mid = pm;
+        acc.pmin = min(acc.pmin, power_hi(pm));
+        if (want_feat) acc.add((T)(M / 2), Mth<T>::sqrt_(pm), pm);
+    }
+    if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, true);
+}
+
 // register-resident variants for fft_size <= 2048, defined in aus_stft_r.cuh
 template <typename T, int LOG2N, typename C>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
@@ -547,7 +637,7 @@ template <typename T, int LOG2N, bool RR, bool FEAT>
 __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftParams<T> p) {
     using C = Cfg<T, LOG2N, RR>;
     static_assert(RR || FEAT, "the spectra-only build exists for the register-resident variant");
-    constexpr int N = C::N, M = C::M, K = C::K, TPF = C::TPF, FPB = C::FPB;
+    constexpr int N = C::N, TPF = C::TPF, FPB = C::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / TPF, t = threadIdx.x % TPF;
     Cx<T> *buf = reinterpret_cast<Cx<T> *>(smem_raw) + (size_t)grp * C::BUF;
@@ -629,8 +719,8 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
             Cx<T> v[32];
             frame_fft_keep<T, LOG2N, C>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v);
             staged = false;
-            if (!want_feat) {
-                // spectra only: nothing below touches the group buffer, and every thread has read its last-pass inputs, so
+            if (!want_feat && TPF <= 32) {
+                // spectra only, frame group inside one warp: nothing below touches the group buffer, and every thread has read its last-pass inputs, so
                 // the next frame's bulk copy starts now and overlaps the butterflies, the real-FFT split and the stores
                 const T *src2;
                 int L2, f2 = f;
@@ -650,99 +740,14 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
             // partner exchange: by shuffles (f32; spectra-only builds, where the buffer now belongs to the next frame) or
             // through the group buffer (f64 with features: frees registers for the feature pass)
             if constexpr (!FEAT) {
-                frame_tail_r<T, LOG2N, C, true, false>(v, buf, scratch, logtab, p, g, active, t, grp);
+                frame_tail_r<T, LOG2N, C, (TPF <= 32), false>(v, buf, scratch, logtab, p, g, active, t, grp);
             } else {
-                frame_tail_r<T, LOG2N, C, sizeof(T) == 4, true>(v, buf, scratch, logtab, p, g, active, t, grp);
+                frame_tail_r<T, LOG2N, C, (sizeof(T) == 4 && TPF <= 32), true>(v, buf, scratch, logtab, p, g, active, t, grp);
             }
-            fence_proxy_async();                                        // generic accesses to buf before the next TMA write
-            group_sync<TPF, C::BLOCK>(grp);
-            continue;
+        } else {
+            frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr);
+            frame_tail_s<T, LOG2N>(buf, scratch, logtab, p, g, active, t, grp, want_feat);
         }
-        frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr);
-
-        // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)
-        FeatAcc<T> acc;
-        Cx<T> *spec = (p.spec != nullptr && active) ? p.spec + g * (unsigned long long)K : nullptr;
-        // four pairs (k, M - k) at a time: loads first, then eight independent post-twiddle / sqrt chains.
-        // slots: zslot(16 t + i) = 17 t + i;  zslot(M - 16 t - i) = h0 - 1 - i for i >= 1 and h0 for i = 0.
-        const int h0 = zslot(M - 16 * t);
-        T *const bufT = reinterpret_cast<T *>(buf);
-        const int hp = hpar<T>(t);
-#pragma unroll 1
-        for (int i0 = 0; i0 < 16; i0 += 4) {
-            Cx<T> A[4], B[4], W[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int i = i0 + c;
-                A[c] = buf[17 * t + i];
-                B[c] = buf[(c == 0 && i0 == 0) ? (t == 0 ? 0 : h0) : h0 - 1 - i];      // k = 0 pairs with itself
-                W[c] = ldg_cx(&p.twNt[i * TPF + t]);
-            }
-            T plo[4], phi[4];
-            if (!want_feat) {
-                // K2 (spectra only): X replaces Z in place, then the whole row leaves in coalesced stores below
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int i = i0 + c;
-                    Cx<T> Xlo, Xhi;
-                    post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
-                    buf[17 * t + i] = Xlo;
-                    buf[(c == 0 && i0 == 0) ? h0 : h0 - 1 - i] = Xhi;
-                }
-                continue;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int k = 16 * t + i0 + c;
-                Cx<T> Xlo, Xhi;
-                post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
-                plo[c] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
-                phi[c] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int i = i0 + c;
-                bufT[2 * (17 * t + i) + hp] = plo[c];
-                bufT[2 * ((c == 0 && i0 == 0) ? h0 : h0 - 1 - i) + hp] = phi[c];
-            }
-            {
-                T mlo[4], mhi[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    acc.pmin = min(acc.pmin, min(power_hi(plo[c]), power_hi(phi[c])));
-                    mlo[c] = Mth<T>::sqrt_(plo[c]);
-                    mhi[c] = Mth<T>::sqrt_(phi[c]);
-                }
-                const T klo = (T)(16 * t + i0), khi = (T)(M - 16 * t - i0);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    acc.lo_sum += plo[c];
-                    acc.hi_sum += phi[c];
-                    acc.add(klo + (T)c, mlo[c], plo[c]);
-                    acc.add(khi - (T)c, mhi[c], phi[c]);
-                }
-            }
-        }
-        if (!want_feat) {
-            if (t == TPF - 1) {
-                const Cx<T> A = buf[zslot(M / 2)];
-                buf[zslot(M / 2)] = Cx<T>{A.x + A.x, -(A.y + A.y)};     // X[M/2] = conj(Z[M/2])
-            }
-            group_sync<TPF, C::BLOCK>(grp);
-            if (spec) {
-#pragma unroll 4
-                for (int k = t; k <= M; k += TPF) spec[k] = buf[zslot(k)];   // consecutive lanes -> consecutive bins
-            }
-        } else if (t == TPF - 1) {
-            const Cx<T> A = buf[zslot(M / 2)];
-            const Cx<T> X = Cx<T>{A.x + A.x, -(A.y + A.y)};             // X[M/2] = conj(Z[M/2])
-            const T pm = X.x * X.x + X.y * X.y;
-            bufT[2 * zslot(M / 2) + hp] = pm;
-            acc.mid = pm;
-            acc.pmin = min(acc.pmin, power_hi(pm));
-            if (want_feat) acc.add((T)(M / 2), Mth<T>::sqrt_(pm), pm);
-        }
-        if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, true);
         fence_proxy_async();                                            // generic accesses to buf before the next TMA write
         group_sync<TPF, C::BLOCK>(grp);
     }

@@ -1,22 +1,19 @@
-// aus_stft_r.cuh -- register-resident tail of the forward kernel for fft_size <= 2048 (TPF <= 32: one frame per
-// warp or less).  sm_100a.
+// aus_stft_r.cuh -- register-resident tail of the forward kernel (the last FFT pass stays in registers), the
+// second feature pass on the transposed power layout (any fft_size) and the analyzer kernel K3 built on it.  sm_100a.
 //
-// The L1/shared data pipe is the busiest unit of the fused kernel (ncu: 70 % of its wavefront peak at 18 % occupancy),
+// The L1/shared data pipe is the busiest unit of the fused kernel (ncu: 63-70 % of its wavefront peak at 18 % occupancy),
 // so this path removes shared-memory round trips instead of arithmetic:
 //   * the last radix-32 pass leaves Z[j + TPF s], s = 0..31, in the registers of thread j (no store);
 //   * the partner Z[M - k] of the real-FFT split (fft.rs:171-172 via the packed transform) lives in thread
-//     (TPF - j) mod TPF at s' = 31 - s, so half of the registers are swapped with it by warp shuffles (in place);
+//     (TPF - j) mod TPF at s' = 31 - s, so half of the registers are swapped with it -- by warp shuffles, in place, or
+//     through a staging area in the free half of the group buffer (f64 with features, where registers are short);
 //   * X[k], X[M-k] are formed in registers and, when the caller wants spectra (K2), stored straight to HBM
 //     (consecutive lanes -> consecutive bins, fully coalesced) -- no staging buffer, no second launch;
 //   * |X|^2 goes to shared memory once, transposed (bin b at slot b + b/32), so that each thread then walks 32
 //     consecutive bins for the order-dependent work (running sum -> roll-off) together with the second feature pass.
+// Which launches use it is a measured table: use_rr() in aus_b200.cu.
 #pragma once
 #include "aus_stft_kernel.cuh"
-
-#ifndef AUS_TAIL_BATCH
-#define AUS_TAIL_BATCH(T) 4
-#endif
-
 
 namespace aus {
 
@@ -30,14 +27,28 @@ template <int M> struct RLay {
 
 // (cos, sin)(2 pi s / 64), s = 0..15: the post-twiddle of bin k = t + TPF s is W_N^t x W_64^s for every fft_size here
 // (N = 64 TPF), so a thread needs one table entry per frame and the rest are constant-bank operands (f64) / immediates.
-__constant__ double c_w64_cos[16] = {1.0, 0.99518472667219688624483695310947992, 0.98078528040323044912618223613423904, 0.95694033573220886493579788698026997, 0.92387953251128675612818318939678829, 0.88192126434835502971275686366038835, 0.83146961230254523707878837761790576, 0.7730104533627369608109066097584698, 0.70710678118654752440084436210484904, 0.63439328416364549821517161322549337, 0.55557023301960222474283081394853287, 0.47139673682599764855638762590525438, 0.38268343236508977172845998403039887, 0.29028467725446236763619237581739527, 0.19509032201612826784828486847702224, 0.098017140329560601994195563888641846};
-__constant__ double c_w64_sin[16] = {0.0, 0.098017140329560601994195563888641846, 0.19509032201612826784828486847702224, 0.29028467725446236763619237581739527, 0.38268343236508977172845998403039887, 0.47139673682599764855638762590525438, 0.55557023301960222474283081394853287, 0.63439328416364549821517161322549337, 0.70710678118654752440084436210484904, 0.7730104533627369608109066097584698, 0.83146961230254523707878837761790576, 0.88192126434835502971275686366038835, 0.92387953251128675612818318939678829, 0.95694033573220886493579788698026997, 0.98078528040323044912618223613423904, 0.99518472667219688624483695310947992};
+#define AUS_W64_COS \
+    1.0, 0.99518472667219688624483695310947992, 0.98078528040323044912618223613423904, \
+    0.95694033573220886493579788698026997, 0.92387953251128675612818318939678829, 0.88192126434835502971275686366038835, \
+    0.83146961230254523707878837761790576, 0.7730104533627369608109066097584698, 0.70710678118654752440084436210484904, \
+    0.63439328416364549821517161322549337, 0.55557023301960222474283081394853287, 0.47139673682599764855638762590525438, \
+    0.38268343236508977172845998403039887, 0.29028467725446236763619237581739527, 0.19509032201612826784828486847702224, \
+    0.098017140329560601994195563888641846
+#define AUS_W64_SIN \
+    0.0, 0.098017140329560601994195563888641846, 0.19509032201612826784828486847702224, \
+    0.29028467725446236763619237581739527, 0.38268343236508977172845998403039887, 0.47139673682599764855638762590525438, \
+    0.55557023301960222474283081394853287, 0.63439328416364549821517161322549337, 0.70710678118654752440084436210484904, \
+    0.7730104533627369608109066097584698, 0.83146961230254523707878837761790576, 0.88192126434835502971275686366038835, \
+    0.92387953251128675612818318939678829, 0.95694033573220886493579788698026997, 0.98078528040323044912618223613423904, \
+    0.99518472667219688624483695310947992
+__constant__ double c_w64_cos[16] = {AUS_W64_COS};
+__constant__ double c_w64_sin[16] = {AUS_W64_SIN};
 __host__ __device__ constexpr double w64_cos(int i) {
-    constexpr double t[16] = {1.0, 0.99518472667219688624483695310947992, 0.98078528040323044912618223613423904, 0.95694033573220886493579788698026997, 0.92387953251128675612818318939678829, 0.88192126434835502971275686366038835, 0.83146961230254523707878837761790576, 0.7730104533627369608109066097584698, 0.70710678118654752440084436210484904, 0.63439328416364549821517161322549337, 0.55557023301960222474283081394853287, 0.47139673682599764855638762590525438, 0.38268343236508977172845998403039887, 0.29028467725446236763619237581739527, 0.19509032201612826784828486847702224, 0.098017140329560601994195563888641846};
+    constexpr double t[16] = {AUS_W64_COS};
     return t[i];
 }
 __host__ __device__ constexpr double w64_sin(int i) {
-    constexpr double t[16] = {0.0, 0.098017140329560601994195563888641846, 0.19509032201612826784828486847702224, 0.29028467725446236763619237581739527, 0.38268343236508977172845998403039887, 0.47139673682599764855638762590525438, 0.55557023301960222474283081394853287, 0.63439328416364549821517161322549337, 0.70710678118654752440084436210484904, 0.7730104533627369608109066097584698, 0.83146961230254523707878837761790576, 0.88192126434835502971275686366038835, 0.92387953251128675612818318939678829, 0.95694033573220886493579788698026997, 0.98078528040323044912618223613423904, 0.99518472667219688624483695310947992};
+    constexpr double t[16] = {AUS_W64_SIN};
     return t[i];
 }
 template <typename T, int S> __device__ __forceinline__ Cx<T> tw64() {
@@ -58,8 +69,7 @@ template <int W> __device__ __forceinline__ Cx<float> shfl_cx(Cx<float> a, int s
 template <typename T, int LOG2N, typename C>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
                                                const Cx<T> *gsrc, Cx<T> (&v)[32]) {
-    constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, XS = C::XS;
-    static_assert(TPF <= 32, "register-resident path: one frame per warp or less");
+    constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, R3 = C::R3, XS = C::XS;
 
     if constexpr (M == 32) {                                  // one thread per frame: a single radix-32 pass
         static_for<0, 32>([&](auto r_) {
@@ -75,6 +85,7 @@ __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &
         int lbase = j, lstride = TPF;
         const Cx<T> *tab = p.win2 + j;
         int tstride = TPF;
+        int sbase = 33 * j, sstride = 1;
 #pragma unroll 1
         for (int pass = 0; pass < p.npass; ++pass) {
             if (pass == 0) {
@@ -97,17 +108,47 @@ __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &
             }
             group_sync<TPF, C::BLOCK>(grp);                   // every load done before buf is overwritten
             dft_dif<32>(v);
-            if (pass == 0) {
+            if (pass == 0 || C::THREE) {                      // two-pass sizes keep the second pass in registers
                 static_for<0, 32>([&](auto r_) {
                     constexpr int r = decltype(r_)::value;
-                    buf[33 * j + r] = v[bitrev(r, 5)];
+                    buf[sbase + r * sstride] = v[bitrev(r, 5)];
                 });
                 group_sync<TPF, C::BLOCK>(grp);
                 lbase = j + (j >> 5);
                 lstride = TPF + TPF / 32;
                 tab = p.tw2 + (j & 31);
                 tstride = 32;
+                const int b = (j >> 5) * 1024 + (j & 31);     // (three-pass sizes) exchange layout: pad5(b + 32 r)
+                sbase = b + (b >> 5);
+                sstride = 33;
             }
+        }
+        if constexpr (C::THREE) {
+            // ---- pass 3 (M > 1024): radix R3, Ns = 1024, B3 = 32 / R3 butterflies per thread, kept in registers: butterfly
+            //      b of thread t yields bins t + TPF b + 1024 r = t + TPF (b + B3 r), i.e. natural index s = b + B3 r
+            constexpr int B3 = 32 / R3;
+            Cx<T> w[32];
+            static_for<0, B3>([&](auto b_) {
+                constexpr int b = decltype(b_)::value;
+                const int jj = t + TPF * b;
+                static_for<0, R3>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    Cx<T> z = buf[padi<XS>(jj + r * 1024)];
+                    if constexpr (r > 0) z = cmul(z, ldg_cx(&p.tw3[r * 1024 + jj]));
+                    w[b * R3 + r] = z;
+                });
+            });
+            group_sync<TPF, C::BLOCK>(grp);
+            static_for<0, B3>([&](auto b_) {
+                constexpr int b = decltype(b_)::value;
+                Cx<T> u[R3];
+                static_for<0, R3>([&](auto r_) { u[decltype(r_)::value] = w[b * R3 + decltype(r_)::value]; });
+                dft_dif<R3>(u);
+                static_for<0, R3>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    v[bitrev(b + B3 * r, 5)] = u[bitrev(r, ilog2(R3))];
+                });
+            });
         }
     } else {
         constexpr int B1 = 32 / R1;
@@ -397,7 +438,8 @@ __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double 
     //      in slot 16 TPF -- where the partner of pair s is slot (16 - s) TPF - t for every thread; twice the shared-memory
     //      traffic, but 64 registers are free right after the store, which the f64 feature pass needs (measured +4..12 %).
     const Cx<T> wt = ldg_cx(&p.twN[t]);                  // (cos, sin)(2 pi t / N)
-    constexpr int PB = AUS_TAIL_BATCH(T);                // pairs per batch
+    constexpr int PB = 4;                                // pairs per batch
+    static_assert(!SHFL || TPF <= 32, "the shuffle exchange needs the whole frame group in one warp");
     Cx<T> *const xb = buf + (C::BUF - 16 * TPF - 2);
     const int partner = (TPF - t) & (TPF - 1);
     auto exchange = [&](auto s_) {                       // shuffle variant: in place, v[bitrev(31 - s)] <- Z'[M - k]

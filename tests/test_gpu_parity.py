@@ -466,10 +466,11 @@ def test_randomised_parameter_sweep(ctx, orc):
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("fft_size,hop", [(64, 16), (128, 32), (256, 64), (512, 128), (1024, 256), (2048, 512), (2048, 300)])
+@pytest.mark.parametrize("fft_size,hop", [(64, 16), (128, 32), (256, 64), (512, 128), (1024, 256), (2048, 512), (2048, 300),
+                                          (4096, 1024), (8192, 2048), (16384, 4096)])
 def test_forward_kernel_variants(ctx, orc, variant, fft_size, hop):
-    """Both forward kernels for fft_size <= 2048 -- shared-memory tail (0) and register-resident tail (1, aus_stft_r.cuh)
-    -- against the oracle, f64 and f32, features + spectra in one call, ragged files incl. silence and a short last frame."""
+    """Both forward kernels -- shared-memory tail (0) and register-resident tail (1, aus_stft_r.cuh) -- against the
+    oracle, f64 and f32, features + spectra in one call, ragged files incl. silence and a short last frame."""
     import torch
     ctx.use_torch_stream()
     ctx.set_forward_variant(variant)
@@ -491,6 +492,22 @@ def test_forward_kernel_variants(ctx, orc, variant, fft_size, hop):
             torch.cuda.synchronize()
             got_f = feat.cpu().numpy().astype(np.float64)
             got_s = torch.view_as_complex(spec).cpu().numpy().astype(np.complex128)
+            # the single-output launches (features only; spectra only = the build that copies the next frame in early)
+            feat1 = torch.zeros_like(feat)
+            spec1 = torch.zeros_like(spec)
+            ctx.stft_features_batch_dev(d, offs, lens, fft_size, hop, orc.HAMMING, SR, prec, feat1, None)
+            ctx.stft_features_batch_dev(d, offs, lens, fft_size, hop, orc.HAMMING, SR, prec, None, spec1)
+            torch.cuda.synchronize()
+            rt = 1e-11 if prec == "f64" else 2e-5
+            pk = np.abs(got_s).max(axis=1, keepdims=True) + 1e-300
+            s1 = torch.view_as_complex(spec1).cpu().numpy().astype(np.complex128)
+            assert np.array_equal(np.isnan(s1), np.isnan(got_s))
+            assert np.nanmax(np.abs(np.nan_to_num(s1) - np.nan_to_num(got_s)) / pk, initial=0.0) <= rt
+            f1 = feat1.cpu().numpy().astype(np.float64)
+            assert np.array_equal(np.isnan(f1), np.isnan(got_f))
+            if prec == "f64":
+                assert_features(f1, got_f, 1e-9, f"variant {variant} {prec} features-only vs mixed launch",
+                                scales=cancellation_scales(np.abs(np.nan_to_num(got_s)), fft_size, SR))
             pos = 0
             for i, (rf, rs) in enumerate(zip(refs_f, refs_s)):
                 gs, gf = got_s[pos:pos + rf.shape[0]], got_f[pos:pos + rf.shape[0]]
