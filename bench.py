@@ -263,6 +263,30 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = e2e_frames * world * e2e_steps / float(te.item())
+    # ---- the same call fed with decoded 16-bit PCM instead of f64 samples (`sample as f64 / INTMAX` of
+    #      audiofile.rs:296-329 done on the device): 2 bytes per sample over PCIe instead of 8.  Extra information, not `e2e`.
+    e2e_pcm = None
+    try:
+        h_pcm = torch.empty(e2e_files * FILE_SAMPLES, dtype=torch.int16, pin_memory=True)
+        h_pcm.copy_((d_audio[: e2e_files * FILE_SAMPLES].double() * 32767.0).round().clamp(-32768, 32767).to(torch.int16))
+        p_np = h_pcm.numpy()
+        for _ in range(2):
+            ctx.stft_features_batch_pcm(p_np, offs[:e2e_files], lens[:e2e_files], FFT, HOP, WINDOW, SR, prec, out=o_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.stft_features_batch_pcm(p_np, offs[:e2e_files], lens[:e2e_files], FFT, HOP, WINDOW, SR, prec, out=o_np)
+        torch.cuda.synchronize()
+        tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        e2e_pcm = {"value": e2e_frames * world * e2e_steps / float(tp.item()), "unit": "frames/s",
+                   "h2d_bytes_per_step": e2e_files * FILE_SAMPLES * 2, "d2h_bytes_per_step": e2e_frames * 14 * 8,
+                   "host_dtype": "int16 PCM (pinned), widened on the device like audiofile.rs:296-329"}
+        ctx.stft_features_batch(a_np, offs[:e2e_files], lens[:e2e_files], FFT, HOP, WINDOW, SR, prec, out=o_np)   # restore o_np
+        torch.cuda.synchronize()
+    except Exception as exc:                       # extra information only: never fail the bench line over it
+        e2e_pcm = {"error": str(exc)[:200]}
     # the e2e result must be the same numbers as the device-resident run (f64 host API converts on the device)
     chk = d_feat[:1000].double().cpu().numpy()
     assert np.allclose(o_np[:1000], chk, rtol=1e-6 if prec == "f32" else 1e-12, atol=0, equal_nan=True)
@@ -305,6 +329,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": e2e_files * FILE_SAMPLES * 8,
                     "d2h_bytes_per_step": e2e_frames * 14 * 8, "files_per_step": e2e_files, "steps": e2e_steps,
                     "host_dtype": "f64 (pinned)", "rank_cpu_affinity": numa},
+            "e2e_pcm16": e2e_pcm,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "stft_kernel<double, 11, 0>" if prec == "f64" else "stft_kernel<float, 11, 1>",

@@ -49,5 +49,6 @@ def test_gpu_arm_line():
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1.2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert d["gpu_launches"] == 2 * d["steps"]                      # stft_kernel + finalize_kernel per step
     assert d["e2e"]["h2d_bytes_per_step"] == 3600 * 44100 * 8 and d["e2e"]["value"] < d["value"]
+    assert d["e2e_pcm16"]["h2d_bytes_per_step"] == 3600 * 44100 * 2 and d["e2e_pcm16"]["value"] > d["e2e"]["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["value"] > 100 * d["cpu_baseline"]["value"]
