@@ -80,6 +80,8 @@ SIGNATURES = {
     "aus_rfft": (c_int, [c_void_p, _p_d, c_size_t, c_int, _p_d]),
     "aus_complex_to_polar": (c_int, [c_void_p, _p_d, c_size_t, _p_d, _p_d]),
     "aus_polar_to_complex": (c_int, [c_void_p, _p_d, _p_d, c_size_t, _p_d]),
+    "aus_spectral_features_generic": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d, _p_d, c_size_t, _p_d, _p_d, c_size_t,
+                                              c_uint32, _p_d]),
     "aus_analyzer_batch": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_uint32, c_int, _p_d]),
     "aus_analyzer_batch_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, c_int, c_void_p]),
     "aus_irstft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, _p_d]),

@@ -53,25 +53,17 @@ def make_power_spectrum(magnitude_spectrum) -> np.ndarray:
     return np.asarray(magnitude_spectrum, dtype=np.float64) ** 2.0
 
 
-def _one(magnitude_spectrum, rfft_freqs, sample_rate=None) -> np.ndarray:
-    """Single-feature wrappers take the bin frequencies as an argument; the device path needs them to be the
-    rfftfreq grid f[k] = f0*k, which is what the reference's own callers pass (analyzer.rs:46)."""
-    m = np.asarray(magnitude_spectrum, dtype=np.float64)
-    fft_size = 2 * (m.shape[-1] - 1)
-    if rfft_freqs is not None:
-        f = np.asarray(rfft_freqs, dtype=np.float64)
-        if f.shape[-1] != m.shape[-1]:
+def _one(magnitude_spectrum, rfft_freqs, roll=(), bands=(), sample_rate=None) -> np.ndarray:
+    """One row through the generic device path (any length, any frequency table, any parameters):
+    [centroid, variance, skewness, kurtosis, entropy, flatness, slope, roll-offs..., band slopes...]."""
+    m = np.asarray(magnitude_spectrum, dtype=np.float64).reshape(-1)
+    if rfft_freqs is None:
+        f = np.arange(m.size, dtype=np.float64)          # features that do not depend on the frequency table
+    else:
+        f = np.asarray(rfft_freqs, dtype=np.float64).reshape(-1)
+        if f.size != m.size:
             raise IndexError("rfft_freqs and magnitude_spectrum differ in length (the reference panics)")
-        sr = float(f[1]) * fft_size
-        if not np.allclose(f, f[1] * np.arange(f.shape[-1]), rtol=1e-12, atol=0.0):
-            raise ValueError("rfft_freqs must be the uniform rfftfreq grid")
-        if sample_rate is None:
-            sample_rate = int(round(sr))
-        if abs(sr - sample_rate) > 1e-6 * max(1.0, sr):
-            raise ValueError("rfft_freqs does not correspond to an integer sample rate")
-    elif sample_rate is None:
-        sample_rate = 44100   # features that do not depend on frequency
-    return default_context().analyzer_batch(m, fft_size, int(sample_rate))[0]
+    return default_context().spectral_features_generic(m, f, roll, bands, sample_rate if sample_rate is not None else 44100)[0]
 
 
 def spectral_centroid(magnitude_spectrum, rfft_freqs) -> float:      # s_a_t.rs:306
@@ -99,21 +91,17 @@ def spectral_flatness(magnitude_spectrum) -> float:                  # :343
 
 
 def spectral_roll_off_point(magnitude_spectrum, rfft_freqs, n: float) -> float:   # :385
-    idx = {0.5: 6, 0.75: 7, 0.9: 8, 0.95: 9}.get(float(n))
-    if idx is None:
-        raise ValueError("the device path provides the analyzer's roll-off points 0.5 / 0.75 / 0.9 / 0.95 (analyzer.rs:53-56)")
-    return float(_one(magnitude_spectrum, rfft_freqs)[idx])
+    """Any roll-off fraction 0 < n <= 1 and any frequency table."""
+    return float(_one(magnitude_spectrum, rfft_freqs, roll=(float(n),))[7])
 
 
 def spectral_slope(magnitude_spectrum) -> float:                     # :426
-    return float(_one(magnitude_spectrum, None)[10])
+    return float(_one(magnitude_spectrum, None)[6])
 
 
 def spectral_slope_region(magnitude_spectrum, rfft_freqs, f_lower: float, f_upper: float, sample_rate: int) -> float:  # :447
-    idx = {(0.0, 1000.0): 11, (1000.0, 5000.0): 12, (0.0, 5000.0): 13}.get((float(f_lower), float(f_upper)))
-    if idx is None:
-        raise ValueError("the device path provides the analyzer's three bands 0-1k / 1-5k / 0-5k Hz (analyzer.rs:60-62)")
-    return float(_one(magnitude_spectrum, rfft_freqs, sample_rate)[idx])
+    """Any band inside the spectrum (the reference panics when the upper edge reaches the last bin: AusError here)."""
+    return float(_one(magnitude_spectrum, rfft_freqs, bands=((float(f_lower), float(f_upper)),), sample_rate=sample_rate)[7])
 
 
 # ---- SURVEY 8(f) "next" rows: analysis::autocorrelation and the time-domain scalars of audio_analysis_tools.rs

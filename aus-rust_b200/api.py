@@ -221,6 +221,24 @@ class Context:
                                                 _prec(precision), _pd(out)))
         return out
 
+    def spectral_features_generic(self, magnitudes, rfft_freqs, roll_fractions=(), bands=(), sample_rate: int = 44100) -> np.ndarray:
+        """The single-feature wrappers of spectral_analysis_tools.rs:306-471 with arbitrary parameters: rows of any
+        length, any frequency table, any roll-off fractions, any slope bands [(f_lower, f_upper), ...].
+        -> [rows, 7 + len(roll_fractions) + len(bands)]: centroid, variance, skewness, kurtosis, entropy, flatness, slope, ..."""
+        m = _f64(magnitudes)
+        if m.ndim == 1:
+            m = m[None, :]
+        f = _f64(rfft_freqs).reshape(-1)
+        if f.size != m.shape[1]:
+            raise IndexError("rfft_freqs and magnitude_spectrum differ in length (the reference panics)")
+        r = _f64(np.asarray(roll_fractions, dtype=np.float64).reshape(-1))
+        b = np.asarray(bands, dtype=np.float64).reshape(-1, 2)
+        lo, hi = _f64(b[:, 0].copy()), _f64(b[:, 1].copy())
+        out = np.empty((m.shape[0], 7 + r.size + lo.size), dtype=np.float64)
+        _lib.check(self._lib.aus_spectral_features_generic(self._h, _pd(m), m.shape[0], m.shape[1], _pd(f), _pd(r), r.size,
+                                                           _pd(lo), _pd(hi), lo.size, int(sample_rate), _pd(out)))
+        return out
+
     def autocorrelation(self, audio, fft_size: int) -> np.ndarray:
         """analysis/spectral_analysis_tools.rs:31 (one chunk, or [n_chunks, fft_size] rows)."""
         a = _f64(audio)

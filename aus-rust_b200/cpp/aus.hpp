@@ -117,6 +117,39 @@ inline Analysis analyzer(const std::vector<double> &magnitude_spectrum, size_t f
                                   reinterpret_cast<double *>(&a)));
     return a;
 }
+// The single-feature wrappers of spectral_analysis_tools.rs:306-471 with the reference's full parameter space (rows of any
+// length, any frequency table, any roll-off fraction, any slope band) through the generic device entry point:
+// [centroid, variance, skewness, kurtosis, entropy, flatness, slope, roll-offs..., band slopes...].
+namespace detail {
+inline std::vector<double> one(const std::vector<double> &m, const std::vector<double> *freqs, const std::vector<double> &roll,
+                               const std::vector<double> &lo, const std::vector<double> &hi, uint32_t sample_rate) {
+    std::vector<double> idx;
+    if (freqs == nullptr) {
+        idx.resize(m.size());
+        for (size_t i = 0; i < m.size(); ++i) idx[i] = (double)i;
+        freqs = &idx;
+    }
+    if (freqs->size() != m.size()) throw std::runtime_error("rfft_freqs and magnitude_spectrum differ in length");
+    std::vector<double> out(7 + roll.size() + lo.size());
+    aus::detail::ok(aus_spectral_features_generic(aus::detail::ctx(), m.data(), 1, m.size(), freqs->data(), roll.data(), roll.size(),
+                                                  lo.data(), hi.data(), lo.size(), sample_rate, out.data()));
+    return out;
+}
+}  // namespace detail
+inline double spectral_centroid(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[0]; }   // :306
+inline double spectral_variance(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[1]; }   // :466
+inline double spectral_skewness(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[2]; }   // :405
+inline double spectral_kurtosis(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[3]; }   // :362
+inline double spectral_entropy(const std::vector<double> &m) { return detail::one(m, nullptr, {}, {}, {}, 44100)[4]; }                             // :324
+inline double spectral_flatness(const std::vector<double> &m) { return detail::one(m, nullptr, {}, {}, {}, 44100)[5]; }                            // :343
+inline double spectral_slope(const std::vector<double> &m) { return detail::one(m, nullptr, {}, {}, {}, 44100)[6]; }                               // :426
+inline double spectral_roll_off_point(const std::vector<double> &m, const std::vector<double> &f, double n) {                                    // :385
+    return detail::one(m, &f, {n}, {}, {}, 44100)[7];
+}
+inline double spectral_slope_region(const std::vector<double> &m, const std::vector<double> &f, double f_lower, double f_upper,
+                                    uint32_t sample_rate) {                                                                                       // :447
+    return detail::one(m, &f, {}, {f_lower}, {f_upper}, sample_rate)[7];
+}
 }  // namespace analysis
 
 namespace mp {

@@ -609,6 +609,78 @@ __global__ void time_final_kernel(const double *partials, const unsigned long lo
     out[f * 4 + 3] = zc * (double)sr / n;                                     // zero_crossing_rate, :98-108
 }
 
+// analysis/spectral_analysis_tools.rs:306-471, generic parameters: one thread per row, the reference's loop order
+__global__ void __launch_bounds__(128) spectral_generic_kernel(const double *mags, unsigned long long n_rows, int K, const double *freqs,
+                                                              const double *roll, int n_roll, const double *blo, const double *bhi,
+                                                              int n_bands, double sr, double *out) {
+    const unsigned long long row = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const double *m = mags + row * (unsigned long long)K;
+    double *o = out + row * (unsigned long long)(7 + n_roll + n_bands);
+    const double n = (double)K;
+    double msum = 0.0, psum = 0.0, mf = 0.0, lsum = 0.0, px = 0.0;
+    for (int i = 0; i < K; ++i) {
+        const double mi = m[i], pi = mi * mi;                       // make_power_spectrum, :273-279
+        msum += mi;
+        psum += pi;
+        mf += mi * freqs[i];                                        // :79-85
+        lsum += log(mi);                                            // :107-114
+        px += pi * (double)i;                                       // dot_product(power, x), :167-182
+    }
+    const double c = mf / msum;
+    double var = 0.0, ent = 0.0;
+    for (int i = 0; i < K; ++i) {
+        const double q = (m[i] * m[i]) / psum;                      // make_spectrum_pmf, :284-290
+        var += pow(freqs[i] - c, 2.0) * q;                          // :238-244
+        ent += q * log2(q);                                         // :93-99
+    }
+    double sk = 0.0, ku = 0.0;
+    for (int i = 0; i < K; ++i) {
+        const double q = (m[i] * m[i]) / psum;
+        sk += pow(freqs[i] - c, 3.0) * q;                           // :153-160
+        ku += pow(freqs[i] - c, 4.0) * q;                           // :122-129
+    }
+    o[0] = c;
+    o[1] = var;
+    o[2] = sk / pow(var, 1.5);
+    o[3] = ku / pow(var, 2.0);
+    o[4] = -ent;
+    o[5] = exp(lsum / n) * n / msum;
+    const double sum_x = n * (n - 1.0) / 2.0, sum_x2 = n * (n - 1.0) * (2.0 * n - 1.0) / 6.0;
+    o[6] = (n * px - sum_x * psum) / (n * sum_x2 - pow(sum_x, 2.0));
+    for (int r = 0; r < n_roll; ++r) {                              // :137-145
+        const double frac = roll[r];
+        long long i = -1;
+        double cum = 0.0;
+        while (cum < frac && i < (long long)K - 1) {
+            ++i;
+            cum += (m[i] * m[i]) / psum;
+        }
+        o[7 + r] = freqs[i < 0 ? 0 : i];                            // i == -1 (frac <= 0): the reference indexes [-1] and panics
+    }
+    const double fund = sr / ((double)(K - 1) * 2.0);
+    for (int b = 0; b < n_bands; ++b) {                             // :190-230 (bounds checked on the host)
+        const double fl = blo[b], fu = bhi[b];
+        const double m_fl = fl / fund, m_fu = fu / fund;
+        const int lc = (int)ceil(m_fl), lf = (int)floor(m_fl), uc = (int)ceil(m_fu), uf = (int)floor(m_fu);
+        double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0;
+        for (int i = lc; i < uf; ++i) {
+            const double pi = m[i] * m[i];
+            sx += freqs[i];
+            sy += pi;
+            sxx += freqs[i] * freqs[i];
+            sxy += pi * freqs[i];
+        }
+        const double pl = m[lf] * m[lf] + (m_fl - (double)lf) * (m[lc] * m[lc] - m[lf] * m[lf]);
+        const double pu = m[uf] * m[uf] + (m_fu - (double)uf) * (m[uc] * m[uc] - m[uf] * m[uf]);
+        const double sum_x = fl + sx + fu;
+        const double sum_y = pl + sy + pu;
+        const double sum_x2 = pow(fl, 2.0) + sxx + pow(fu, 2.0);
+        const double sum_xy = fl * pl + sxy + fu * pu;
+        o[7 + n_roll + b] = (n * sum_xy - sum_x * sum_y) / (n * sum_x2 - pow(sum_x, 2.0));
+    }
+}
+
 // fft_tools.rs:41-55
 __global__ void to_polar_kernel(const double2 *s, double *mag, double *ph, unsigned long long n) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -1121,6 +1193,43 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
+    return AUS_OK;
+}
+
+extern "C" int aus_spectral_features_generic(aus_ctx *c, const double *mags, size_t n_rows, size_t n_bins, const double *freqs,
+                                             const double *roll, size_t n_roll, const double *band_lo, const double *band_hi,
+                                             size_t n_bands, uint32_t sr, double *out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (!mags || !freqs || !out || (n_roll && !roll) || (n_bands && (!band_lo || !band_hi))) return fail(AUS_ERR_INVALID, "null argument");
+    if (n_bins < 2 || n_bins > (1u << 24) || n_roll > 4096 || n_bands > 4096) return fail(AUS_ERR_INVALID, "bad size");
+    if (n_rows == 0) return AUS_OK;
+    const double fund = (double)sr / ((double)(n_bins - 1) * 2.0);
+    for (size_t b = 0; b < n_bands; ++b) {            // the reference slices power_spectrum[m_fl_ceil..m_fu_floor] and indexes
+        const double m_fl = band_lo[b] / fund, m_fu = band_hi[b] / fund;      // [m_fu_ceil]: out of range -> it panics
+        if (!(m_fl >= 0.0) || !(m_fu >= m_fl) || !(std::ceil(m_fu) < (double)n_bins))
+            return fail(AUS_ERR_INVALID, "slope band outside the spectrum (the reference panics: index out of bounds)");
+    }
+    for (size_t r = 0; r < n_roll; ++r)
+        if (!(roll[r] > 0.0)) return fail(AUS_ERR_INVALID, "roll-off fraction must be > 0 (the reference indexes [-1] and panics)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t w = 7 + n_roll + n_bands;
+    const size_t n_in = n_rows * n_bins, n_par = n_bins + n_roll + 2 * n_bands;
+    AUS_TRY(c->aux64.ensure((n_in + n_par) * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n_rows * w * sizeof(double)));
+    double *d_m = (double *)c->aux64.p, *d_f = d_m + n_in, *d_r = d_f + n_bins, *d_bl = d_r + n_roll, *d_bh = d_bl + n_bands;
+    CUDA_TRY(cudaMemcpyAsync(d_m, mags, n_in * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_f, freqs, n_bins * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n_roll) CUDA_TRY(cudaMemcpyAsync(d_r, roll, n_roll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (n_bands) {
+        CUDA_TRY(cudaMemcpyAsync(d_bl, band_lo, n_bands * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_bh, band_hi, n_bands * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    spectral_generic_kernel<<<(unsigned int)((n_rows + 127) / 128), 128, 0, c->stream>>>(
+        d_m, n_rows, (int)n_bins, d_f, d_r, (int)n_roll, d_bl, d_bh, (int)n_bands, (double)sr, (double *)c->out64.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, n_rows * w * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
 

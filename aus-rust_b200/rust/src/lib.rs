@@ -45,6 +45,9 @@ extern "C" {
     fn aus_polar_to_complex(ctx: *mut AusCtx, mag: *const f64, ph: *const f64, n: usize, spectra: *mut f64) -> c_int;
     fn aus_analyzer_batch(ctx: *mut AusCtx, mags: *const f64, n_frames: usize, fft_size: usize, sample_rate: u32,
                           precision: c_int, features: *mut f64) -> c_int;
+    fn aus_spectral_features_generic(ctx: *mut AusCtx, mags: *const f64, n_rows: usize, n_bins: usize, rfft_freqs: *const f64,
+                                     roll_fractions: *const f64, n_roll: usize, band_lo: *const f64, band_hi: *const f64,
+                                     n_bands: usize, sample_rate: u32, out: *mut f64) -> c_int;
 }
 
 const AUS_ERR_SIZE: c_int = -4;
@@ -254,34 +257,32 @@ pub mod analysis {
         magnitude_spectrum.iter().map(|m| m * m).collect()
     }
 
-    // The single-feature wrappers (spectral_analysis_tools.rs:306-471) take the bin frequencies as an argument; the
-    // device path needs the rfftfreq grid the reference's own callers pass (analyzer.rs:46).
-    fn one(m: &Vec<f64>, freqs: Option<&Vec<f64>>, sample_rate: Option<u32>) -> Analysis {
-        let fft_size = 2 * (m.len() - 1);
-        let sr = sample_rate.unwrap_or_else(|| freqs.map_or(44100, |f| (f[1] * fft_size as f64).round() as u32));
-        analyzer(m, fft_size, sr)
+    // The single-feature wrappers (spectral_analysis_tools.rs:306-471) keep the reference's full parameter space -- rows of
+    // any length, any frequency table, any roll-off fraction, any slope band -- through the generic device entry point:
+    // [centroid, variance, skewness, kurtosis, entropy, flatness, slope, roll-offs..., band slopes...].
+    fn one(m: &Vec<f64>, freqs: Option<&Vec<f64>>, roll: &[f64], band: Option<(f64, f64)>, sample_rate: u32) -> Vec<f64> {
+        let idx: Vec<f64>;
+        let f: &Vec<f64> = match freqs { Some(f) => { assert_eq!(f.len(), m.len()); f }, None => { idx = (0..m.len()).map(|i| i as f64).collect(); &idx } };
+        let (lo, hi): (Vec<f64>, Vec<f64>) = band.map_or((vec![], vec![]), |(l, h)| (vec![l], vec![h]));
+        let mut out = vec![0.0f64; 7 + roll.len() + lo.len()];
+        with_ctx(|c| ok(unsafe {
+            aus_spectral_features_generic(c, m.as_ptr(), 1, m.len(), f.as_ptr(), roll.as_ptr(), roll.len(), lo.as_ptr(), hi.as_ptr(),
+                                          lo.len(), sample_rate, out.as_mut_ptr())
+        }));
+        out
     }
-    pub fn spectral_centroid(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_centroid }   // :306
-    pub fn spectral_entropy(m: &Vec<f64>) -> f64 { one(m, None, None).spectral_entropy }                                       // :324
-    pub fn spectral_flatness(m: &Vec<f64>) -> f64 { one(m, None, None).spectral_flatness }                                     // :343
-    pub fn spectral_kurtosis(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_kurtosis }   // :362
-    pub fn spectral_skewness(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_skewness }   // :405
-    pub fn spectral_variance(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), None).spectral_variance }   // :466
-    pub fn spectral_slope(m: &Vec<f64>) -> f64 { one(m, None, None).spectral_slope }                                           // :426
-    /// :385 -- the analyzer's roll-off points 0.5 / 0.75 / 0.9 / 0.95 (analyzer.rs:53-56)
-    pub fn spectral_roll_off_point(m: &Vec<f64>, rfft_freqs: &Vec<f64>, n: f64) -> f64 {
-        let a = one(m, Some(rfft_freqs), None);
-        if n == 0.5 { a.spectral_roll_off_50 } else if n == 0.75 { a.spectral_roll_off_75 }
-        else if n == 0.9 { a.spectral_roll_off_90 } else if n == 0.95 { a.spectral_roll_off_95 }
-        else { panic!("aus_b200: roll-off point {} is not one of the analyzer's four", n) }
-    }
-    /// :447 -- the analyzer's bands 0-1k / 1-5k / 0-5k Hz (analyzer.rs:60-62)
+    pub fn spectral_centroid(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), &[], None, 44100)[0] }   // :306
+    pub fn spectral_variance(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), &[], None, 44100)[1] }   // :466
+    pub fn spectral_skewness(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), &[], None, 44100)[2] }   // :405
+    pub fn spectral_kurtosis(m: &Vec<f64>, rfft_freqs: &Vec<f64>) -> f64 { one(m, Some(rfft_freqs), &[], None, 44100)[3] }   // :362
+    pub fn spectral_entropy(m: &Vec<f64>) -> f64 { one(m, None, &[], None, 44100)[4] }                                      // :324
+    pub fn spectral_flatness(m: &Vec<f64>) -> f64 { one(m, None, &[], None, 44100)[5] }                                     // :343
+    pub fn spectral_slope(m: &Vec<f64>) -> f64 { one(m, None, &[], None, 44100)[6] }                                        // :426
+    /// :385
+    pub fn spectral_roll_off_point(m: &Vec<f64>, rfft_freqs: &Vec<f64>, n: f64) -> f64 { one(m, Some(rfft_freqs), &[n], None, 44100)[7] }
+    /// :447 (a band that reaches the last bin panics, as in the reference)
     pub fn spectral_slope_region(m: &Vec<f64>, rfft_freqs: &Vec<f64>, f_lower: f64, f_upper: f64, sample_rate: u32) -> f64 {
-        let a = one(m, Some(rfft_freqs), Some(sample_rate));
-        match (f_lower as i64, f_upper as i64) {
-            (0, 1000) => a.spectral_slope_0_1_khz, (1000, 5000) => a.spectral_slope_1_5_khz, (0, 5000) => a.spectral_slope_0_5_khz,
-            _ => panic!("aus_b200: slope band is not one of the analyzer's three"),
-        }
+        one(m, Some(rfft_freqs), &[], Some((f_lower, f_upper)), sample_rate)[7]
     }
 }
 

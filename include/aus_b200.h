@@ -173,6 +173,19 @@ int aus_analyzer_batch(aus_ctx *ctx, const double *magnitudes, size_t n_frames, 
 int aus_analyzer_batch_dev(aus_ctx *ctx, const void *d_magnitudes, size_t n_frames, size_t fft_size,
                            uint32_t sample_rate, int precision, void *d_features);
 
+/* analysis::spectral_centroid / _variance / _skewness / _kurtosis / _entropy / _flatness / _slope / _roll_off_point /
+ * _slope_region (analysis/spectral_analysis_tools.rs:306-471) with the reference's full parameter space: rows of ANY
+ * length n_bins, the caller's own rfft_freqs table (need not be uniform), any roll-off fractions and any slope bands
+ * (band i = [band_lo[i], band_hi[i]] Hz at sample_rate).  One device thread per row walks the bins in the reference's
+ * summation order, so roll-off decisions are those of the reference's own `cum += p[i] / P` arithmetic.  This is the
+ * generic fallback of the single-feature wrappers, not the hot path (aus_analyzer_batch is).
+ * out: n_rows x (7 + n_roll + n_bands) = centroid, variance, skewness, kurtosis, entropy, flatness, slope, roll-offs, band
+ * slopes.  A band whose upper edge reaches the last bin (the reference indexes out of bounds) gives AUS_ERR_INVALID. */
+int aus_spectral_features_generic(aus_ctx *ctx, const double *magnitudes, size_t n_rows, size_t n_bins,
+                                  const double *rfft_freqs, const double *roll_fractions, size_t n_roll,
+                                  const double *band_lo, const double *band_hi, size_t n_bands, uint32_t sample_rate,
+                                  double *out);
+
 /* ---- inverse (kernels K4/K5) ------------------------------------------------------------------------- */
 /* spectrum/fft.rs:204 `irstft`: Hermitian extend, un-normalised inverse, window, overlap-add, window-norm divide,
  * peak-normalise to -6 dBFS.  frame_len must be fft_size/2+1, else AUS_ERR_SIZE with the reference's message.

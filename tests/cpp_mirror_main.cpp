@@ -25,6 +25,13 @@ int main(int argc, char **argv) {
         double mx = 0;
         for (double s : y) mx = std::fmax(mx, s);
         std::printf("irstft %zu %.17g\n", y.size(), mx);
+        {   // single-feature wrappers with non-analyzer parameters (spectral_analysis_tools.rs:385, :447)
+            std::vector<double> mag(S[1].size());
+            for (size_t k = 0; k < mag.size(); ++k) mag[k] = std::abs(S[1][k]);
+            const auto freqs = aus::spectrum::rfftfreq(2048, 44100);
+            std::printf("wrappers %.17g %.17g %.17g\n", aus::analysis::spectral_roll_off_point(mag, freqs, 0.85),
+                        aus::analysis::spectral_slope_region(mag, freqs, 105.0, 852.0, 44100), aus::analysis::spectral_centroid(mag, freqs));
+        }
         S[1].pop_back();
         try {
             aus::spectrum::irstft(S, 2048, 1024, aus::WindowType::Hamming);

@@ -39,5 +39,11 @@ def test_cpp_mirror_matches_oracle(aus, orc, tmp_path):
     ir = [l for l in out if l.startswith("irstft")][0].split()
     assert int(ir[1]) == 2048 + 1024 * (orc.num_frames(x.size, 2048, 1024) - 1)
     assert float(ir[2]) == pytest.approx(10 ** (-6 / 20), rel=1e-12)
+    w = [float(v) for v in [l for l in out if l.startswith("wrappers")][0].split()[1:]]
+    mag = np.abs(orc.rstft(x, 2048, 1024, orc.HAMMING)[1])
+    fr = orc.rfftfreq(2048, 44100)
+    assert w[0] == orc.spectral_roll_off_point(mag, fr, 0.85)
+    assert w[1] == pytest.approx(orc.spectral_slope_region(mag, fr, 105.0, 852.0, 44100), rel=1e-7)
+    assert w[2] == pytest.approx(orc.spectral_centroid(mag, fr), rel=1e-9)
     err = [l for l in out if l.startswith("error")][0]
     assert "The spectrum at frame 1 has an incorrect length. It should be 1025, but it is actually 1024." in err

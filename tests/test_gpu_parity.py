@@ -525,3 +525,51 @@ def test_forward_kernel_variants(ctx, orc, variant, fft_size, hop):
                                     scales=sc[ok][:, cols])
     finally:
         ctx.set_forward_variant(-1)
+
+
+def test_single_feature_wrappers_generic_parameters(ctx, aus, orc):
+    """spectral_analysis_tools.rs:306-471 with the reference's full parameter space: rows of any length, a non-uniform
+    frequency table, arbitrary roll-off fractions and slope bands (the doc example's 105-852 Hz), zero bins."""
+    rng = np.random.default_rng(11)
+    for K, sr in ((1025, 44100), (513, 48000), (100, 8000), (2, 44100), (4097, 22050)):
+        m = np.abs(rng.normal(size=K)) + 1e-3
+        f_uniform = orc.rfftfreq(2 * (K - 1), sr) if K > 2 else np.array([0.0, sr / 2.0])
+        f_warped = np.sort(rng.uniform(0.0, sr / 2.0, K))               # any table is legal in the reference
+        for f in (f_uniform, f_warped):
+            A = aus.analysis
+            assert A.spectral_centroid(m, f) == pytest.approx(orc.spectral_centroid(m, f), rel=RTOL64)
+            assert A.spectral_variance(m, f) == pytest.approx(orc.spectral_variance(m, f), rel=RTOL64)
+            assert A.spectral_skewness(m, f) == pytest.approx(orc.spectral_skewness(m, f), rel=1e-7, abs=1e-9)
+            assert A.spectral_kurtosis(m, f) == pytest.approx(orc.spectral_kurtosis(m, f), rel=RTOL64)
+            for n in (0.3, 0.5, 0.85, 0.999, 1.0):
+                assert A.spectral_roll_off_point(m, f, n) == orc.spectral_roll_off_point(m, f, n)
+        assert aus.analysis.spectral_entropy(m) == pytest.approx(orc.spectral_entropy(m), rel=RTOL64)
+        assert aus.analysis.spectral_flatness(m) == pytest.approx(orc.spectral_flatness(m), rel=RTOL64)
+        assert aus.analysis.spectral_slope(m) == pytest.approx(orc.spectral_slope(m), rel=1e-7, abs=1e-12)
+        if K >= 100:
+            fund = sr / (2.0 * (K - 1))
+            for fl, fu in ((105.0, 852.0), (0.0, 3.5 * fund), (2 * fund, 40 * fund), (1000.0, 1000.0 + 10.25 * fund)):
+                if fu / fund >= K - 1:
+                    continue
+                got = aus.analysis.spectral_slope_region(m, f_uniform, fl, fu, sr)
+                ref = orc.spectral_slope_region(m, f_uniform, fl, fu, sr)
+                assert got == pytest.approx(ref, rel=1e-7, abs=1e-9 * float(np.max(m * m))), (K, fl, fu)
+            with pytest.raises(aus.AusError):                                  # the reference indexes out of bounds
+                aus.analysis.spectral_slope_region(m, f_uniform, 0.0, sr / 2.0 + 1.5 * fund, sr)
+            got = aus.analysis.spectral_slope_region(m, f_uniform, 0.0, sr / 2.0, sr)     # up to the last bin is legal
+            assert got == pytest.approx(orc.spectral_slope_region(m, f_uniform, 0.0, sr / 2.0, sr), rel=1e-7,
+                                        abs=1e-9 * float(np.max(m * m)))
+    # zero bins: entropy NaN (0 * -inf), flatness 0 (exp(-inf)), like the reference
+    m = np.abs(rng.normal(size=1025)) + 1e-3
+    m[7] = 0.0
+    assert np.isnan(aus.analysis.spectral_entropy(m)) and np.isnan(orc.spectral_entropy(m))
+    assert aus.analysis.spectral_flatness(m) == 0.0 == orc.spectral_flatness(m)
+    # many rows in one call
+    M = np.abs(rng.normal(size=(300, 513))) + 1e-3
+    f = orc.rfftfreq(1024, 44100)
+    got = ctx.spectral_features_generic(M, f, (0.25, 0.9), ((105.0, 852.0),), 44100)
+    assert got.shape == (300, 10)
+    for r in (0, 150, 299):
+        assert got[r, 0] == pytest.approx(orc.spectral_centroid(M[r], f), rel=RTOL64)
+        assert got[r, 7] == orc.spectral_roll_off_point(M[r], f, 0.25) and got[r, 8] == orc.spectral_roll_off_point(M[r], f, 0.9)
+        assert got[r, 9] == pytest.approx(orc.spectral_slope_region(M[r], f, 105.0, 852.0, 44100), rel=1e-7)
