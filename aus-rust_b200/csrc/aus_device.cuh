@@ -302,6 +302,14 @@ __device__ __forceinline__ bool abnormal(double x) { return (unsigned)__double2h
 __device__ __forceinline__ bool abnormal(float) { return false; }
 
 template <typename T> struct Mth;
+// log2 polynomial coefficients and the exponent-conversion constant as constant-bank operands: as 64-bit literals each
+// costs two MOVs per use, which the compiler re-materialises inside the rolled per-bin loops (5 of 35 instructions per bin)
+__constant__ double c_log2_k[6] = {0.28853900817779268147,      // 1/(5 ln2)
+                                   -0.36067376022224085184,     // -1/(4 ln2)
+                                   0.48089834696298780245,      // 1/(3 ln2)
+                                   -0.72134752044448170368,     // -1/(2 ln2)
+                                   1.44269504088896340736,      // 1/ln2
+                                   4503601774854144.0};         // 2^52 + 2^31
 template <> struct Mth<double> {
     static __device__ __forceinline__ double sqrt_exact(double x) { return sqrt(x); }
     static __device__ __forceinline__ double log2_exact(double x) { return log2(x); }
@@ -318,12 +326,12 @@ template <> struct Mth<double> {
         const double2 tc = tab[((hi >> 13) & (LOG2_TAB - 1)) * 8];     // 8 replicas per entry: see Cfg::LOGREP
         const double z = __hiloint2double((int)((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
         // exponent as a double without an I2F: 2^52 + 2^31 + (e ^ 0x80000000) trick
-        const double ed = __hiloint2double(0x43300000, (int)(((hi >> 20) - 1023u) ^ 0x80000000u)) - 4503601774854144.0;
+        const double ed = __hiloint2double(0x43300000, (int)(((hi >> 20) - 1023u) ^ 0x80000000u)) - c_log2_k[5];
         const double r = fma(z, tc.x, -1.0);
-        double pl = fma(r, 0.28853900817779268147, -0.36067376022224085184);   // 1/(5 ln2), -1/(4 ln2)
-        pl = fma(pl, r, 0.48089834696298780245);                                // 1/(3 ln2)
-        pl = fma(pl, r, -0.72134752044448170368);                               // -1/(2 ln2)
-        pl = fma(pl, r, 1.44269504088896340736);                                // 1/ln2
+        double pl = fma(r, c_log2_k[0], c_log2_k[1]);
+        pl = fma(pl, r, c_log2_k[2]);
+        pl = fma(pl, r, c_log2_k[3]);
+        pl = fma(pl, r, c_log2_k[4]);
         return fma(pl, r, ed + tc.y);
     }
 };

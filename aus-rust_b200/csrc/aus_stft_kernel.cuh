@@ -401,15 +401,15 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     };
     {
         T cum = base_lo;
-        const T dlo = (T)(16 * t) - kappa;
+        T dlo = (T)(16 * t) - kappa;                   // running (bin - centroid): no integer -> double conversion per block
 #pragma unroll 1
-        for (int i0 = 0; i0 < 16; i0 += 4) block4(17 * t + i0, 0, dlo + (T)i0, cum);       // zslot(16 t + i) = 17 t + i
+        for (int i0 = 0; i0 < 16; i0 += 4, dlo += (T)4) block4(17 * t + i0, 0, dlo, cum);   // zslot(16 t + i) = 17 t + i
         // high chunk, ascending bins hb .. hb + 15: slots hs .. hs + 14 and hs + 16 (hs + 15 is the pad slot)
         cum = base_hi;
         const int hs = zslot(hb);
-        const T dhi = (T)hb - kappa;
+        T dhi = (T)hb - kappa;
 #pragma unroll 1
-        for (int i0 = 0; i0 < 16; i0 += 4) block4(hs + i0, i0 == 12 ? 1 : 0, dhi + (T)i0, cum);
+        for (int i0 = 0; i0 < 16; i0 += 4, dhi += (T)4) block4(hs + i0, i0 == 12 ? 1 : 0, dhi, cum);
         if (t == TPF - 1) {                            // bin M/2 sits between the low and the high chunks
             const T pw = bufT[2 * zslot(M / 2) + hp];
             const T d = (T)(M / 2) - kappa;
@@ -546,8 +546,10 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
     const int h0 = zslot(M - 16 * t);
     T *const bufT = reinterpret_cast<T *>(buf);
     const int hp = hpar<T>(t);
+    // bin numbers as running floating-point values: converted from the thread index once, not per bin (I2F.F64 is slow)
+    T klo_run = (T)(16 * t), khi_run = (T)(M - 16 * t);
 #pragma unroll 1
-    for (int i0 = 0; i0 < 16; i0 += 4) {
+    for (int i0 = 0; i0 < 16; i0 += 4, klo_run += (T)4, khi_run -= (T)4) {
         Cx<T> A[4], B[4], W[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -590,7 +592,7 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
                 mlo[c] = Mth<T>::sqrt_(plo[c]);
                 mhi[c] = Mth<T>::sqrt_(phi[c]);
             }
-            const T klo = (T)(16 * t + i0), khi = (T)(M - 16 * t - i0);
+            const T klo = klo_run, khi = khi_run;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 acc.lo_sum += plo[c];

@@ -241,15 +241,15 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
     const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);
     T cum = 0;
     {
-        const T d0 = (T)(32 * t) - kappa;
-#pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += 4) {
+        T dj = (T)(32 * t) - kappa;                     // bin - centroid of the block's first bin (kept as a running value:
+#pragma unroll 1                                         //  no integer -> double conversion per bin)
+        for (int j0 = 0; j0 < 32; j0 += 4, dj += (T)4) {
             T pv[4], q[4], l[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) pv[c] = pw[c0 + j0 + c];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const T d = d0 + (T)(j0 + c);
+                const T d = dj + (T)c;
                 const T dd = d * d;
                 const T w2 = dd * pv[c];
                 d2s += w2;
