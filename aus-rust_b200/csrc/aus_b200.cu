@@ -1,9 +1,8 @@
 // aus_b200.cu -- host side of the C ABI declared in include/aus_b200.h: per-device context, twiddle/window
 // tables, feature-parameter derivation, kernel dispatch.  There is no CPU compute path in this file: every
 // entry point either launches the sm_100a kernels or returns an error.
-#include "../../include/aus_b200.h"
+#include "aus_host.cuh"
 #include <cstdlib>
-#include "aus_istft_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -14,77 +13,6 @@
 #include <string>
 #include <thread>
 #include <vector>
-
-using namespace aus;
-
-// ------------------------------------------------------------------------------------------------ errors
-static thread_local std::string g_err = "";
-static int fail(int code, const std::string &msg) {
-    g_err = msg;
-    return code;
-}
-#define CUDA_TRY(...)                                                                               \
-    do {                                                                                            \
-        cudaError_t e_ = (__VA_ARGS__);                                                             \
-        if (e_ != cudaSuccess) {                                                                    \
-            (void)cudaGetLastError(); /* un-latch, or the next launch check would report this one */ \
-            return fail(AUS_ERR_CUDA, std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_));   \
-        }                                                                                           \
-    } while (0)
-#define AUS_TRY(...)                   \
-    do {                               \
-        int r_ = (__VA_ARGS__);        \
-        if (r_ != AUS_OK) return r_;   \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------ context
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return AUS_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return fail(AUS_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-        }
-        cap = want;
-        return AUS_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct Tables {
-    void *tw2 = nullptr, *tw3 = nullptr, *twNt = nullptr, *twN = nullptr;
-    void *win2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    void *winf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // full-scale window pairs (inverse transform)
-};
-
-struct aus_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = true;
-    int sm_count = 148;
-    uint64_t launches = 0;
-    int direct_load = 0;                      // experiment knob, see aus_ctx_set_direct_load
-    uint64_t chunk_samples = 32ull << 20;     // host pipeline granularity: 32 Mi samples = 256 MB of f64
-    int rr_mode = -1;                         // forward-kernel variant: -1 auto, 0 shared-memory tail, 1 register-resident tail
-    std::map<int, Tables> tables;          // key = log2n * 2 + precision
-    void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
-    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw, normtab;
-    long long normtab_key = -1;            // (fft_size, hop, window, precision) the reciprocal-norm table was built for
-    DevBuf pin64[2], pin32[2], pout64[2], pout32[2], ppcm[2];   // double buffers of the chunked host pipeline
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-};
 
 static int log2_exact(size_t n) {
     if (n == 0 || (n & (n - 1))) return -1;
@@ -372,88 +300,19 @@ static int fill_feature_params_check(size_t N, uint32_t sr) {     // argument va
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-template <typename T, int LG, bool RR, bool FEAT> static int launch_stft_v(aus_ctx *c, const StftParams<T> &p) {
-    using C = Cfg<T, LG, RR>;
-    static bool attr_done[64] = {false};
-    auto kern = stft_kernel<T, LG, RR, FEAT>;
-    const size_t smem = FEAT ? C::smem_bytes() : C::off_log();          // the spectra-only build carries no log2 table
-    if (!attr_done[c->device & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[c->device & 63] = true;
-    }
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
-    if (occ < 1) return fail(AUS_ERR_CUDA, "stft kernel does not fit on an SM");
-    const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
-    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
-    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
-    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
-    c->launches++;
-    return AUS_OK;
-}
-#ifndef AUS_RR_F64_FEAT_MIN_LG
-#define AUS_RR_F64_FEAT_MIN_LG 14
+// The launch templates are in aus_host.cuh; each fft_size is instantiated in its own translation unit (aus_kernels.cu
+// with -DAUS_LG=n).  A development build (-DAUS_DEV_LG=n) instantiates that one size right here instead.
+#ifndef AUS_DEV_LG
+#define AUS_EXTERN_LG(LG)                                                                      \
+    extern template int launch_stft_t<double, LG>(aus_ctx *, const StftParams<double> &);      \
+    extern template int launch_stft_t<float, LG>(aus_ctx *, const StftParams<float> &);        \
+    extern template int launch_analyzer_t<double, LG>(aus_ctx *, const StftParams<double> &);  \
+    extern template int launch_analyzer_t<float, LG>(aus_ctx *, const StftParams<float> &);    \
+    extern template int launch_istft_t<double, LG>(aus_ctx *, const IstftParams<double> &);    \
+    extern template int launch_istft_t<float, LG>(aus_ctx *, const IstftParams<float> &);
+AUS_EXTERN_LG(6) AUS_EXTERN_LG(7) AUS_EXTERN_LG(8) AUS_EXTERN_LG(9) AUS_EXTERN_LG(10) AUS_EXTERN_LG(11) AUS_EXTERN_LG(12)
+AUS_EXTERN_LG(13) AUS_EXTERN_LG(14)
 #endif
-// Which forward kernel: shared-memory tail or register-resident tail (aus_stft_r.cuh).  Measured on B200 over
-// fft_size 64..16384 x {f64, f32} x {features, spectra, both} on >= 15 min inputs (tools/kbench.py, AUS_B200_RR=0|1):
-//   f32: the register-resident tail wins everywhere (features +3..32 %, spectra +18..90 %, both outputs in one launch
-//        +17..110 %);
-//   f64: both outputs +15..80 %; spectra alone +15..70 % except at fft_size 4096 / 8192 (-1..-4 %); features alone lose
-//        4..30 % up to fft_size 8192 (its CTAs are 8 warps x 255 registers against 12 x 168, and the FP64 feature pass
-//        needs the resident warps) and gain 8 % at 16384, where the shared-memory tail has 8 warps per SM as well.
-// c->rr_mode (aus_ctx_set_forward_variant / AUS_B200_RR) overrides the table for ablations.
-static bool use_rr(const aus_ctx *c, int lg, bool f32, bool feat, bool spec) {
-    if (c->rr_mode >= 0) return c->rr_mode == 1;
-    if (f32 || (feat && spec)) return true;
-    if (feat) return lg >= AUS_RR_F64_FEAT_MIN_LG;       // f64 features alone
-    return lg <= 11 || lg >= 14;                         // f64 spectra alone
-}
-template <typename T, int LG> static int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
-    if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
-        return p.raw != nullptr ? launch_stft_v<T, LG, true, true>(c, p) : launch_stft_v<T, LG, true, false>(c, p);
-    return launch_stft_v<T, LG, false, true>(c, p);
-}
-template <typename T, int LG> static int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
-    using C = CfgA<T, LG>;
-    static bool attr_done[64] = {false};
-    auto kern = analyzer_kernel<T, LG>;
-    const size_t smem = C::smem_bytes();
-    if (!attr_done[c->device & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[c->device & 63] = true;
-    }
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
-    if (occ < 1) return fail(AUS_ERR_CUDA, "analyzer kernel does not fit on an SM");
-    const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
-    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
-    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
-    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
-    c->launches++;
-    return AUS_OK;
-}
-template <typename T, int LG> static int launch_istft_t(aus_ctx *c, const IstftParams<T> &p) {
-    using C = Cfg<T, LG>;
-    static bool attr_done[64] = {false};
-    auto kern = istft_kernel<T, LG>;
-    const size_t smem = C::off_log();                                     // no log2 table in the inverse kernel
-    if (!attr_done[c->device & 63]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done[c->device & 63] = true;
-    }
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
-    if (occ < 1) return fail(AUS_ERR_CUDA, "istft kernel does not fit on an SM");
-    const unsigned long long need = (p.n_seg + C::FPB - 1) / C::FPB;
-    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
-    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
-    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
-    c->launches++;
-    return AUS_OK;
-}
 
 // AUS_DEV_LG (development builds only, e.g. -DAUS_DEV_LG=11): instantiate a single fft_size so one kernel iterates in seconds
 #ifdef AUS_DEV_LG

@@ -90,7 +90,7 @@ __host__ __device__ constexpr double w32_sin(int i) {
 
 // FP64 twiddles live in the constant bank so DFMA/DMUL read them as c[bank][offset] operands; a 64-bit literal
 // would cost two MOVs at every use.  FP32 twiddles fit a 32-bit immediate.
-__constant__ double c_w32_cos[16] = {1.0,
+static __constant__ double c_w32_cos[16] = {1.0,
                                      0.98078528040323044912618223613424, 0.92387953251128675612818318939679,
                                      0.83146961230254523707878837761791, 0.70710678118654752440084436210485,
                                      0.55557023301960222474283081394853, 0.38268343236508977172845998403040,
@@ -99,7 +99,7 @@ __constant__ double c_w32_cos[16] = {1.0,
                                      -0.55557023301960222474283081394853, -0.70710678118654752440084436210485,
                                      -0.83146961230254523707878837761791, -0.92387953251128675612818318939679,
                                      -0.98078528040323044912618223613424};
-__constant__ double c_w32_sin[16] = {0.0,
+static __constant__ double c_w32_sin[16] = {0.0,
                                      0.19509032201612826784828486847702, 0.38268343236508977172845998403040,
                                      0.55557023301960222474283081394853, 0.70710678118654752440084436210485,
                                      0.83146961230254523707878837761791, 0.92387953251128675612818318939679,
@@ -304,7 +304,7 @@ __device__ __forceinline__ bool abnormal(float) { return false; }
 template <typename T> struct Mth;
 // log2 polynomial coefficients and the exponent-conversion constant as constant-bank operands: as 64-bit literals each
 // costs two MOVs per use, which the compiler re-materialises inside the rolled per-bin loops (5 of 35 instructions per bin)
-__constant__ double c_log2_k[6] = {0.28853900817779268147,      // 1/(5 ln2)
+static __constant__ double c_log2_k[6] = {0.28853900817779268147,      // 1/(5 ln2)
                                    -0.36067376022224085184,     // -1/(4 ln2)
                                    0.48089834696298780245,      // 1/(3 ln2)
                                    -0.72134752044448170368,     // -1/(2 ln2)

@@ -1,0 +1,166 @@
+// aus_host.cuh -- host-side pieces shared by the translation units of libaus_b200.so: error state, the per-device
+// context, and the kernel launch templates.  The kernels of one fft_size live in one translation unit (aus_kernels.cu
+// compiled with -DAUS_LG=6..14) so that `make -j` builds the sizes in parallel; aus_b200.cu holds everything else.
+#pragma once
+#include "../../include/aus_b200.h"
+#include "aus_istft_kernel.cuh"
+
+#include <algorithm>
+#include <map>
+#include <string>
+
+using namespace aus;
+
+// ------------------------------------------------------------------------------------------------ errors
+inline thread_local std::string g_err = "";
+inline int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(...)                                                                               \
+    do {                                                                                            \
+        cudaError_t e_ = (__VA_ARGS__);                                                             \
+        if (e_ != cudaSuccess) {                                                                    \
+            (void)cudaGetLastError(); /* un-latch, or the next launch check would report this one */ \
+            return fail(AUS_ERR_CUDA, std::string(#__VA_ARGS__) + ": " + cudaGetErrorString(e_));   \
+        }                                                                                           \
+    } while (0)
+#define AUS_TRY(...)                   \
+    do {                               \
+        int r_ = (__VA_ARGS__);        \
+        if (r_ != AUS_OK) return r_;   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ context
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return AUS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(AUS_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return AUS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Tables {
+    void *tw2 = nullptr, *tw3 = nullptr, *twNt = nullptr, *twN = nullptr;
+    void *win2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *winf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // full-scale window pairs (inverse transform)
+};
+
+struct aus_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    int direct_load = 0;                      // experiment knob, see aus_ctx_set_direct_load
+    uint64_t chunk_samples = 32ull << 20;     // host pipeline granularity: 32 Mi samples = 256 MB of f64
+    int rr_mode = -1;                         // forward-kernel variant: -1 auto, 0 shared-memory tail, 1 register-resident tail
+    std::map<int, Tables> tables;          // key = log2n * 2 + precision
+    void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
+    DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw, normtab;
+    long long normtab_key = -1;            // (fft_size, hop, window, precision) the reciprocal-norm table was built for
+    DevBuf pin64[2], pin32[2], pout64[2], pout32[2], ppcm[2];   // double buffers of the chunked host pipeline
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+
+// ------------------------------------------------------------------------------------------------ launches
+template <typename T, int LG, bool RR, bool FEAT> int launch_stft_v(aus_ctx *c, const StftParams<T> &p) {
+    using C = Cfg<T, LG, RR>;
+    static bool attr_done[64] = {false};
+    auto kern = stft_kernel<T, LG, RR, FEAT>;
+    const size_t smem = FEAT ? C::smem_bytes() : C::off_log();          // the spectra-only build carries no log2 table
+    if (!attr_done[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 63] = true;
+    }
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+    if (occ < 1) return fail(AUS_ERR_CUDA, "stft kernel does not fit on an SM");
+    const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
+    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
+    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
+    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+#ifndef AUS_RR_F64_FEAT_MIN_LG
+#define AUS_RR_F64_FEAT_MIN_LG 14
+#endif
+// Which forward kernel: shared-memory tail or register-resident tail (aus_stft_r.cuh).  Measured on B200 over
+// fft_size 64..16384 x {f64, f32} x {features, spectra, both} on >= 15 min inputs (tools/kbench.py, AUS_B200_RR=0|1):
+//   f32: the register-resident tail wins everywhere (features +3..32 %, spectra +18..90 %, both outputs in one launch
+//        +17..110 %);
+//   f64: both outputs +15..80 %; spectra alone +15..70 % except at fft_size 4096 / 8192 (-1..-4 %); features alone lose
+//        4..30 % up to fft_size 8192 (its CTAs are 8 warps x 255 registers against 12 x 168, and the FP64 feature pass
+//        needs the resident warps) and gain 8 % at 16384, where the shared-memory tail has 8 warps per SM as well.
+// c->rr_mode (aus_ctx_set_forward_variant / AUS_B200_RR) overrides the table for ablations.
+inline bool use_rr(const aus_ctx *c, int lg, bool f32, bool feat, bool spec) {
+    if (c->rr_mode >= 0) return c->rr_mode == 1;
+    if (f32 || (feat && spec)) return true;
+    if (feat) return lg >= AUS_RR_F64_FEAT_MIN_LG;       // f64 features alone
+    return lg <= 11 || lg >= 14;                         // f64 spectra alone
+}
+template <typename T, int LG> int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
+    if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
+        return p.raw != nullptr ? launch_stft_v<T, LG, true, true>(c, p) : launch_stft_v<T, LG, true, false>(c, p);
+    return launch_stft_v<T, LG, false, true>(c, p);
+}
+template <typename T, int LG> int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
+    using C = CfgA<T, LG>;
+    static bool attr_done[64] = {false};
+    auto kern = analyzer_kernel<T, LG>;
+    const size_t smem = C::smem_bytes();
+    if (!attr_done[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 63] = true;
+    }
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+    if (occ < 1) return fail(AUS_ERR_CUDA, "analyzer kernel does not fit on an SM");
+    const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
+    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
+    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
+    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+template <typename T, int LG> int launch_istft_t(aus_ctx *c, const IstftParams<T> &p) {
+    using C = Cfg<T, LG>;
+    static bool attr_done[64] = {false};
+    auto kern = istft_kernel<T, LG>;
+    const size_t smem = C::off_log();                                     // no log2 table in the inverse kernel
+    if (!attr_done[c->device & 63]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done[c->device & 63] = true;
+    }
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+    if (occ < 1) return fail(AUS_ERR_CUDA, "istft kernel does not fit on an SM");
+    const unsigned long long need = (p.n_seg + C::FPB - 1) / C::FPB;
+    const unsigned long long cap = (unsigned long long)c->sm_count * occ;
+    const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
+    kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+

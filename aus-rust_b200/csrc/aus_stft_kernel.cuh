@@ -101,7 +101,7 @@ enum RawIdx { RAW_SM = 0, RAW_SMK, RAW_SPK, RAW_B1P, RAW_B1PK, RAW_B2P, RAW_B2PK
               RAW_ENT, RAW_SLQ, RAW_ROLL0, RAW_ROLL1, RAW_ROLL2, RAW_ROLL3, RAW_PICK0, RAW_N = RAW_PICK0 + 6 };
 
 // window.rs:26-98 evaluated for one index (used only for the short last frame of a file, fft.rs:148-159)
-__device__ __noinline__ double window_value(int wtype, double i, double L) {
+static __device__ __noinline__ double window_value(int wtype, double i, double L) {
     const double PI = 3.14159265358979323846264338327950288;
     switch (wtype) {
     case 0: return (2.0 / (L - 1.0)) * ((L - 1.0) / 2.0 - fabs(i - (L - 1.0) / 2.0));

@@ -41,8 +41,8 @@ template <int M> struct RLay {
     0.7730104533627369608109066097584698, 0.83146961230254523707878837761790576, 0.88192126434835502971275686366038835, \
     0.92387953251128675612818318939678829, 0.95694033573220886493579788698026997, 0.98078528040323044912618223613423904, \
     0.99518472667219688624483695310947992
-__constant__ double c_w64_cos[16] = {AUS_W64_COS};
-__constant__ double c_w64_sin[16] = {AUS_W64_SIN};
+static __constant__ double c_w64_cos[16] = {AUS_W64_COS};
+static __constant__ double c_w64_sin[16] = {AUS_W64_SIN};
 __host__ __device__ constexpr double w64_cos(int i) {
     constexpr double t[16] = {AUS_W64_COS};
     return t[i];
