@@ -29,7 +29,7 @@
 
 namespace aus {
 
-// RR: register-resident tail (aus_stft_r.cuh), fft_size <= 2048 only.  It wants ~230 registers in f64, so those CTAs are
+// RR: register-resident tail (aus_stft_r.cuh).  It wants ~230 registers in f64, so those CTAs are
 // 8 warps x 255 registers instead of 12 x 168; that also shrinks the shared-memory carve-out enough for the window table
 // to stay in L1 (hit rate 68 % -> 99 %).
 template <typename T, int LOG2N, bool RR = false> struct Cfg {
@@ -624,7 +624,7 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
     if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, true);
 }
 
-// register-resident variants for fft_size <= 2048, defined in aus_stft_r.cuh
+// register-resident variants, defined in aus_stft_r.cuh
 template <typename T, int LOG2N, typename C>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
                                                const Cx<T> *gsrc, Cx<T> (&v)[32]);
@@ -716,27 +716,32 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
         }
         group_sync<TPF, C::BLOCK>(grp);
 
+        const T *half2 = nullptr;                                       // second half of the next frame, still to be copied
         if constexpr (RR) {
             // the last pass, the real-FFT split and the first feature pass stay in registers (aus_stft_r.cuh)
             Cx<T> v[32];
             frame_fft_keep<T, LOG2N, C>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v);
             staged = false;
-            if (!want_feat && TPF <= 32) {
-                // spectra only, frame group inside one warp: nothing below touches the group buffer, and every thread has read its last-pass inputs, so
-                // the next frame's bulk copy starts now and overlaps the butterflies, the real-FFT split and the stores
-                const T *src2;
+            if (!want_feat) {
+                // spectra only: every thread has read its last-pass inputs, so the next frame's bulk copy starts now and
+                // overlaps the butterflies, the real-FFT split and the stores.  One warp per group: the tail works from
+                // registers and the whole frame goes.  Larger groups exchange partners through the upper half of the buffer,
+                // so only the first half of the frame goes now and the second half follows after the tail (same mbarrier).
+                const T *srcn;
                 int L2, f2 = f;
-                const bool act2 = it + 1 < iters && locate(g + stride, f2, src2, L2);
+                const bool act2 = it + 1 < iters && locate(g + stride, f2, srcn, L2);
                 const bool tma2 = act2 && L2 == N && p.tma_ok && !(p.direct && C::R1 == 32) &&
-                                  ((reinterpret_cast<uintptr_t>(src2) & 15) == 0);      // = the next iteration's use_tma
+                                  ((reinterpret_cast<uintptr_t>(srcn) & 15) == 0);      // = the next iteration's use_tma
                 fence_proxy_async();                                    // pass-1 stores (generic proxy) before the async write
                 group_sync<TPF, C::BLOCK>(grp);                         // (outside the branch: groups may share a warp)
                 if (tma2) {                                             // group-uniform
+                    constexpr uint32_t FIRST = (uint32_t)((TPF <= 32 ? N : N / 2) * sizeof(T));
                     if (t == 0) {
                         mbar_arrive_expect_tx(bar, (uint32_t)(N * sizeof(T)));
-                        tma_load_1d(buf, src2, (uint32_t)(N * sizeof(T)), bar);
+                        tma_load_1d(buf, srcn, FIRST, bar);
                     }
                     staged = true;
+                    if constexpr (TPF > 32) half2 = srcn + N / 2;
                 }
             }
             // partner exchange: by shuffles (f32; spectra-only builds, where the buffer now belongs to the next frame) or
@@ -752,6 +757,10 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
         }
         fence_proxy_async();                                            // generic accesses to buf before the next TMA write
         group_sync<TPF, C::BLOCK>(grp);
+        if constexpr (RR && TPF > 32) {
+            if (half2 != nullptr && t == 0)                             // second half of the early copy (see above)
+                tma_load_1d(reinterpret_cast<T *>(buf) + N / 2, half2, (uint32_t)((N / 2) * sizeof(T)), bar);
+        }
     }
 }
 

@@ -90,7 +90,7 @@ uint64_t aus_ctx_launch_count(const aus_ctx *ctx);
 /* input staging of the forward kernels for full, 16-byte aligned frames: 0 (default) = TMA bulk copy into the frame
  * group's shared buffer; 1 = coalesced 16-byte loads global -> registers (no shared staging).  Results are identical. */
 int aus_ctx_set_direct_load(aus_ctx *ctx, int on);
-/* forward-kernel variant for fft_size <= 2048: -1 (default) = chosen per precision / output from B200 measurements,
+/* forward-kernel variant: -1 (default) = chosen per fft_size / precision / outputs from B200 measurements,
  * 0 = shared-memory tail, 1 = register-resident tail (last FFT pass, real-FFT split and |X|^2 stay in registers; spectra
  * are stored straight from them).  Results agree to rounding (same arithmetic, different summation grouping).
  * The environment variable AUS_B200_RR=0|1 sets the initial value. */
