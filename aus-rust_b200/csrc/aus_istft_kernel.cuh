@@ -100,6 +100,12 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             } else {
                 for (int i = t; i < K; i += TPF) buf[i] = active ? row[i] : Cx<T>{(T)0, (T)0};
             }
+            // pre-twiddle factors of this thread's 16 pairs: exact table values (the first samples of a Hann-windowed
+            // signal divide by a window norm of ~1e-15, so every rounding of the pre-twiddle is amplified there), fetched
+            // while the row copy is in flight instead of inside the pre-twiddle loop
+            Cx<T> Wp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Wp[i] = ldg_cx(&p.fwd.twN[t + TPF * i]);
             if (use_tma) {
                 mbar_wait(bar, parity);
                 parity ^= 1u;
@@ -108,20 +114,24 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
 
             // ---- Hermitian pre-twiddle, in place: buf[k] <- conj(Zi[k]),
             //      Zi[k] = (Y[k] + conj Y[M-k]) + i W_N^{-k} (Y[k] - conj Y[M-k])   (fft.rs:221-229 folded in)
-#pragma unroll 4
-            for (int i = 0; i <= 16; ++i) {
+            //      The twiddles (cos, sin)(2 pi k / N) of this thread's pairs were loaded before the wait for the row (Wp).
+            static_for<0, 17>([&](auto i_) {
+                constexpr int i = decltype(i_)::value;
                 const int k = t + TPF * i;                 // pairs (k, M-k), k = 0 .. M/2
-                if (i == 16 && t != 0) break;
-                Cx<T> Yk = buf[k], Ym = buf[M - k];
-                if (k == 0) { Yk.y = (T)0; Ym.y = (T)0; }   // imaginary parts of DC / Nyquist vanish under `.re` (fft.rs:235)
-                const Cx<T> W = ldg_cx(&p.fwd.twN[k]);      // (cos, sin)(2 pi k / N)
-                const T sx = Yk.x + Ym.x, sy = Yk.y - Ym.y;
-                const T dx = Yk.x - Ym.x, dy = Yk.y + Ym.y;
-                const T ux = W.x * dx - W.y * dy;          // U = W^{-k} D, W^{-k} = c + i s
-                const T uy = W.x * dy + W.y * dx;
-                buf[k] = Cx<T>{sx - uy, -(sy + ux)};
-                if (k != 0 && k != M / 2) buf[M - k] = Cx<T>{sx + uy, sy - ux};
-            }
+                if (i < 16 || t == 0) {
+                    Cx<T> Yk = buf[k], Ym = buf[M - k];
+                    if (k == 0) { Yk.y = (T)0; Ym.y = (T)0; }   // imaginary parts of DC / Nyquist vanish under `.re` (fft.rs:235)
+                    Cx<T> W;
+                    if constexpr (i == 16) W = Cx<T>{(T)0, (T)1};               // only t == 0: k = M/2, angle pi/2
+                    else W = Wp[i];
+                    const T sx = Yk.x + Ym.x, sy = Yk.y - Ym.y;
+                    const T dx = Yk.x - Ym.x, dy = Yk.y + Ym.y;
+                    const T ux = W.x * dx - W.y * dy;      // U = W^{-k} D, W^{-k} = c + i s
+                    const T uy = W.x * dy + W.y * dx;
+                    buf[k] = Cx<T>{sx - uy, -(sy + ux)};
+                    if (k != 0 && k != M / 2) buf[M - k] = Cx<T>{sx + uy, sy - ux};
+                }
+            });
             group_sync<TPF, C::BLOCK>(grp);
 
             frame_fft<T, LOG2N>(buf, p.fwd, t, grp, /*prewindowed=*/true);     // buf: conj(z) in the Z layout
@@ -143,13 +153,15 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                 const int nprev = N - p.hop;
 #pragma unroll 1
                 for (int i0 = 0; i0 < 32; i0 += 8) {
-                    V2 prev[8];
+                    V2 prev[8], rn[8];
                     Cx<T> z[8], w[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const int n = t + TPF * (i0 + c), u0 = 2 * n;
                         prev[c] = V2{(T)0, (T)0};
+                        rn[c] = V2{(T)1, (T)1};
                         if (u0 >= ulo && u0 < uhi && u0 < nprev) prev[c] = __ldcg(reinterpret_cast<const V2 *>(outh + u0));
+                        if (u0 < p.hop) rn[c] = __ldg(reinterpret_cast<const V2 *>(p.rnorm + u0));   // with the other loads
                         z[c] = buf[padi<4>(n)];
                         w[c] = ldg_cx(&p.winf[n]);
                     }
@@ -160,9 +172,8 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                         T v0 = z[c].x * w[c].x + prev[c].x;                 // fft.rs:234-236 + overlap-add (ascending frames)
                         T v1 = -z[c].y * w[c].y + prev[c].y;
                         if (u0 < p.hop) {                                   // no later frame reaches it: fft.rs:250-258
-                            const V2 rn = __ldg(reinterpret_cast<const V2 *>(p.rnorm + u0));
-                            v0 *= rn.x;
-                            v1 *= rn.y;
+                            v0 *= rn[c].x;
+                            v1 *= rn[c].y;
                             if (v0 > vmax) vmax = v0;                       // f64::max skips NaN
                             if (v1 > vmax) vmax = v1;
                         }
