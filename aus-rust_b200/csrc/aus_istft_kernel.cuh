@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             });
             group_sync<TPF, C::BLOCK>(grp);
 
-            frame_fft<T, LOG2N>(buf, p.fwd, t, grp, /*prewindowed=*/true);     // buf: conj(z) in the Z layout
+            {
+                Cx<T> v[32];
+                frame_fft<T, LOG2N>(buf, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);     // buf: conj(z) in the Z layout
+            }
 
             // ---- window + overlap-add into the output (ascending frame order), finalise completed samples.
             //      u = offset inside the frame.  Frames h - b (b >= 1) also cover the sample iff b <= (N-1-u)/hop, frames

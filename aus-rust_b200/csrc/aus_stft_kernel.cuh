@@ -21,6 +21,9 @@
 #ifndef AUS_F64_BLOCK_R
 #define AUS_F64_BLOCK_R 256      // f64 CTA size of the register-resident path; registers are allocated per 4 warps
 #endif
+#ifndef AUS_WINDOW_PRELOAD
+#define AUS_WINDOW_PRELOAD 1     // fetch the pass-1 window values before waiting for the frame's bulk copy
+#endif
 #ifndef AUS_L2_PREFETCH
 #define AUS_L2_PREFETCH 0        // experiment: cp.async.bulk.prefetch.L2 of the next frame / row while this one is processed.
                                  // Measured on 2 h inputs: forward features -1..-6 %, spectra -4..-6 %, analyzer +1 %, irstft +-4 %
@@ -119,10 +122,9 @@ template <int SHIFT> __device__ __forceinline__ int padi(int i) { return i + (i 
 // Z'[k] = FFT_M(z')[k] in the "Z layout" (index k + (k >> 4)), where z' = 0.5 * window * z.
 template <typename T, int LOG2N>
 __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
-                                          const Cx<T> *gsrc = nullptr) {
+                                          const Cx<T> *gsrc, Cx<T> (&v)[32], bool wpre) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, R3 = C::R3, XS = C::XS;
-    Cx<T> v[32];
 
     if constexpr (M == 32) {                                  // one thread per frame: a single radix-32 pass
         static_for<0, 32>([&](auto r_) {
@@ -157,11 +159,12 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
                 } else if (prewindowed) {
 #pragma unroll
                     for (int r = 0; r < 32; ++r) v[r] = buf[lbase + r * lstride];
+                } else if (wpre) {                            // v already holds the window (loaded before the wait for the frame)
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = emul(buf[lbase + r * lstride], v[r]);
                 } else {
 #pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                        v[r] = emul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
-                    }
+                    for (int r = 0; r < 32; ++r) v[r] = emul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
                 }
             } else {
                 v[0] = buf[lbase];
@@ -627,7 +630,7 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
 // register-resident variants, defined in aus_stft_r.cuh
 template <typename T, int LOG2N, typename C>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
-                                               const Cx<T> *gsrc, Cx<T> (&v)[32]);
+                                               const Cx<T> *gsrc, Cx<T> (&v)[32], bool wpre);
 template <typename T, int LOG2N, typename C, bool SHFL, bool FEAT>
 __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double *scratch, const double2 *logtab,
                                              const StftParams<T> &p, unsigned long long g, bool active, int t, int grp);
@@ -710,6 +713,18 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
                 bufr[i] = x;
             }
         }
+        // the window values this thread multiplies in pass 1 do not depend on the frame: fetch them (L1 / L2) while the bulk
+        // copy is still in flight, into the registers that receive the frame afterwards
+        Cx<T> v[32];
+        bool wpre = false;
+        // (only where registers allow: the f64 spectra-only build, +3 %; with features the 128 live registers spill)
+        if constexpr (C::R1 == 32 && AUS_WINDOW_PRELOAD && RR && !FEAT && sizeof(T) == 8) {
+            if (!prewindowed && !direct) {                             // group-uniform
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = ldg_cx(p.win2 + t + r * TPF);
+                wpre = true;
+            }
+        }
         if (use_tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
@@ -719,8 +734,7 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
         const T *half2 = nullptr;                                       // second half of the next frame, still to be copied
         if constexpr (RR) {
             // the last pass, the real-FFT split and the first feature pass stay in registers (aus_stft_r.cuh)
-            Cx<T> v[32];
-            frame_fft_keep<T, LOG2N, C>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v);
+            frame_fft_keep<T, LOG2N, C>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v, wpre);
             staged = false;
             if (!want_feat) {
                 // spectra only: every thread has read its last-pass inputs, so the next frame's bulk copy starts now and
@@ -752,7 +766,7 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
                 frame_tail_r<T, LOG2N, C, (sizeof(T) == 4 && TPF <= 32), true>(v, buf, scratch, logtab, p, g, active, t, grp);
             }
         } else {
-            frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr);
+            frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v, wpre);
             frame_tail_s<T, LOG2N>(buf, scratch, logtab, p, g, active, t, grp, want_feat);
         }
         fence_proxy_async();                                            // generic accesses to buf before the next TMA write

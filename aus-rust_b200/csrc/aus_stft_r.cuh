@@ -68,7 +68,7 @@ template <int W> __device__ __forceinline__ Cx<float> shfl_cx(Cx<float> a, int s
 // finished reading buf (which may be overwritten).
 template <typename T, int LOG2N, typename C>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
-                                               const Cx<T> *gsrc, Cx<T> (&v)[32]) {
+                                               const Cx<T> *gsrc, Cx<T> (&v)[32], bool wpre) {
     constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, R3 = C::R3, XS = C::XS;
 
     if constexpr (M == 32) {                                  // one thread per frame: a single radix-32 pass
@@ -95,6 +95,9 @@ __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &
                 } else if (prewindowed) {
 #pragma unroll
                     for (int r = 0; r < 32; ++r) v[r] = buf[lbase + r * lstride];
+                } else if (wpre) {                            // v already holds the window (loaded before the wait for the frame)
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = emul(buf[lbase + r * lstride], v[r]);
                 } else {
 #pragma unroll
                     for (int r = 0; r < 32; ++r) v[r] = emul(buf[lbase + r * lstride], ldg_cx(tab + r * tstride));
