@@ -573,3 +573,34 @@ def test_single_feature_wrappers_generic_parameters(ctx, aus, orc):
         assert got[r, 0] == pytest.approx(orc.spectral_centroid(M[r], f), rel=RTOL64)
         assert got[r, 7] == orc.spectral_roll_off_point(M[r], f, 0.25) and got[r, 8] == orc.spectral_roll_off_point(M[r], f, 0.9)
         assert got[r, 9] == pytest.approx(orc.spectral_slope_region(M[r], f, 105.0, 852.0, 44100), rel=1e-7)
+
+
+@pytest.mark.parametrize("fft_size,hop", [(1024, 256), (2048, 512), (4096, 1024)])
+def test_direct_load_knob_is_bit_identical(ctx, orc, fft_size, hop):
+    """aus_ctx_set_direct_load: TMA staging vs global->register loads of pass 1 give identical bits (same arithmetic),
+    for every forward variant, features and spectra."""
+    import torch
+    ctx.use_torch_stream()
+    x = orc.synth_signal(9 * fft_size + 5, SR, seed=41, file_id=fft_size)
+    d = torch.from_numpy(x).cuda()
+    F, K = orc.num_frames(x.size, fft_size, hop), fft_size // 2 + 1
+    res = {}
+    try:
+        for variant in (0, 1):
+            ctx.set_forward_variant(variant)
+            for direct in (False, True):
+                ctx.set_direct_load(direct)
+                feat = torch.empty((F, 14), dtype=torch.float64, device="cuda")
+                spec = torch.empty((F, K, 2), dtype=torch.float64, device="cuda")
+                spec_only = torch.empty((F, K, 2), dtype=torch.float64, device="cuda")
+                ctx.stft_features_batch_dev(d, [0], [x.size], fft_size, hop, orc.HANNING, SR, "f64", feat, spec)
+                ctx.stft_features_batch_dev(d, [0], [x.size], fft_size, hop, orc.HANNING, SR, "f64", None, spec_only)
+                torch.cuda.synchronize()
+                res[(variant, direct)] = (feat.cpu().numpy(), spec.cpu().numpy(), spec_only.cpu().numpy())
+            for a, b in zip(res[(variant, False)], res[(variant, True)]):
+                assert np.array_equal(a, b, equal_nan=True)
+        assert_spectra(res[(1, True)][2][..., 0] + 1j * res[(1, True)][2][..., 1], orc.rstft(x, fft_size, hop, orc.HANNING),
+                       RTOL64, "direct load, spectra only")
+    finally:
+        ctx.set_direct_load(False)
+        ctx.set_forward_variant(-1)
