@@ -374,12 +374,27 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
                 const T *pl = pw + 33 * c;                 // no stored running sums: walk the chunk's powers (a warp-
                                                            // cooperative scan of the chunk measured no faster)
                 T run = bs;
-                int j = 0;
+                int j = n;                                 // first bin of the chunk whose running sum is not below th
+                // eight bins per trip: the loads go out together, so the shared-memory latency is paid four times per
+                // chunk instead of thirty-two (the sum itself stays sequential, as in the reference)
 #pragma unroll 1
-                for (; j < n; ++j) {
-                    const T nx = run + pl[j];
-                    if (!(nx < th)) { c_at = nx; break; }
-                    run = nx;
+                for (int j0 = 0; j0 < 32 && j == n; j0 += 8) {
+                    T x[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[e] = pl[j0 + e];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if (j == n) {
+                            const T nx = run + x[e];
+                            if (!(nx < th)) { c_at = nx; j = j0 + e; }
+                            else run = nx;
+                        }
+                    }
+                }
+                if (j == n && n == 33) {                   // bin M closes the last chunk
+                    const T nx = run + pl[32];
+                    if (!(nx < th)) { c_at = nx; j = 32; }
+                    else run = nx;
                 }
                 res = 32 * c + j;
                 if (j == n) amb = c < TPF - 1;
