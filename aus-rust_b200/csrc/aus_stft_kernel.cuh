@@ -21,6 +21,9 @@
 #ifndef AUS_F64_BLOCK_R
 #define AUS_F64_BLOCK_R 256      // f64 CTA size of the register-resident path; registers are allocated per 4 warps
 #endif
+#ifndef AUS_F32_MINB
+#define AUS_F32_MINB 2              // f32 CTAs (256 threads) per SM
+#endif
 #ifndef AUS_WINDOW_PRELOAD
 #define AUS_WINDOW_PRELOAD 1     // fetch the pass-1 window values before waiting for the frame's bulk copy
 #endif
@@ -46,7 +49,7 @@ template <typename T, int LOG2N, bool RR = false> struct Cfg {
     // f64: 12 warps x 168 registers per SM (3 per scheduler) when the group buffers fit; f32: 2 CTAs x 8 warps x 128 regs
     static constexpr int BLOCK = (sizeof(T) == 8 && RR) ? AUS_F64_BLOCK_R
                                  : (sizeof(T) == 8 && TPF >= 16 && TPF <= 128) ? 384 : 256;
-    static constexpr int MINB = (sizeof(T) == 4) ? 2 : 1;
+    static constexpr int MINB = (sizeof(T) == 4) ? AUS_F32_MINB : 1;
     static constexpr int FPB = BLOCK / TPF;                  // frame groups per CTA
     // register budget of the forward kernel: all 64 Ki registers of the SM split over the resident warps (allocation
     // granularity: 8 registers per thread).  __maxnreg__ instead of __launch_bounds__, which rounds the CTA up to 128 threads.
