@@ -21,6 +21,9 @@
 #ifndef AUS_F64_BLOCK_R
 #define AUS_F64_BLOCK_R 256      // f64 CTA size of the register-resident path; registers are allocated per 4 warps
 #endif
+#ifndef AUS_PASSB_W
+#define AUS_PASSB_W 4            // bins per block of the second feature pass (shared-memory tail)
+#endif
 #ifndef AUS_F32_MINB
 #define AUS_F32_MINB 2              // f32 CTAs (256 threads) per SM
 #endif
@@ -381,12 +384,13 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     T *const bufT = reinterpret_cast<T *>(buf);
     const int hp = hpar<T>(t);                        // this thread's power half; running sum in the other one
     const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);   // this lane's bank column
-    auto block4 = [&](int s0, int skip, T d0, T &cum) {
-        T pw[4], q[4], l[4];
+    constexpr int PW = AUS_PASSB_W;                   // bins per block: that many independent log2 chains in flight
+    auto blockw = [&](int s0, int skip, T d0, T &cum) {
+        T pw[PW], q[PW], l[PW];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) pw[c] = bufT[2 * (s0 + c + (c == 3 ? skip : 0)) + hp];
+        for (int c = 0; c < PW; ++c) pw[c] = bufT[2 * (s0 + c + (c == PW - 1 ? skip : 0)) + hp];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PW; ++c) {
             const T d = d0 + (T)c;
             const T dd = d * d;
             const T w2 = dd * pw[c];
@@ -396,26 +400,26 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
             q[c] = pw[c] * inv_p;                     // make_spectrum_pmf, s_a_t.rs:284-290
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
+        for (int c = 0; c < PW; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PW; ++c) {
             ent += q[c] * l[c];
             slq += l[c];
             cum += pw[c];
-            bufT[2 * (s0 + c + (c == 3 ? skip : 0)) + 1 - hp] = cum;
+            bufT[2 * (s0 + c + (c == PW - 1 ? skip : 0)) + 1 - hp] = cum;
         }
     };
     {
         T cum = base_lo;
         T dlo = (T)(16 * t) - kappa;                   // running (bin - centroid): no integer -> double conversion per block
 #pragma unroll 1
-        for (int i0 = 0; i0 < 16; i0 += 4, dlo += (T)4) block4(17 * t + i0, 0, dlo, cum);   // zslot(16 t + i) = 17 t + i
+        for (int i0 = 0; i0 < 16; i0 += PW, dlo += (T)PW) blockw(17 * t + i0, 0, dlo, cum);   // zslot(16 t + i) = 17 t + i
         // high chunk, ascending bins hb .. hb + 15: slots hs .. hs + 14 and hs + 16 (hs + 15 is the pad slot)
         cum = base_hi;
         const int hs = zslot(hb);
         T dhi = (T)hb - kappa;
 #pragma unroll 1
-        for (int i0 = 0; i0 < 16; i0 += 4, dhi += (T)4) block4(hs + i0, i0 == 12 ? 1 : 0, dhi, cum);
+        for (int i0 = 0; i0 < 16; i0 += PW, dhi += (T)PW) blockw(hs + i0, i0 == 16 - PW ? 1 : 0, dhi, cum);
         if (t == TPF - 1) {                            // bin M/2 sits between the low and the high chunks
             const T pw = bufT[2 * zslot(M / 2) + hp];
             const T d = (T)(M / 2) - kappa;
