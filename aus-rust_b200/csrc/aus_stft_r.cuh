@@ -66,7 +66,7 @@ template <int W> __device__ __forceinline__ Cx<float> shfl_cx(Cx<float> a, int s
 // Forward packed FFT like frame_fft(), but the last pass stays in registers: on return natural output s of
 // thread j's final radix-32 butterfly, Z'[j + TPF s], is v[bitrev(s, 5)], and every thread of the group has
 // finished reading buf (which may be overwritten).
-template <typename T, int LOG2N, typename C>
+template <typename T, int LOG2N, typename C, bool UNR>
 __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
                                                const Cx<T> *gsrc, Cx<T> (&v)[32], bool wpre) {
     constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, R3 = C::R3, XS = C::XS;
@@ -86,8 +86,7 @@ __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &
         const Cx<T> *tab = p.win2 + j;
         int tstride = TPF;
         int sbase = 33 * j, sstride = 1;
-#pragma unroll 1
-        for (int pass = 0; pass < p.npass; ++pass) {
+        auto one_pass = [&](int pass) {
             if (pass == 0) {
                 if (gsrc != nullptr) {
 #pragma unroll
@@ -125,6 +124,15 @@ __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &
                 sbase = b + (b >> 5);
                 sstride = 33;
             }
+        };
+        if constexpr (UNR) {
+            // two copies of the pass body with compile-time strides save the per-load address arithmetic of the shared
+            // (rolled) body; the f64 feature kernels keep the rolled body (AUS_UNROLL_PASSES)
+            one_pass(0);
+            one_pass(1);
+        } else {
+#pragma unroll 1
+            for (int pass = 0; pass < p.npass; ++pass) one_pass(pass);
         }
         if constexpr (C::THREE) {
             // ---- pass 3 (M > 1024): radix R3, Ns = 1024, B3 = 32 / R3 butterflies per thread, kept in registers: butterfly
