@@ -299,6 +299,57 @@ __device__ __forceinline__ void group_allreduce(double (&v)[NV], double *scratch
     }
 }
 
+// The same collectives in the arithmetic type of the kernel (R = float in f32 mode: half the shuffles of the double
+// versions and no conversions; f32 results are compared at 1e-4) -- used by the transposed-layout feature pass.
+template <int TPF, int BLOCK, int NV, typename R>
+__device__ __forceinline__ void group_allreduce_t(R (&v)[NV], double *scratch_d, int t, int grp) {
+    constexpr int W = TPF < 32 ? TPF : 32;
+#pragma unroll
+    for (int off = W / 2; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+    if constexpr (TPF > 32) {
+        R *scratch = reinterpret_cast<R *>(scratch_d);
+        constexpr int NW = TPF / 32;
+        const int w = t >> 5;
+        if ((t & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) scratch[w * NV + i] = v[i];
+        }
+        group_sync<TPF, BLOCK>(grp);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            R s = scratch[i];
+            for (int ww = 1; ww < NW; ++ww) s += scratch[ww * NV + i];
+            v[i] = s;
+        }
+        group_sync<TPF, BLOCK>(grp);
+    }
+}
+template <int TPF, int BLOCK, typename R>
+__device__ __forceinline__ void group_inclusive_scan1(R &a, double *scratch_d, int t, int grp) {
+    constexpr int W = TPF < 32 ? TPF : 32;
+    const int l = t & (W - 1);
+#pragma unroll
+    for (int off = 1; off < W; off <<= 1) {
+        const R ua = __shfl_up_sync(0xffffffffu, a, off, W);
+        if (l >= off) a += ua;
+    }
+    if constexpr (TPF > 32) {
+        R *scratch = reinterpret_cast<R *>(scratch_d);
+        constexpr int NW = TPF / 32;
+        const int w = t >> 5;
+        if ((t & 31) == 31) scratch[w] = a;
+        group_sync<TPF, BLOCK>(grp);
+        R pa = (R)0;
+        for (int ww = 0; ww < NW; ++ww)
+            if (ww < w) pa += scratch[ww];
+        a += pa;
+        group_sync<TPF, BLOCK>(grp);
+    }
+}
+
 // Inclusive prefix sum over the group's threads (ascending t) of two doubles at once.
 template <int TPF, int BLOCK>
 __device__ __forceinline__ void group_inclusive_scan2(double &a, double &b, double *scratch, int t, int grp) {

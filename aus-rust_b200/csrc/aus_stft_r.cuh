@@ -236,10 +236,9 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
         if (b < p.r_hi[0]) { b1p += pv; b1pk += pk; }
         if (b >= p.r_lo[1]) { b2p += pv; b2pk += pk; }
     }
-    double r[8] = {(double)s_m, (double)s_mk, (double)s_pk, (double)b1p, (double)b1pk, (double)b2p, (double)b2pk,
-                   (double)p_part};
-    group_allreduce<TPF, C::BLOCK, 8>(r, scratch, t, grp);
-    const double S_m = r[0], S_mk = r[1], P = r[7];
+    T r[8] = {s_m, s_mk, s_pk, b1p, b1pk, b2p, b2pk, p_part};       // combined in the kernel's arithmetic type
+    group_allreduce_t<TPF, C::BLOCK, 8, T>(r, scratch, t, grp);
+    const double S_m = (double)r[0], S_mk = (double)r[1], P = (double)r[7];
 
     // central moments about the (magnitude-weighted) centroid in bins; entropy and log-mean from q = p / P; the
     // chunk-local running sum goes to the second region (global running sum = chunk base + local, see below)
@@ -305,14 +304,14 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
             slq += l;
         }
     }
-    double q[5] = {(double)d2s, (double)d3s, (double)d4s, (double)ent, (double)slq};
-    group_allreduce<TPF, C::BLOCK, 5>(q, scratch, t, grp);
+    T q[5] = {d2s, d3s, d4s, ent, slq};
+    group_allreduce_t<TPF, C::BLOCK, 5, T>(q, scratch, t, grp);
 
     // running sum at the end of each chunk (bin order), published in the chunk's pad slot of the power region (the last
     // chunk's pad slot holds bin M; its end value is the total and never needed)
-    double inc = (double)cum, dummy = 0.0;
-    group_inclusive_scan2<TPF, C::BLOCK>(inc, dummy, scratch, t, grp);
-    if (t < TPF - 1) pw[c0 + 32] = (T)inc;
+    T inc = cum;
+    group_inclusive_scan1<TPF, C::BLOCK, T>(inc, scratch, t, grp);
+    if (t < TPF - 1) pw[c0 + 32] = inc;
     group_sync<TPF, C::BLOCK>(grp);                      // chunk ends and local running sums visible to the searching threads
 
     // roll-off (s_a_t.rs:137-145): index = number of bins whose inclusive running sum is below theta * P; one thread per
@@ -417,10 +416,11 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
 #pragma unroll 1
         for (int qq = t; qq < 6; qq += TPF) rec[RAW_PICK0 + qq] = (double)pw[pslot<M>(p.pick[qq])];
         if (t == 0) {
-            rec[RAW_SM] = r[0]; rec[RAW_SMK] = r[1]; rec[RAW_SPK] = r[2];
-            rec[RAW_B1P] = r[3]; rec[RAW_B1PK] = r[4]; rec[RAW_B2P] = r[5]; rec[RAW_B2PK] = r[6];
+            rec[RAW_SM] = (double)r[0]; rec[RAW_SMK] = (double)r[1]; rec[RAW_SPK] = (double)r[2];
+            rec[RAW_B1P] = (double)r[3]; rec[RAW_B1PK] = (double)r[4]; rec[RAW_B2P] = (double)r[5]; rec[RAW_B2PK] = (double)r[6];
             rec[RAW_P] = P;
-            rec[RAW_D2] = q[0]; rec[RAW_D3] = q[1]; rec[RAW_D4] = q[2]; rec[RAW_ENT] = q[3]; rec[RAW_SLQ] = q[4];
+            rec[RAW_D2] = (double)q[0]; rec[RAW_D3] = (double)q[1]; rec[RAW_D4] = (double)q[2]; rec[RAW_ENT] = (double)q[3];
+            rec[RAW_SLQ] = (double)q[4];
         }
     }
 }
