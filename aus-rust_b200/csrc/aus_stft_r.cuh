@@ -245,9 +245,11 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
     const T kappa = (T)(S_mk / S_m);
     const T inv_p = (T)(1.0 / P);
     T d2s = 0, d3s = 0, d4s = 0, ent = 0, slq = 0;
-    const unsigned gpmin = group_min_u32<TPF, C::BLOCK>(pmin, scratch, t, grp);
-    const bool badq = sizeof(T) == 8 && (!power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) ||
-                                         abnormal((T)(power_from_hi<T>(gpmin) * inv_p)));
+    bool badq = false;                                   // (f32 uses lg2.approx, which handles every argument)
+    if constexpr (sizeof(T) == 8) {
+        const unsigned gpmin = group_min_u32<TPF, C::BLOCK>(pmin, scratch, t, grp);
+        badq = !power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) || abnormal((T)(power_from_hi<T>(gpmin) * inv_p));
+    }
     const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);
     T cum = 0;
     {
@@ -521,7 +523,7 @@ __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double 
                 phi[c] = Xhi[c].x * Xhi[c].x + Xhi[c].y * Xhi[c].y;
                 pw[pslot_lt(k)] = plo[c];
                 pw[(i0 + c == 0) ? pslot<M>(M - k) : pslot_lt(M - k)] = phi[c];   // only k = 0 pairs with bin M
-                pmin = min(pmin, min(power_hi(plo[c]), power_hi(phi[c])));
+                if constexpr (sizeof(T) == 8) pmin = min(pmin, min(power_hi(plo[c]), power_hi(phi[c])));
                 mlo[c] = Mth<T>::sqrt_(plo[c]);
                 mhi[c] = Mth<T>::sqrt_(phi[c]);
             }
@@ -611,7 +613,7 @@ __global__ void __maxnreg__((CfgA<T, LOG2N>::MAXREG)) analyzer_kernel(const Stft
             const T m = mv[s];
             const T pv = m * m;                            // make_power_spectrum, s_a_t.rs:273-279
             pw[pslot_lt(t + TPF * s)] = pv;
-            pmin = min(pmin, power_hi(pv));
+            if constexpr (sizeof(T) == 8) pmin = min(pmin, power_hi(pv));
             const T cs = (T)(TPF * s);
             s_m += m;
             c_m += m * cs;
