@@ -22,9 +22,10 @@
 #define AUS_F64_BLOCK_R 256      // f64 CTA size of the register-resident path; registers are allocated per 4 warps
 #endif
 #ifndef AUS_UNROLL_PASSES
-// register-resident kernels: two copies of the radix-32 pass body with compile-time strides instead of one rolled loop.
-// Measured at fft 2048: f32 +7 % (features) / +9 % (spectra), f64 spectra-only +10 %, f64 with features -1.4 %.
-#define AUS_UNROLL_PASSES(T, FEAT) (sizeof(T) == 4 || !(FEAT))
+// register-resident kernels: two copies of the radix-32 pass body with compile-time strides instead of one rolled loop
+// (saves the per-load address arithmetic).  Measured at fft 2048: f32 +7 % (features) / +9 % (spectra), f64 spectra-only
+// +10 %, f64 both outputs +8 %; the 12-warp shared-memory-tail kernel keeps the rolled body (-1.4 % unrolled).
+#define AUS_UNROLL_PASSES 1
 #endif
 #ifndef AUS_PASSB_W
 #define AUS_PASSB_W 4            // bins per block of the second feature pass (shared-memory tail)
@@ -746,7 +747,7 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
         const T *half2 = nullptr;                                       // second half of the next frame, still to be copied
         if constexpr (RR) {
             // the last pass, the real-FFT split and the first feature pass stay in registers (aus_stft_r.cuh)
-            frame_fft_keep<T, LOG2N, C, AUS_UNROLL_PASSES(T, FEAT)>(buf, p, t, grp, prewindowed,
+            frame_fft_keep<T, LOG2N, C, (AUS_UNROLL_PASSES != 0)>(buf, p, t, grp, prewindowed,
                                                                     direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v, wpre);
             staged = false;
             if (!want_feat) {

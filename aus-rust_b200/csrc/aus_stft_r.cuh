@@ -127,7 +127,7 @@ __device__ __forceinline__ void frame_fft_keep(Cx<T> *buf, const StftParams<T> &
         };
         if constexpr (UNR) {
             // two copies of the pass body with compile-time strides save the per-load address arithmetic of the shared
-            // (rolled) body; the f64 feature kernels keep the rolled body (AUS_UNROLL_PASSES)
+            // (rolled) body (AUS_UNROLL_PASSES)
             one_pass(0);
             one_pass(1);
         } else {
