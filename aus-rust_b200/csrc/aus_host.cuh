@@ -101,22 +101,18 @@ template <typename T, int LG, bool RR, bool FEAT> int launch_stft_v(aus_ctx *c, 
     c->launches++;
     return AUS_OK;
 }
-#ifndef AUS_RR_F64_FEAT_MIN_LG
-#define AUS_RR_F64_FEAT_MIN_LG 14
-#endif
 // Which forward kernel: shared-memory tail or register-resident tail (aus_stft_r.cuh).  Measured on B200 over
-// fft_size 64..16384 x {f64, f32} x {features, spectra, both} on >= 15 min inputs (tools/kbench.py, AUS_B200_RR=0|1):
+// fft_size 64..16384 x {f64, f32} x {features, spectra, both} on 0.5-2 h inputs (tools/kbench.py, AUS_B200_RR=0|1):
 //   f32: the register-resident tail wins everywhere (features +3..32 %, spectra +18..90 %, both outputs in one launch
 //        +17..110 %);
-//   f64: both outputs +15..80 %; spectra alone +15..70 % (fft_size 8192: +-0); features alone lose
-//        4..30 % up to fft_size 8192 (its CTAs are 8 warps x 255 registers against 12 x 168, and the FP64 feature pass
-//        needs the resident warps) and gain 8 % at 16384, where the shared-memory tail has 8 warps per SM as well.
+//   f64: both outputs +15..80 %; spectra alone +15..70 % (fft_size 8192: +-0); features alone +4..35 % up to fft_size 512
+//        and +8 % at 16384, but -3..-5 % at 1024..8192 (its CTAs are 8 warps x 255 registers against 12 x 168 there,
+//        and the FP64 feature pass needs the resident warps).
 // c->rr_mode (aus_ctx_set_forward_variant / AUS_B200_RR) overrides the table for ablations.
 inline bool use_rr(const aus_ctx *c, int lg, bool f32, bool feat, bool spec) {
     if (c->rr_mode >= 0) return c->rr_mode == 1;
-    if (f32 || (feat && spec)) return true;
-    if (feat) return lg >= AUS_RR_F64_FEAT_MIN_LG;       // f64 features alone
-    return true;                                         // f64 spectra alone
+    if (f32 || !feat || spec) return true;
+    return lg <= 9 || lg >= 14;                          // f64 features alone
 }
 template <typename T, int LG> int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
     if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
