@@ -1006,6 +1006,7 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     p.file_out_off = dp[4];
     p.file_max_bits = (unsigned long long *)c->misc.p;
     p.n_seg = nseg;
+    p.total_rows = F;
     p.hop = (int)hop;
     p.hop_magic = hop == 1 ? 0xffffffffu : (unsigned)((1ull << 32) / hop + 1);   // exact for x < 2^15 (hop == 1: see kernel)
     p.halo = (int)halo;

@@ -25,6 +25,7 @@ template <typename T> struct IstftParams {
     const unsigned long long *file_out_off;  // [n_files] first output sample of each file
     unsigned long long *file_max_bits;       // [n_files] bit pattern of max(out, 0.0) as f64 (fft.rs:255-258)
     unsigned long long n_seg;
+    unsigned long long total_rows;           // rows of `spec` (f32: the array's last row is not over-read)
     int hop;
     unsigned hop_magic;                      // floor(2^32 / hop) + 1: x / hop == umulhi(x, hop_magic) for x < 2^15
     const T *rnorm;                          // [hop] reciprocal steady-state window norm (fast path)
@@ -89,17 +90,30 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             if (active && t == 0 && h + 1 < b && ((K * sizeof(Cx<T>)) % 16 == 0) && p.tma_ok)
                 prefetch_l2(row + K, (uint32_t)(K * sizeof(Cx<T>)));        // next frame of this segment -> L2
 #endif
-            // ---- stage the K bins of this frame (TMA bulk copy when the row is 16-byte sized and aligned)
-            const bool use_tma = active && p.tma_ok && ((K * sizeof(Cx<T>)) % 16 == 0) &&
-                                 ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+            // ---- stage the K bins of this frame with a TMA bulk copy.  f64 rows (K x 16 bytes) are 16-byte sized and aligned.
+            //      f32 rows are K x 8 = 8 (mod 16) bytes, so every second row starts 8 bytes into a 16-byte unit: the copy
+            //      takes the enclosing 16-byte aligned range (one extra element before or after the row; never past the end of
+            //      the array: its last row goes the cooperative way) and the frame then lives one element further (`sh`).
+            constexpr bool ROW16 = (K * sizeof(Cx<T>)) % 16 == 0;
+            const uintptr_t ra = reinterpret_cast<uintptr_t>(row);
+            int sh = 0;
+            bool use_tma = active && p.tma_ok;
+            if constexpr (ROW16) {
+                use_tma = use_tma && (ra & 15) == 0;
+            } else {
+                use_tma = use_tma && gfirst + (unsigned long long)h + 1 < p.total_rows;
+                if (use_tma) sh = (int)((ra & 15) >> 3);
+            }
+            constexpr uint32_t ROWB = (uint32_t)((K * sizeof(Cx<T>) + 15) & ~(size_t)15);     // f32: 8208 for either alignment
             if (use_tma) {
                 if (t == 0) {
-                    mbar_arrive_expect_tx(bar, (uint32_t)(K * sizeof(Cx<T>)));
-                    tma_load_1d(buf, row, (uint32_t)(K * sizeof(Cx<T>)), bar);
+                    mbar_arrive_expect_tx(bar, ROWB);
+                    tma_load_1d(buf, reinterpret_cast<const void *>(ra & ~(uintptr_t)15), ROWB, bar);
                 }
             } else {
                 for (int i = t; i < K; i += TPF) buf[i] = active ? row[i] : Cx<T>{(T)0, (T)0};
             }
+            Cx<T> *const fb = buf + sh;                    // the frame (and everything derived from it below)
             // pre-twiddle factors of this thread's 16 pairs: exact table values (the first samples of a Hann-windowed
             // signal divide by a window norm of ~1e-15, so every rounding of the pre-twiddle is amplified there), fetched
             // while the row copy is in flight instead of inside the pre-twiddle loop
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                 constexpr int i = decltype(i_)::value;
                 const int k = t + TPF * i;                 // pairs (k, M-k), k = 0 .. M/2
                 if (i < 16 || t == 0) {
-                    Cx<T> Yk = buf[k], Ym = buf[M - k];
+                    Cx<T> Yk = fb[k], Ym = fb[M - k];
                     if (k == 0) { Yk.y = (T)0; Ym.y = (T)0; }   // imaginary parts of DC / Nyquist vanish under `.re` (fft.rs:235)
                     Cx<T> W;
                     if constexpr (i == 16) W = Cx<T>{(T)0, (T)1};               // only t == 0: k = M/2, angle pi/2
@@ -128,15 +142,15 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                     const T dx = Yk.x - Ym.x, dy = Yk.y + Ym.y;
                     const T ux = W.x * dx - W.y * dy;      // U = W^{-k} D, W^{-k} = c + i s
                     const T uy = W.x * dy + W.y * dx;
-                    buf[k] = Cx<T>{sx - uy, -(sy + ux)};
-                    if (k != 0 && k != M / 2) buf[M - k] = Cx<T>{sx + uy, sy - ux};
+                    fb[k] = Cx<T>{sx - uy, -(sy + ux)};
+                    if (k != 0 && k != M / 2) fb[M - k] = Cx<T>{sx + uy, sy - ux};
                 }
             });
             group_sync<TPF, C::BLOCK>(grp);
 
             {
                 Cx<T> v[32];
-                frame_fft<T, LOG2N>(buf, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);     // buf: conj(z) in the Z layout
+                frame_fft<T, LOG2N>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);     // buf: conj(z) in the Z layout
             }
 
             // ---- window + overlap-add into the output (ascending frame order), finalise completed samples.
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                         rn[c] = V2{(T)1, (T)1};
                         if (u0 >= ulo && u0 < uhi && u0 < nprev) prev[c] = __ldcg(reinterpret_cast<const V2 *>(outh + u0));
                         if (u0 < p.hop) rn[c] = __ldg(reinterpret_cast<const V2 *>(p.rnorm + u0));   // with the other loads
-                        z[c] = buf[padi<4>(n)];
+                        z[c] = fb[padi<4>(n)];
                         w[c] = ldg_cx(&p.winf[n]);
                     }
 #pragma unroll
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         const int n = t + TPF * (i0 + c);
-                        z[c] = buf[padi<4>(n)];
+                        z[c] = fb[padi<4>(n)];
                         w[c] = ldg_cx(&p.fwd.win2[n]);
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
