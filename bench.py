@@ -122,7 +122,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    secs = 120.0                                  # bounded sample per step: 2 min of audio = 10 332 frames
+    secs = 300.0                                  # bounded sample per step: 5 min of audio = 25 836 frames, ~1.5 s
     for _ in range(args.warmup):
         cpu_port_rate(10.0, cores, 0)
     t0 = time.perf_counter()
@@ -311,10 +311,10 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu:
-            r0, F0, dt0 = cpu_port_rate(600.0, cores, 0)
-            r1, F1, dt1 = cpu_port_rate(600.0, cores, 1)
+            r0, F0, dt0 = cpu_port_rate(3600.0, cores, 0)                   # one of the workload's 1-hour files: ~15-20 s
+            r1, F1, dt1 = cpu_port_rate(3600.0, cores, 1)
             cpu = {"value": r0, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": f"10 min synthetic mono 44.1 kHz ({F0} frames), fft 2048 hop 512 Hann, C port of mp.rs structure "
+                   "sample": f"one 1-hour synthetic mono 44.1 kHz file ({F0} frames), fft 2048 hop 512 Hann, C port of mp.rs structure "
                              f"(serial rstft + atan2 polar, analyzer on {cores} threads), {dt0:.1f} s",
                    "all_stages_parallel_value": r1}
         print(json.dumps({
@@ -335,7 +335,7 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src, "kernel": "stft_kernel<double, 11, 0>" if prec == "f64" else "stft_kernel<float, 11, 1>",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "fused f64 path is co-limited by the FP64 pipe, issue slots and the L1/shared data pipe, not by HBM "
-                                 "(DESIGN.md section 5); the spectra-writing kernel of the same path runs at ~59 % (profiles/)"},
+                                 "(DESIGN.md section 5); the spectra-writing kernel of the same path (rstft, spectra out) runs at ~73 % (profiles/r1s2_extra_configs.jsonl)"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }))
