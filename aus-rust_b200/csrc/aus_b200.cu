@@ -672,12 +672,27 @@ static int check_common(aus_ctx *c, size_t N, size_t hop, int wtype, int precisi
     return AUS_OK;
 }
 
+// device pointers: reals need the alignment of their type, complex spectra that of a (re, im) pair (the kernels move a
+// bin as one 8- or 16-byte unit); anything stricter (16-byte rows for the bulk copies) is decided per row in the kernels
+static int check_dev_align(const void *p, int precision, bool cx, const char *name) {
+    const uintptr_t a = (precision == AUS_F64 ? 8u : 4u) * (cx ? 2u : 1u);
+    if (p && (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0) {
+        char msg[96];
+        snprintf(msg, sizeof msg, "%s must be %u-byte aligned", name, (unsigned)a);
+        return fail(AUS_ERR_INVALID, msg);
+    }
+    return AUS_OK;
+}
+
 extern "C" int aus_stft_features_batch_dev(aus_ctx *c, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
                                            size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr, int precision,
                                            void *d_features, void *d_spectra) {
     AUS_TRY(check_common(c, N, hop, wtype, precision));
     if (!lengths || (!d_audio && n_files)) return fail(AUS_ERR_INVALID, "null input");
     if (!d_features && !d_spectra) return fail(AUS_ERR_INVALID, "no output requested");
+    AUS_TRY(check_dev_align(d_audio, precision, false, "d_audio"));
+    AUS_TRY(check_dev_align(d_features, precision, false, "d_features"));
+    AUS_TRY(check_dev_align(d_spectra, precision, true, "d_spectra"));
     Batch b;
     make_batch(b, offsets, lengths, n_files, N, hop);
     if (precision == AUS_F64)
@@ -947,6 +962,8 @@ template <typename T> static int analyzer_dev_t(aus_ctx *c, const T *d_mags, siz
 extern "C" int aus_analyzer_batch_dev(aus_ctx *c, const void *d_mags, size_t F, size_t N, uint32_t sr, int precision, void *d_feat) {
     AUS_TRY(check_common(c, N, 1, 0, precision));
     if (!d_mags || !d_feat) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_mags, precision, false, "d_magnitudes"));
+    AUS_TRY(check_dev_align(d_feat, precision, false, "d_features"));
     if (precision == AUS_F64) return analyzer_dev_t<double>(c, (const double *)d_mags, F, N, sr, (double *)d_feat);
     return analyzer_dev_t<float>(c, (const float *)d_mags, F, N, sr, (float *)d_feat);
 }
@@ -1098,6 +1115,8 @@ extern "C" int aus_irstft_dev(aus_ctx *c, const void *d_spec, size_t F, size_t N
     AUS_TRY(check_common(c, N, hop, wtype, precision));
     if (F == 0) return fail(AUS_ERR_INVALID, "empty spectrogram (the reference underflows at fft.rs:208)");
     if (!d_spec || !d_audio) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_spec, precision, true, "d_spectra"));
+    AUS_TRY(check_dev_align(d_audio, precision, false, "d_audio"));
     if (precision == AUS_F64) return irstft_dev_t<double>(c, (const Cx<double> *)d_spec, F, N, hop, wtype, normalize, 1, (double *)d_audio);
     return irstft_dev_t<float>(c, (const Cx<float> *)d_spec, F, N, hop, wtype, normalize, 1, (float *)d_audio);
 }

@@ -124,7 +124,8 @@ int aus_stft_features_batch(aus_ctx *ctx, const double *audio, const uint64_t *o
                             int precision, double *features, uint64_t *frame_starts);
 /* device-resident variant: d_audio is T[...], d_features is T[total_frames x 14] (T = double or float per
  * `precision`); offsets/lengths are HOST arrays.  Optionally also writes spectra (d_spectra: T[frames x K x 2],
- * may be NULL).  Stream-ordered, no sync. */
+ * may be NULL).  Stream-ordered, no sync.  Alignment of device pointers (all *_dev entry points): sizeof(T) for real
+ * arrays, 2 sizeof(T) for complex spectra (AUS_ERR_INVALID otherwise); 16-byte aligned bases take the fastest staging. */
 int aus_stft_features_batch_dev(aus_ctx *ctx, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
                                 size_t n_files, size_t fft_size, size_t hop, int window_type, uint32_t sample_rate,
                                 int precision, void *d_features, void *d_spectra);

@@ -604,3 +604,51 @@ def test_direct_load_knob_is_bit_identical(ctx, orc, fft_size, hop):
     finally:
         ctx.set_direct_load(False)
         ctx.set_forward_variant(-1)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("fft_size,hop", [(256, 64), (2048, 512), (4096, 1000)])
+def test_device_entry_points_stay_inside_their_buffers(ctx, orc, prec, fft_size, hop):
+    """Every device-pointer entry point, with its inputs and outputs carved out of one arena at 0-, 1- and 3-element
+    offsets (16-byte aligned, 8-byte aligned, odd: the bulk-copy, vector and scalar staging paths): the guard bands
+    around every output keep their fill value, and the results do not depend on the alignment."""
+    import torch
+    ctx.use_torch_stream()
+    dt = torch.float64 if prec == "f64" else torch.float32
+    N, K, FILL = fft_size, fft_size // 2 + 1, 1234.5
+    x = orc.synth_signal(37 * hop + N + 11, SR, seed=23, file_id=N)
+    n, F = x.size, orc.num_frames(x.size, N, hop)
+    L = N + hop * (F - 1)
+    sizes = {"audio": n, "feat": F * 14, "spec": F * K * 2, "mags": F * K, "feat2": F * 14, "rec": L}
+    results = []
+    for shift in (0, 1, 3):
+        G = 64 + shift
+        arena = torch.full((sum(sizes.values()) + G * (len(sizes) + 1),), FILL, dtype=dt, device="cuda")
+        view, guards, pos = {}, [], 0
+        for name, sz in sizes.items():
+            guards.append(arena[pos:pos + G + ((pos + G) & 1 if name == "spec" else 0)])   # spectra: whole (re, im) pairs
+            pos += guards[-1].numel()
+            view[name] = arena[pos:pos + sz]
+            pos += sz
+        guards.append(arena[pos:])
+        view["audio"].copy_(torch.from_numpy(x).to(dt))
+        ctx.stft_features_batch_dev(view["audio"], [0], [n], N, hop, orc.HAMMING, SR, prec, view["feat"], view["spec"])
+        view["mags"].copy_(torch.view_as_complex(view["spec"].clone().view(F * K, 2)).abs())
+        ctx.analyzer_batch_dev(view["mags"], F, N, SR, prec, view["feat2"])
+        ctx.irstft_dev(view["spec"], F, N, hop, orc.HAMMING, prec, view["rec"], True)
+        torch.cuda.synchronize()
+        for i, g in enumerate(guards):
+            assert bool((g == FILL).all()), f"guard band {i} overwritten (shift {shift})"
+        results.append({k: view[k].cpu().numpy().copy() for k in ("feat", "spec", "feat2", "rec")})
+    tol = 1e-12 if prec == "f64" else 2e-6
+    for r in results[1:]:
+        assert np.array_equal(r["feat"], results[0]["feat"], equal_nan=True)          # staging differs, arithmetic does not
+        assert np.array_equal(r["spec"], results[0]["spec"])
+        assert np.array_equal(r["feat2"], results[0]["feat2"], equal_nan=True)
+        # irstft: the aligned fast path multiplies by a reciprocal norm where the generic path divides
+        assert np.max(np.abs(r["rec"] - results[0]["rec"])) <= tol * max(1.0, np.max(np.abs(results[0]["rec"])))
+    odd = torch.empty(2 * F * K + 1, dtype=dt, device="cuda")[1:]                    # spectra not on a (re, im) boundary
+    with pytest.raises(Exception, match="aligned"):
+        ctx.irstft_dev(odd, F, N, hop, orc.HAMMING, prec, view["rec"], True)
+    with pytest.raises(Exception, match="aligned"):
+        ctx.stft_features_batch_dev(view["audio"], [0], [n], N, hop, orc.HAMMING, SR, prec, None, odd)
