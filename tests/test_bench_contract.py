@@ -47,6 +47,7 @@ def test_gpu_arm_line():
     assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["scaling"] == "weak" and d["data"] == "synthetic"
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1.2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0.2 < d["roofline_fp64"]["frac"] < 1.0                   # extra key: the pipe that really bounds the f64 kernel
     assert d["gpu_launches"] == 2 * d["steps"]                      # stft_kernel + finalize_kernel per step
     assert d["e2e"]["h2d_bytes_per_step"] == 3600 * 44100 * 8 and d["e2e"]["value"] < d["value"]
     assert d["e2e_pcm16"]["h2d_bytes_per_step"] == 3600 * 44100 * 2 and d["e2e_pcm16"]["value"] > d["e2e"]["value"]

@@ -438,10 +438,11 @@ def test_next_rows_autocorrelation_and_time_features(ctx, aus, orc):
 
 
 def test_randomised_parameter_sweep(ctx, orc):
-    """Random fft sizes, hops (odd, 1, = fft_size), windows and lengths, features + spectra + inverse, f64."""
-    rng = np.random.default_rng(2026)
+    """Random fft sizes, hops (odd, 1, = fft_size), windows and lengths: features (f64), spectra and inverse (f64, f32)."""
+    import os
+    rng = np.random.default_rng(int(os.environ.get("AUS_SWEEP_SEED", "2026")))     # soak runs: more trials, other seeds
     sizes = [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
-    for trial in range(36):
+    for trial in range(int(os.environ.get("AUS_SWEEP_TRIALS", "36"))):
         N = int(sizes[trial % len(sizes)])
         hop = int(rng.choice([1, 3, N // 4, N // 2, N, int(rng.integers(1, N + 1)), N // 3 + 1]))
         if hop < 8 and N > 512:
@@ -455,6 +456,9 @@ def test_randomised_parameter_sweep(ctx, orc):
         assert S.shape == Sref.shape, what
         assert np.array_equal(np.isnan(S), np.isnan(Sref)), what
         assert_spectra(np.nan_to_num(S), np.nan_to_num(Sref), RTOL64, what)
+        S32 = ctx.rstft(x, N, hop, window, "f32")
+        assert np.array_equal(np.isnan(S32), np.isnan(Sref)), what
+        assert_spectra(np.nan_to_num(S32), np.nan_to_num(Sref), RTOL32, what + " f32")
         if not np.isnan(Sref).any():
             sc = cancellation_scales(np.abs(Sref), N, SR)
             assert_features(ctx.stft_features(x, N, hop, window, SR), orc.stft_features(x, N, hop, window, SR), RTOL64, what, scales=sc)
@@ -463,6 +467,8 @@ def test_randomised_parameter_sweep(ctx, orc):
                 got = ctx.irstft(Sref, N, hop, window, normalize=False)
                 assert got.shape == ref.shape, what
                 assert np.max(np.abs(got - ref)) <= RTOL64 * max(np.max(np.abs(ref)), 1e-300), what
+                got32 = ctx.irstft(Sref, N, hop, window, "f32", normalize=False)
+                assert np.max(np.abs(got32 - ref)) <= RTOL32 * max(np.max(np.abs(ref)), 1e-300), what + " f32"
 
 
 @pytest.mark.parametrize("variant", [0, 1])
