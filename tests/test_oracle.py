@@ -291,3 +291,38 @@ def test_time_domain_scalars(orc):
     # i=1: 0.5*-0.25<0 (+1); i=2: prod 0, a[3]<0 and a[2]==0 (+1); i=3: prod 0, a[4]<0? no; i=4: a[5]<0? no; i=5, 6: no
     assert orc.zero_crossing_rate(a, 7) == 2.0
     assert orc.energy(np.array([])) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------- independent library
+def test_oracle_against_scipy(orc):
+    """A second, unrelated implementation (scipy.signal) of the pieces whose conventions scipy shares: the symmetric
+    Hann / Hamming / Bartlett windows, the periodic Blackman, the un-normalised one-sided STFT of full frames
+    (scipy's 'spectrum' scaling undone), and the weighted-overlap-add inverse of the interior samples."""
+    sig = pytest.importorskip("scipy.signal")
+    L = 256
+    assert np.allclose(orc.generate_window(orc.HANNING, L), sig.windows.hann(L, sym=True), rtol=0, atol=1e-15)
+    assert np.allclose(orc.generate_window(orc.HAMMING, L), sig.windows.hamming(L, sym=True), rtol=0, atol=1e-15)
+    assert np.allclose(orc.generate_window(orc.BARTLETT, L), sig.windows.bartlett(L, sym=True), rtol=0, atol=1e-15)
+    assert np.allclose(orc.generate_window(orc.BLACKMAN, L), sig.windows.blackman(L, sym=False), rtol=0, atol=1e-15)
+    for N, hop, wt in ((512, 128, orc.HANNING), (1024, 300, orc.HAMMING), (256, 256, orc.BLACKMAN)):
+        x = orc.synth_signal(9 * N + 3, 44100, seed=5, file_id=N)
+        w = orc.generate_window(wt, N)
+        S = orc.rstft(x, N, hop, wt)
+        _, _, Z = sig.stft(x, window=w, nperseg=N, noverlap=N - hop, nfft=N, boundary=None, padded=False,
+                           return_onesided=True, scaling="spectrum")
+        Z = Z.T * w.sum()                                        # scipy keeps full frames only
+        nfull = Z.shape[0]
+        assert nfull >= S.shape[0] - 1 and nfull <= S.shape[0]
+        peak = np.abs(S[:nfull]).max(axis=1, keepdims=True)
+        assert np.max(np.abs(S[:nfull] - Z) / peak) < 1e-13, (N, hop, wt)
+    # inverse: interior samples of irstft (before peak normalisation) equal the signal when sum w^2 is the divisor
+    N, hop = 512, 128
+    x = orc.synth_signal(20 * N, 44100, seed=6)
+    y = orc.irstft(orc.rstft(x, N, hop, orc.HAMMING), N, hop, orc.HAMMING, normalize=False)
+    w = orc.generate_window(orc.HAMMING, N)
+    _, _, Z = sig.stft(x, window=w, nperseg=N, noverlap=N - hop, boundary=None, padded=False, scaling="spectrum")
+    _, ys = sig.istft(Z, window=w, nperseg=N, noverlap=N - hop, boundary=False, scaling="spectrum")
+    body = slice(N, min(ys.size, y.size, x.size) - N)
+    # the reference's irfft is un-normalised (N x the signal, fft.rs:66-93) and irstft keeps that factor
+    assert np.max(np.abs(y[body] / N - x[body])) < 1e-12
+    assert np.max(np.abs(ys[body] - x[body])) < 1e-12
