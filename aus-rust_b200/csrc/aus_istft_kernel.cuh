@@ -14,6 +14,10 @@
 #include "aus_stft_kernel.cuh"
 #include "aus_stft_r.cuh"
 
+#ifndef AUS_K4_PRE_REG
+#define AUS_K4_PRE_REG 0            // experiment: correct, -2 %
+#endif
+
 namespace aus {
 
 template <typename T> struct IstftParams {
@@ -129,6 +133,39 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             // ---- Hermitian pre-twiddle, in place: buf[k] <- conj(Zi[k]),
             //      Zi[k] = (Y[k] + conj Y[M-k]) + i W_N^{-k} (Y[k] - conj Y[M-k])   (fft.rs:221-229 folded in)
             //      The twiddles (cos, sin)(2 pi k / N) of this thread's pairs were loaded before the wait for the row (Wp).
+            // Experiment, off: f32, fft 2048 (one warp per frame, two radix-32 passes), pre-twiddled values kept out of shared memory.
+            // Thread t forms conj Zi[k] and conj Zi[M-k] for its k = t + 32 i; the first is its own pass-1 input r = i,
+            // the second is input 31 - i of thread 32 - t (thread 0: its own input 32 - i), handed over by a shuffle --
+            // 64 shared-memory accesses per thread less, 32 shuffles more: measured -2 % (the shuffles use the same data pipe).
+            constexpr bool PRE_REG = AUS_K4_PRE_REG && sizeof(T) == 4 && TPF == 32 && C::R1 == 32 && !C::THREE;
+            if constexpr (PRE_REG) {
+                Cx<T> v[32];
+                auto pretw = [&](Cx<T> Yk, Cx<T> Ym, const Cx<T> W, Cx<T> &A, Cx<T> &B) {
+                    const T sx = Yk.x + Ym.x, sy = Yk.y - Ym.y;
+                    const T dx = Yk.x - Ym.x, dy = Yk.y + Ym.y;
+                    const T ux = W.x * dx - W.y * dy;
+                    const T uy = W.x * dy + W.y * dx;
+                    A = Cx<T>{sx - uy, -(sy + ux)};
+                    B = Cx<T>{sx + uy, sy - ux};
+                };
+                static_for<0, 16>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    const int k = t + TPF * i;
+                    Cx<T> Yk = fb[k], Ym = fb[M - k];
+                    if (i == 0 && t == 0) { Yk.y = (T)0; Ym.y = (T)0; }        // DC / Nyquist: fft.rs:235
+                    pretw(Yk, Ym, Wp[i], v[i], v[31 - i]);
+                });
+                Cx<T> mid = Cx<T>{(T)0, (T)0}, dummy;
+                if (t == 0) pretw(fb[M / 2], fb[M / 2], Cx<T>{(T)0, (T)1}, mid, dummy);    // k = M/2 pairs with itself
+                const int partner = (TPF - t) & (TPF - 1);
+                static_for<0, 16>([&](auto c_) {                               // r = 31 .. 16: thread 0's sources stay intact
+                    constexpr int r = 31 - decltype(c_)::value;
+                    Cx<T> snd = v[r];
+                    if (t == 0) snd = (r == 16) ? mid : v[r == 16 ? 16 : r - 1];
+                    v[r] = shfl_cx<TPF>(snd, partner);
+                });
+                frame_fft<T, LOG2N>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false, /*vin=*/true);
+            } else {
             static_for<0, 17>([&](auto i_) {
                 constexpr int i = decltype(i_)::value;
                 const int k = t + TPF * i;                 // pairs (k, M-k), k = 0 .. M/2
@@ -151,6 +188,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             {
                 Cx<T> v[32];
                 frame_fft<T, LOG2N>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);     // buf: conj(z) in the Z layout
+            }
             }
 
             // ---- window + overlap-add into the output (ascending frame order), finalise completed samples.

@@ -134,7 +134,7 @@ template <int SHIFT> __device__ __forceinline__ int padi(int i) { return i + (i 
 // Z'[k] = FFT_M(z')[k] in the "Z layout" (index k + (k >> 4)), where z' = 0.5 * window * z.
 template <typename T, int LOG2N>
 __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, int t, int grp, bool prewindowed,
-                                          const Cx<T> *gsrc, Cx<T> (&v)[32], bool wpre) {
+                                          const Cx<T> *gsrc, Cx<T> (&v)[32], bool wpre, bool vin = false) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, TPF = C::TPF, R1 = C::R1, R3 = C::R3, XS = C::XS;
 
@@ -165,7 +165,8 @@ __device__ __forceinline__ void frame_fft(Cx<T> *buf, const StftParams<T> &p, in
 #pragma unroll 1
         for (int pass = 0; pass < p.npass; ++pass) {
             if (pass == 0) {
-                if (gsrc != nullptr) {                        // samples straight from global memory (16-byte, coalesced)
+                if (vin) {                                    // v[r] already holds the pass-1 input buf[j + r TPF] (K4, R1 == 32)
+                } else if (gsrc != nullptr) {                 // samples straight from global memory (16-byte, coalesced)
 #pragma unroll
                     for (int r = 0; r < 32; ++r) v[r] = emul(ldg_cx(gsrc + lbase + r * lstride), ldg_cx(tab + r * tstride));
                 } else if (prewindowed) {
