@@ -134,3 +134,36 @@ def test_shard_plan_many_files(aus, orc):
         assert np.all(np.diff(vd) >= 0) and vd.min() == 0 and vd.max() == n_dev - 1
         per_dev = np.array([frames[vd == d].sum() for d in range(n_dev)])
         assert per_dev.max() <= frames.sum() / n_dev + frames.max()           # balanced to within one file
+
+
+def test_shard_plan_properties(aus, orc):
+    """Property test of the pure-host planner (hypothesis): for any batch of files, fft_size, hop and device count the
+    virtual files (a) stay inside their source file, (b) tile the frame rows 0..total without gap or overlap, (c) each
+    produce exactly the rows they claim under the reference's frame-count rule, and (d) go to devices in ascending
+    contiguous runs."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=150, deadline=None)
+    @hyp.given(st.lists(st.integers(0, 60000), min_size=1, max_size=12), st.sampled_from([64, 256, 1024, 4096]),
+               st.integers(1, 4096), st.integers(1, 9), st.integers(0, 7))
+    def run(lens, N, hop, n_dev, gap):
+        hop = min(hop, N)
+        lens = np.asarray(lens, dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens + np.uint64(gap))[:-1]]).astype(np.uint64)
+        vo, vl, vr, vd = aus.plan_shards(offs, lens, N, hop, n_dev)
+        frames = [orc.num_frames(int(n), N, hop) for n in lens]
+        starts = np.concatenate([[0], np.cumsum(frames)])
+        assert len(vo) >= len(lens) and np.all(np.diff(vd) >= 0) and vd.min() >= 0 and vd.max() < n_dev
+        row = 0
+        for o, l, r in zip(vo, vl, vr):
+            f = int(np.searchsorted(starts, r, side="right") - 1)               # the file this row range belongs to
+            while frames[f] == 0 or r >= starts[f + 1]:
+                f += 1
+            assert int(offs[f]) <= o and o + l <= int(offs[f]) + int(lens[f])   # (a)
+            assert r == row                                                      # (b)
+            assert (o - int(offs[f])) % hop == 0 and (o - int(offs[f])) // hop == r - starts[f]   # a frame boundary
+            row += orc.num_frames(int(l), N, hop)                                # (c)
+        assert row == starts[-1]
+
+    run()
