@@ -98,7 +98,7 @@ extern "C" int aus_ctx_create(int device, aus_ctx **out) {
     if (!c) return fail(AUS_ERR_ALLOC, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (const char *rr = getenv("AUS_B200_RR")) c->rr_mode = (rr[0] == '0') ? 0 : (rr[0] == '1') ? 1 : -1;   // ablation knob
+    if (const char *rr = getenv("AUS_B200_RR")) c->rr_mode = (rr[0] == '0') ? 0 : (rr[0] == '1') ? 1 : (rr[0] == '2') ? 2 : -1;   // ablation knob
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
@@ -173,7 +173,7 @@ extern "C" int aus_ctx_set_direct_load(aus_ctx *c, int on) {
     return AUS_OK;
 }
 extern "C" int aus_ctx_set_forward_variant(aus_ctx *c, int mode) {
-    if (!c || mode < -1 || mode > 1) return fail(AUS_ERR_INVALID, "bad argument");
+    if (!c || mode < -1 || mode > 2) return fail(AUS_ERR_INVALID, "bad argument");
     c->rr_mode = mode;
     return AUS_OK;
 }
@@ -1354,3 +1354,14 @@ extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const 
         if (rc[d] != AUS_OK) return fail(rc[d], msg[d]);
     return AUS_OK;
 }
+
+#if AUS_PC_TIMING
+// development only: per-phase clock totals of the producer/consumer kernel (block 0, pair 0)
+extern "C" int aus_debug_pc_timing(unsigned long long *out32) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out32, aus::g_pc_timing, 40 * sizeof(unsigned long long)));
+    unsigned long long z[40] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(aus::g_pc_timing, z, sizeof z));
+    return AUS_OK;
+}
+#endif

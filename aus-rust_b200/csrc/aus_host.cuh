@@ -4,6 +4,7 @@
 #pragma once
 #include "../../include/aus_b200.h"
 #include "aus_istft_kernel.cuh"
+#include "aus_stft_pc.cuh"
 
 #include <algorithm>
 #include <map>
@@ -70,7 +71,8 @@ struct aus_ctx {
     uint64_t launches = 0;
     int direct_load = 0;                      // experiment knob, see aus_ctx_set_direct_load
     uint64_t chunk_samples = 32ull << 20;     // host pipeline granularity: 32 Mi samples = 256 MB of f64
-    int rr_mode = -1;                         // forward-kernel variant: -1 auto, 0 shared-memory tail, 1 register-resident tail
+    int rr_mode = -1;                         // forward-kernel variant: -1 auto, 0 shared-memory tail, 1 register-resident tail,
+                                              // 2 producer/consumer warps (f64 features at fft_size 2048; aus_stft_pc.cuh)
     std::map<int, Tables> tables;          // key = log2n * 2 + precision
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
     DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw, normtab;
@@ -110,11 +112,39 @@ template <typename T, int LG, bool RR, bool FEAT> int launch_stft_v(aus_ctx *c, 
 //        and the FP64 feature pass needs the resident warps).
 // c->rr_mode (aus_ctx_set_forward_variant / AUS_B200_RR) overrides the table for ablations.
 inline bool use_rr(const aus_ctx *c, int lg, bool f32, bool feat, bool spec) {
-    if (c->rr_mode >= 0) return c->rr_mode == 1;
+    if (c->rr_mode >= 0 && c->rr_mode <= 1) return c->rr_mode == 1;
     if (f32 || !feat || spec) return true;
     return lg <= 9 || lg >= 14;                          // f64 features alone
 }
+// Producer/consumer build (aus_stft_pc.cuh): f64, features only, one warp per frame.  Measured on B200 against the
+// single-role kernel on 1 h inputs: 1.15-1.19e8 frames/s against 1.22e8 (profiles/r2_k1_pc_experiment.md), so it is an
+// opt-in variant (rr_mode 2 / AUS_B200_RR=2), not the default.
+template <int LG> constexpr bool pc_built() { return LG == 11; }
+template <int LG> int launch_stft_pc(aus_ctx *c, const StftParams<double> &p) {
+    if constexpr (pc_built<LG>()) {
+        using C = CfgPC<LG>;
+        static bool attr_done[64] = {false};
+        auto kern = stft_pc_kernel<LG>;
+        const size_t smem = C::smem_bytes();
+        if (!attr_done[c->device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done[c->device & 63] = true;
+        }
+        const unsigned long long need = (p.total_frames + C::NPAIR - 1) / C::NPAIR;
+        const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min<unsigned long long>(need, (unsigned long long)c->sm_count));
+        kern<<<grid, C::BLOCK, smem, c->stream>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        return AUS_OK;
+    } else {
+        return fail(AUS_ERR_UNSUPPORTED, "producer/consumer kernel is not built for this fft_size");
+    }
+}
 template <typename T, int LG> int launch_stft_t(aus_ctx *c, const StftParams<T> &p) {
+    if constexpr (sizeof(T) == 8 && pc_built<LG>()) {
+        if (p.raw != nullptr && p.spec == nullptr && !p.direct && c->rr_mode == 2)
+            return launch_stft_pc<LG>(c, p);
+    }
     if (use_rr(c, LG, sizeof(T) == 4, p.raw != nullptr, p.spec != nullptr))
         return p.raw != nullptr ? launch_stft_v<T, LG, true, true>(c, p) : launch_stft_v<T, LG, true, false>(c, p);
     return launch_stft_v<T, LG, false, true>(c, p);
