@@ -8,7 +8,7 @@ every compute call needs the CUDA library and a B200, and fails loudly otherwise
 
 from ._lib import AusError, SpectrumError, lib_path, load_library, FEATURE_NAMES, NUM_FEATURES  # noqa: F401
 from .api import (Context, default_context, num_frames, irstft_len, batch_num_frames, plan_shards,  # noqa: F401
-                  stft_features_multi)
+                  stft_features_multi, irstft_multi, multi_shutdown)
 from .window import (WindowType, generate_window, generate_window_bartlett, generate_window_blackman,  # noqa: F401
                      generate_window_hanning, generate_window_hamming, generate_window_rectangular)
 from . import spectrum, analysis, mp  # noqa: F401

@@ -58,6 +58,8 @@ SIGNATURES = {
     "aus_ctx_set_chunk_samples": (c_int, [c_void_p, c_uint64]),
     "aus_ctx_set_direct_load": (c_int, [c_void_p, c_int]),
     "aus_ctx_set_forward_variant": (c_int, [c_void_p, c_int]),
+    "aus_ctx_set_host_register": (c_int, [c_void_p, c_int]),
+    "aus_multi_shutdown": (c_int, []),
     "aus_num_frames": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "aus_irstft_len": (c_size_t, [c_size_t, c_size_t, c_size_t]),
     "aus_generate_window": (c_int, [c_int, c_size_t, _p_d]),
@@ -80,6 +82,8 @@ SIGNATURES = {
     "aus_rfft": (c_int, [c_void_p, _p_d, c_size_t, c_int, _p_d]),
     "aus_complex_to_polar": (c_int, [c_void_p, _p_d, c_size_t, _p_d, _p_d]),
     "aus_polar_to_complex": (c_int, [c_void_p, _p_d, _p_d, c_size_t, _p_d]),
+    "aus_complex_to_polar_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "aus_polar_to_complex_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "aus_spectral_features_generic": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d, _p_d, c_size_t, _p_d, _p_d, c_size_t,
                                               c_uint32, _p_d]),
     "aus_analyzer_batch": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_uint32, c_int, _p_d]),
@@ -87,9 +91,18 @@ SIGNATURES = {
     "aus_irstft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, _p_d]),
     "aus_irstft_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p]),
     "aus_irfft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_int, _p_d]),
+    "aus_irstft_batch": (c_int, [c_void_p, _p_d, _p_u64, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, _p_d]),
+    "aus_irstft_batch_dev": (c_int, [c_void_p, c_void_p, _p_u64, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "aus_irstft_multi": (c_int, [POINTER(c_int), c_int, _p_d, _p_u64, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, _p_d]),
     "aus_autocorrelation": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d]),
     "aus_autocorrelation_batch": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d]),
     "aus_time_features_batch": (c_int, [c_void_p, _p_d, _p_u64, _p_u64, c_size_t, c_uint32, _p_d]),
+    "aus_time_features_frames": (c_int, [c_void_p, _p_d, _p_u64, _p_u64, c_size_t, c_size_t, c_size_t, c_uint32, _p_d]),
+    "aus_time_features_frames_dev": (c_int, [c_void_p, c_void_p, _p_u64, _p_u64, c_size_t, c_size_t, c_size_t, c_uint32, c_void_p]),
+    "aus_pcm_to_f64": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_int, c_int, c_int, _p_d]),
+    "aus_pcm_to_f64_dev": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "aus_mixdown": (c_int, [c_void_p, _p_d, c_size_t, c_int, _p_d]),
+    "aus_mixdown_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "aus_synth_dev": (c_int, [c_void_p, c_void_p, c_uint64, c_uint64, c_uint32, c_double, c_uint64, c_uint64, c_int]),
 }
 

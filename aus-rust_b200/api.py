@@ -37,6 +37,40 @@ def _pu64(a: np.ndarray):
     return a.ctypes.data_as(_lib._p_u64)
 
 
+def _batch_desc(offsets, lengths, n_available: int):
+    """offsets / lengths as uint64 arrays, checked against the buffer they index (the C ABI takes no total size: a bad
+    descriptor would make the H2D copy read past the caller's buffer)."""
+    off = np.ascontiguousarray(offsets, dtype=np.uint64).reshape(-1)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint64).reshape(-1)
+    if off.size != ln.size:
+        raise ValueError("offsets and lengths differ in length")
+    if ln.size and int((off.astype(object) + ln.astype(object)).max()) > int(n_available):
+        raise ValueError("a file descriptor (offset + length) reaches past the end of the audio buffer")
+    return off, ln
+
+
+def _check_out(out, total_rows: int, width: int = NUM_FEATURES):
+    if out.dtype != np.float64 or not out.flags.c_contiguous or out.size != total_rows * width:
+        raise ValueError(f"out must be a C-contiguous float64 array of {total_rows} x {width}")
+
+
+def _pcm_bits(p: np.ndarray, sample_bits=None) -> int:
+    """int8 -> 8, int16 -> 16, int32 -> 24 or 32 (``sample_bits``, default 32): the widths audiofile.rs:296-329 reads."""
+    if p.dtype == np.int8:
+        bits = 8
+    elif p.dtype == np.int16:
+        bits = 16
+    elif p.dtype == np.int32:
+        bits = int(sample_bits or 32)
+        if bits not in (24, 32):
+            raise ValueError("int32 PCM holds 24- or 32-bit samples")
+    else:
+        raise ValueError("pcm must be int8, int16 or int32")
+    if sample_bits is not None and int(sample_bits) != bits:
+        raise ValueError(f"sample_bits={sample_bits} does not match dtype {p.dtype}")
+    return bits
+
+
 def num_frames(n_samples: int, fft_size: int, hop: int) -> int:
     """Frame count of the loop in spectrum/fft.rs:126-176."""
     return int(_lib.load_library().aus_num_frames(int(n_samples), int(fft_size), int(hop)))
@@ -123,13 +157,12 @@ class Context:
         """Batch of files in one launch.  ``audio`` / ``out`` may be views of pinned host memory (then the copies
         inside the call run at full PCIe rate)."""
         a = _f64(audio)
-        off = np.ascontiguousarray(offsets, dtype=np.uint64)
-        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        off, ln = _batch_desc(offsets, lengths, a.size)
         total = batch_num_frames(ln, fft_size, hop)
         if out is None:
             out = np.empty((total, NUM_FEATURES), dtype=np.float64)
-        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != total * NUM_FEATURES:
-            raise ValueError("out must be a C-contiguous float64 array of total_frames x 14")
+        else:
+            _check_out(out, total)
         starts = np.empty(ln.size + 1, dtype=np.uint64)
         _lib.check(self._lib.aus_stft_features_batch(self._h, _pd(a), _pu64(off), _pu64(ln), ln.size, int(fft_size),
                                                      int(hop), int(window_type), int(sample_rate), _prec(precision),
@@ -141,17 +174,13 @@ class Context:
         """Decoded integer PCM (int16, or int32 holding 24- or 32-bit samples) uploaded as-is and widened on the device
         like the reference's reader: ``sample as f64 / INTMAX`` (audiofile.rs:296-329)."""
         p = np.ascontiguousarray(pcm)
-        if p.dtype == np.int16:
-            bits = 16
-        elif p.dtype == np.int32:
-            bits = int(sample_bits or 32)
-        else:
-            raise ValueError("pcm must be int16 or int32")
-        off = np.ascontiguousarray(offsets, dtype=np.uint64)
-        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        bits = _pcm_bits(p, sample_bits)
+        off, ln = _batch_desc(offsets, lengths, p.size)
         total = batch_num_frames(ln, fft_size, hop)
         if out is None:
             out = np.empty((total, NUM_FEATURES), dtype=np.float64)
+        else:
+            _check_out(out, total)
         starts = np.empty(ln.size + 1, dtype=np.uint64)
         _lib.check(self._lib.aus_stft_features_batch_pcm(self._h, p.ctypes.data_as(c_void_p), bits, _pu64(off), _pu64(ln),
                                                          ln.size, int(fft_size), int(hop), int(window_type),
@@ -255,11 +284,56 @@ class Context:
     def time_features_batch(self, audio, offsets, lengths, sample_rate: int) -> np.ndarray:
         """dc_bias, dbfs_max, energy, zero_crossing_rate per file (analysis/audio_analysis_tools.rs:22-108)."""
         a = _f64(audio)
-        off = np.ascontiguousarray(offsets, dtype=np.uint64)
-        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        off, ln = _batch_desc(offsets, lengths, a.size)
         out = np.empty((ln.size, 4), dtype=np.float64)
         _lib.check(self._lib.aus_time_features_batch(self._h, _pd(a), _pu64(off), _pu64(ln), ln.size, int(sample_rate), _pd(out)))
         return out
+
+    def time_features_frames(self, audio, offsets, lengths, fft_size: int, hop: int, sample_rate: int) -> np.ndarray:
+        """dc_bias, dbfs_max, energy, zero_crossing_rate of every STFT frame (same rows as the feature matrix)."""
+        a = _f64(audio)
+        off, ln = _batch_desc(offsets, lengths, a.size)
+        out = np.empty((batch_num_frames(ln, fft_size, hop), 4), dtype=np.float64)
+        _lib.check(self._lib.aus_time_features_frames(self._h, _pd(a), _pu64(off), _pu64(ln), ln.size, int(fft_size), int(hop),
+                                                      int(sample_rate), _pd(out)))
+        return out
+
+    def pcm_to_f64(self, pcm, n_channels: int = 1, interleaved: bool = True, mixdown: bool = False, sample_bits=None) -> np.ndarray:
+        """Decoded integer PCM -> f64 as audiofile.rs:296-329 does (``sample as f64 / INTMAX``), optionally followed by
+        ``mixdown`` (audiofile.rs:168-178).  -> ``[n_channels, n_frames]``, or ``[n_frames]`` after mixdown."""
+        p = np.ascontiguousarray(pcm)
+        bits = _pcm_bits(p, sample_bits)
+        if p.size % int(n_channels):
+            raise ValueError("sample count is not a multiple of the channel count")
+        nf = p.size // int(n_channels)
+        out = np.empty(nf if mixdown else (int(n_channels), nf), dtype=np.float64)
+        _lib.check(self._lib.aus_pcm_to_f64(self._h, p.ctypes.data_as(c_void_p), bits, nf, int(n_channels), 1 if interleaved else 0,
+                                            1 if mixdown else 0, _pd(out)))
+        return out
+
+    def mixdown(self, channels) -> np.ndarray:
+        """audiofile.rs:168-178 on f64 channels ``[n_channels, n_frames]`` (channel 0 is counted twice, as in the reference)."""
+        ch = _f64(channels)
+        if ch.ndim == 1:
+            ch = ch[None, :]
+        out = np.empty(ch.shape[1], dtype=np.float64)
+        _lib.check(self._lib.aus_mixdown(self._h, _pd(ch), ch.shape[1], ch.shape[0], _pd(out)))
+        return out
+
+    def irstft_batch(self, spectrograms, fft_size: int, hop: int, window_type: int, precision="f64", normalize=True):
+        """Several spectrograms (list of ``[frames_i, bins]``) in one launch -> list of signals (fft.rs:204 each)."""
+        specs = [np.ascontiguousarray(s, dtype=np.complex128) for s in spectrograms]
+        nf = np.array([s.shape[0] for s in specs], dtype=np.uint64)
+        cat = np.ascontiguousarray(np.concatenate(specs, axis=0))
+        lens = [irstft_len(int(f), fft_size, hop) for f in nf]
+        out = np.empty(int(sum(lens)), dtype=np.float64)
+        _lib.check(self._lib.aus_irstft_batch(self._h, cat.ctypes.data_as(_lib._p_d), _pu64(nf), nf.size, cat.shape[1], int(fft_size),
+                                              int(hop), int(window_type), _prec(precision), 1 if normalize else 0, _pd(out)))
+        return list(np.split(out, np.cumsum(lens)[:-1]))
+
+    def set_host_register(self, mode: int):
+        """Page-lock pageable inputs of the host-pointer feature calls: -1 auto (>= 64 MB), 0 never, 1 always."""
+        _lib.check(self._lib.aus_ctx_set_host_register(self._h, int(mode)))
 
     # ---- device-pointer API (torch CUDA tensors; stream-ordered, no sync)
     def _check_dev(self, t, precision, name):
@@ -273,8 +347,12 @@ class Context:
 
     def stft_features_batch_dev(self, d_audio, offsets, lengths, fft_size: int, hop: int, window_type: int,
                                 sample_rate: int, precision="f64", d_features=None, d_spectra=None):
-        off = np.ascontiguousarray(offsets, dtype=np.uint64)
-        ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+        off, ln = _batch_desc(offsets, lengths, d_audio.numel())
+        total = batch_num_frames(ln, fft_size, hop)
+        if d_features is not None and d_features.numel() < total * NUM_FEATURES:
+            raise ValueError("d_features is smaller than total_frames x 14")
+        if d_spectra is not None and d_spectra.numel() < total * (fft_size // 2 + 1) * 2:
+            raise ValueError("d_spectra is smaller than total_frames x (fft_size/2+1) x 2")
         _lib.check(self._lib.aus_stft_features_batch_dev(
             self._h, self._check_dev(d_audio, precision, "d_audio"), _pu64(off), _pu64(ln), ln.size, int(fft_size),
             int(hop), int(window_type), int(sample_rate), _prec(precision),
@@ -291,6 +369,32 @@ class Context:
                                             int(fft_size), int(hop), int(window_type), _prec(precision),
                                             1 if normalize else 0, self._check_dev(d_audio, precision, "d_audio")))
 
+    def complex_to_polar_dev(self, d_spectra, d_mag, d_ph=None):
+        """fft_tools.rs:41-55 on device tensors (f64; d_spectra is ``[..., 2]`` re/im pairs)."""
+        _lib.check(self._lib.aus_complex_to_polar_dev(self._h, self._check_dev(d_spectra, "f64", "d_spectra"), d_mag.numel(),
+                                                      self._check_dev(d_mag, "f64", "d_mag"), self._check_dev(d_ph, "f64", "d_ph")))
+
+    def polar_to_complex_dev(self, d_mag, d_ph, d_spectra):
+        """fft_tools.rs:164-188 on device tensors (f64)."""
+        _lib.check(self._lib.aus_polar_to_complex_dev(self._h, self._check_dev(d_mag, "f64", "d_mag"), self._check_dev(d_ph, "f64", "d_ph"),
+                                                      d_mag.numel(), self._check_dev(d_spectra, "f64", "d_spectra")))
+
+    def irstft_batch_dev(self, d_spectra, n_frames, fft_size: int, hop: int, window_type: int, precision, d_audio, normalize=True):
+        nf = np.ascontiguousarray(n_frames, dtype=np.uint64)
+        _lib.check(self._lib.aus_irstft_batch_dev(self._h, self._check_dev(d_spectra, precision, "d_spectra"), _pu64(nf), nf.size,
+                                                  int(fft_size), int(hop), int(window_type), _prec(precision), 1 if normalize else 0,
+                                                  self._check_dev(d_audio, precision, "d_audio")))
+
+    def time_features_frames_dev(self, d_audio, offsets, lengths, fft_size: int, hop: int, sample_rate: int, d_out):
+        off, ln = _batch_desc(offsets, lengths, d_audio.numel())
+        _lib.check(self._lib.aus_time_features_frames_dev(self._h, self._check_dev(d_audio, "f64", "d_audio"), _pu64(off), _pu64(ln),
+                                                          ln.size, int(fft_size), int(hop), int(sample_rate),
+                                                          self._check_dev(d_out, "f64", "d_out")))
+
+    def mixdown_dev(self, d_channels, n_frames: int, n_channels: int, d_out):
+        _lib.check(self._lib.aus_mixdown_dev(self._h, self._check_dev(d_channels, "f64", "d_channels"), int(n_frames), int(n_channels),
+                                             self._check_dev(d_out, "f64", "d_out")))
+
     def synth_dev(self, d_audio, n0: int = 0, sample_rate: int = 44100, freq: float = 440.0, seed: int = 0,
                   file_id: int = 0, precision="f64"):
         _lib.check(self._lib.aus_synth_dev(self._h, self._check_dev(d_audio, precision, "d_audio"), d_audio.numel(),
@@ -303,13 +407,31 @@ def stft_features_multi(devices, audio, offsets, lengths, fft_size: int, hop: in
     """Shard a batch (or one long file) over several GPUs of this box; host threads, ordered gather."""
     lib = _lib.load_library()
     a = _f64(audio)
-    off = np.ascontiguousarray(offsets, dtype=np.uint64)
-    ln = np.ascontiguousarray(lengths, dtype=np.uint64)
+    off, ln = _batch_desc(offsets, lengths, a.size)
     devs = (c_int * len(devices))(*[int(d) for d in devices])
     out = np.empty((batch_num_frames(ln, fft_size, hop), NUM_FEATURES), dtype=np.float64)
     _lib.check(lib.aus_stft_features_multi(devs, len(devices), _pd(a), _pu64(off), _pu64(ln), ln.size, int(fft_size),
                                            int(hop), int(window_type), int(sample_rate), _prec(precision), _pd(out)))
     return out
+
+
+def irstft_multi(devices, spectrograms, fft_size: int, hop: int, window_type: int, normalize=True):
+    """irstft sharded by frame range (or by spectrogram) over several GPUs; list of ``[frames_i, bins]`` -> list of signals."""
+    lib = _lib.load_library()
+    specs = [np.ascontiguousarray(s, dtype=np.complex128) for s in spectrograms]
+    nf = np.array([s.shape[0] for s in specs], dtype=np.uint64)
+    cat = np.ascontiguousarray(np.concatenate(specs, axis=0))
+    lens = [irstft_len(int(f), fft_size, hop) for f in nf]
+    out = np.empty(int(sum(lens)), dtype=np.float64)
+    devs = (c_int * len(devices))(*[int(d) for d in devices])
+    _lib.check(lib.aus_irstft_multi(devs, len(devices), cat.ctypes.data_as(_lib._p_d), _pu64(nf), nf.size, cat.shape[1], int(fft_size),
+                                    int(hop), int(window_type), 1 if normalize else 0, _pd(out)))
+    return list(np.split(out, np.cumsum(lens)[:-1]))
+
+
+def multi_shutdown():
+    """Free the contexts cached by the multi-device entry points."""
+    _lib.check(_lib.load_library().aus_multi_shutdown())
 
 
 def plan_shards(offsets, lengths, fft_size: int, hop: int, n_devices: int):

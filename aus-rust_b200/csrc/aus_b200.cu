@@ -93,7 +93,8 @@ extern "C" int aus_ctx_create(int device, aus_ctx **out) {
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(AUS_ERR_CUDA, "device is not sm_100-class; kernels are built for sm_100a only");
+    if (prop.major != 10 || prop.minor != 0)      // sm_100a SASS is arch-specific: no PTX, not forward compatible
+        return fail(AUS_ERR_CUDA, "device is not sm_100 (B200); the kernels are built for sm_100a only and there is no CPU fallback");
     aus_ctx *c = new (std::nothrow) aus_ctx();
     if (!c) return fail(AUS_ERR_ALLOC, "out of host memory");
     c->device = device;
@@ -137,7 +138,7 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
         for (void *w : kv.second.winf) cudaFree(w);
     }
     cudaFree(c->log2tab);
-    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw, &c->normtab,
+    for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw, &c->normtab, &c->acorr,
                       &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1], &c->ppcm[0], &c->ppcm[1]})
         b->release();
     if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -414,8 +415,11 @@ __global__ void __launch_bounds__(256) time_partial_kernel(const double *audio, 
                                                            int n_files, double *partials) {
     __shared__ double sh[4][8];
     const unsigned long long chunk = blockIdx.x;
-    int f = 0;
-    while (f + 1 < n_files && chunk >= chunk_first[f + 1]) ++f;         // few files per launch: linear is fine
+    int f = 0, fh = n_files - 1;                                        // last file whose first chunk is <= chunk
+    while (f < fh) {
+        const int mid = (f + fh + 1) >> 1;
+        if (chunk_first[mid] <= chunk) f = mid; else fh = mid - 1;
+    }
     const unsigned long long n = len[f], c0 = (chunk - chunk_first[f]) * (unsigned long long)TF_CHUNK;
     const double *a = audio + off[f];
     const unsigned long long c1 = c0 + TF_CHUNK < n ? c0 + TF_CHUNK : n;
@@ -715,6 +719,7 @@ static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offs
     if (frame_starts) for (size_t i = 0; i <= n_files; ++i) frame_starts[i] = b.first[i];
     if (b.total_frames == 0) return AUS_OK;
     if (!audio && b.span) return fail(AUS_ERR_INVALID, "null audio");
+    if (features) AUS_TRY(fill_feature_params_check(N, sr));      // before any copy from / to the caller's buffers is queued
     if (features && !spectra)      // the fused feature path: chunked, copy/compute overlapped
         return stft_features_host_pipelined(c, audio, 0, b, N, hop, wtype, sr, precision, features, c->chunk_samples);
     const size_t K = N / 2 + 1;
@@ -774,12 +779,48 @@ static int ensure_pipeline(aus_ctx *c) {
     return AUS_OK;
 }
 
-// pcm_bits: 0 = the host buffer is f64 samples; 16 = int16_t PCM; 24 / 32 = int32_t PCM (24-bit samples in 32-bit words)
+// pcm_bits: 0 = the host buffer is f64 samples; 8 = int8_t PCM; 16 = int16_t PCM; 24 / 32 = int32_t PCM (24-bit samples in 32-bit words)
+static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
+                                             int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples);
+
+// Error exits of the pipeline must not leave DMA running on the caller's buffers: whatever happens, all three streams are
+// drained before the call returns.  A pageable input (what a Rust Vec<f64> is) is page-locked for the duration of the
+// call when that pays (aus_ctx_set_host_register), so its chunked H2D copies are real asynchronous DMA.
 static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
                                         int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples) {
     AUS_TRY(ensure_pipeline(c));
-    const size_t in_bytes = pcm_bits == 0 ? sizeof(double) : (pcm_bits == 16 ? 2 : 4);
-    const double intmax = pcm_bits == 16 ? 32767.0 : (pcm_bits == 24 ? 8388607.0 : 2147483647.0);   // audiofile.rs:12-15
+    const size_t in_bytes_ = pcm_bits == 0 ? sizeof(double) : (pcm_bits == 8 ? 1 : (pcm_bits == 16 ? 2 : 4));
+    const size_t bytes = (size_t)b.span * in_bytes_;
+    bool registered = false;
+    if (c->hostreg_mode != 0 && audio && bytes) {
+        cudaPointerAttributes at;
+        const bool pageable = cudaPointerGetAttributes(&at, audio) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+        (void)cudaGetLastError();
+        if (pageable && (c->hostreg_mode == 1 || bytes >= c->hostreg_min_bytes)) {
+            registered = cudaHostRegister(const_cast<void *>(audio), bytes, cudaHostRegisterDefault) == cudaSuccess;
+            (void)cudaGetLastError();                           // registration is an optimisation: failure falls back to staging
+        }
+    }
+    const int rc = stft_features_host_pipelined_body(c, audio, pcm_bits, b, N, hop, wtype, sr, precision, features, chunk_samples);
+    const std::string msg = g_err;
+    if (rc != AUS_OK) {
+        (void)cudaStreamSynchronize(c->s_in);
+        (void)cudaStreamSynchronize(c->s_out);
+        (void)cudaStreamSynchronize(c->stream);
+        (void)cudaGetLastError();
+    }
+    if (registered) {
+        (void)cudaHostUnregister(const_cast<void *>(audio));
+        (void)cudaGetLastError();
+    }
+    if (rc != AUS_OK) g_err = msg;
+    return rc;
+}
+
+static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
+                                             int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples) {
+    const size_t in_bytes = pcm_bits == 0 ? sizeof(double) : (pcm_bits == 8 ? 1 : (pcm_bits == 16 ? 2 : 4));
+    const double intmax = pcm_bits == 8 ? 127.0 : pcm_bits == 16 ? 32767.0 : (pcm_bits == 24 ? 8388607.0 : 2147483647.0);   // audiofile.rs:12-15
     // virtual files no longer than a chunk
     std::vector<VFile> vf;
     for (size_t i = 0; i < b.off.size(); ++i) {
@@ -832,7 +873,8 @@ static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_b
             cb.off[i - ch.lo] = vf[i].off - ch.s0; cb.len[i - ch.lo] = vf[i].len; cb.first[i - ch.lo] = f; f += vf[i].frames;
         }
         cb.first[ch.hi - ch.lo] = f; cb.total_frames = f; cb.span = ch.span;
-        if (pcm_bits == 16) AUS_TRY(pcm_dev<int16_t, double>(c, (const int16_t *)c->ppcm[bb].p, (double *)c->pin64[bb].p, ch.span, intmax));
+        if (pcm_bits == 8) AUS_TRY(pcm_dev<int8_t, double>(c, (const int8_t *)c->ppcm[bb].p, (double *)c->pin64[bb].p, ch.span, intmax));
+        else if (pcm_bits == 16) AUS_TRY(pcm_dev<int16_t, double>(c, (const int16_t *)c->ppcm[bb].p, (double *)c->pin64[bb].p, ch.span, intmax));
         else if (pcm_bits) AUS_TRY(pcm_dev<int32_t, double>(c, (const int32_t *)c->ppcm[bb].p, (double *)c->pin64[bb].p, ch.span, intmax));
         if (precision == AUS_F64) {
             AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->pin64[bb].p, cb, N, hop, wtype, sr, (double *)c->pout64[bb].p, nullptr));
@@ -865,10 +907,9 @@ extern "C" int aus_stft_features_batch_pcm(aus_ctx *c, const void *pcm, int samp
                                            const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype,
                                            uint32_t sr, int precision, double *features, uint64_t *frame_starts) {
     AUS_TRY(check_common(c, N, hop, wtype, precision));
-    if (sample_bits != 16 && sample_bits != 24 && sample_bits != 32)
-        return fail(AUS_ERR_INVALID, "sample_bits must be 16 (int16_t), 24 or 32 (int32_t)");
+    if (sample_bits != 8 && sample_bits != 16 && sample_bits != 24 && sample_bits != 32)
+        return fail(AUS_ERR_INVALID, "sample_bits must be 8 (int8_t), 16 (int16_t), 24 or 32 (int32_t)");
     if (!lengths || !features) return fail(AUS_ERR_INVALID, "null argument");
-    if (sample_bits != 16 && sample_bits != 24 && sample_bits != 32) return fail(AUS_ERR_INVALID, "bad sample_bits");
     AUS_TRY(fill_feature_params_check(N, sr));
     Batch b;
     make_batch(b, offsets, lengths, n_files, N, hop);
@@ -990,9 +1031,21 @@ extern "C" int aus_analyzer_batch(aus_ctx *c, const double *mags, size_t F, size
 }
 
 // ------------------------------------------------------------------------------------------------ inverse (K4/K5)
+// One unit of inverse work: frames [a, b) of a spectrogram of F frames whose rows [row0, b) sit in the device array from
+// row `row_off` on; its output samples [a * hop, (b == F) ? N + hop (F - 1) : b * hop) go to d_out + out_off.  A whole
+// spectrogram is the shard {F, 0, 0, 0, F, 0}; aus_irstft_multi cuts a long one into frame ranges over several devices
+// (row0 = max(0, a - halo): the frames that still overlap the shard are recomputed, not communicated -- SURVEY 8e).
+struct IShard {
+    unsigned long long F, row_off, row0, a, b, out_off;
+    unsigned long long samp0(size_t hop) const { return a * hop; }
+    unsigned long long out_len(size_t N, size_t hop) const { return (b == F ? N + hop * (F - 1) : b * hop) - a * hop; }
+};
+
+// K4 over a list of shards.  Leaves the signed, NaN-skipping max (fft.rs:255-258, starting at 0.0) of every shard's own
+// samples in c->misc[shard] (bit pattern of a double) and the K5 descriptors in c->desc.
 template <typename T>
-static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, size_t hop, int wtype, int normalize,
-                        int apply_window, T *d_out) {
+static int irstft_k4(aus_ctx *c, const Cx<T> *d_spec, unsigned long long total_rows, const std::vector<IShard> &sh, size_t N,
+                     size_t hop, int wtype, int apply_window, T *d_out) {
     const int lg = log2_exact(N);
     Tables *tb = nullptr;
     AUS_TRY(get_tables<T>(c, lg, wtype, &tb));
@@ -1000,18 +1053,28 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     // segments: contiguous frame ranges, about one per resident frame group, never shorter than 4 * (halo + 1)
     const size_t tpf = std::max<size_t>(1, N / 64);
     const unsigned long long groups = (unsigned long long)c->sm_count * (((sizeof(T) == 8 && tpf >= 16 && tpf <= 128) ? 384 : 256) / tpf) * (sizeof(T) == 4 ? 2 : 1);
-    unsigned long long seglen = std::max<unsigned long long>((F + groups - 1) / groups, 4ull * (unsigned long long)(halo + 1));
-    const unsigned long long nseg = std::max<unsigned long long>(1, (F + seglen / 2) / seglen);
-    std::vector<unsigned long long> sfile(nseg, 0), sa(nseg), sb(nseg), first = {0ull, (unsigned long long)F}, ooff = {0ull},
-                                    olen = {(unsigned long long)aus_irstft_len(F, N, hop)};
-    for (unsigned long long s = 0; s < nseg; ++s) {
-        sa[s] = F * s / nseg;
-        sb[s] = F * (s + 1) / nseg;
+    unsigned long long Ftot = 0;
+    for (const IShard &x : sh) Ftot += x.b - x.a;
+    const unsigned long long seglen = std::max<unsigned long long>((Ftot + groups - 1) / groups, 4ull * (unsigned long long)(halo + 1));
+    const size_t ns = sh.size();
+    std::vector<unsigned long long> sfile, sa, sb, first(ns), frames(ns), row0(ns), samp0(ns), ooff(ns), olen(ns);
+    for (size_t i = 0; i < ns; ++i) {
+        const IShard &x = sh[i];
+        first[i] = x.row_off; frames[i] = x.F; row0[i] = x.row0; samp0[i] = x.samp0(hop); ooff[i] = x.out_off; olen[i] = x.out_len(N, hop);
+        const unsigned long long Fi = x.b - x.a;
+        const unsigned long long nseg = std::max<unsigned long long>(1, (Fi + seglen / 2) / seglen);
+        for (unsigned long long k = 0; k < nseg; ++k) {
+            sfile.push_back(i);
+            sa.push_back(x.a + Fi * k / nseg);
+            sb.push_back(x.a + Fi * (k + 1) / nseg);
+        }
     }
     std::vector<const unsigned long long *> dp;
-    AUS_TRY(upload_desc(c, c->desc, {&sfile, &sa, &sb, &first, &ooff, &olen}, dp));
-    AUS_TRY(c->misc.ensure(sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, sizeof(unsigned long long), c->stream));      // maxval = 0.0, fft.rs:255
+    AUS_TRY(upload_desc(c, c->desc, {&sfile, &sa, &sb, &first, &frames, &row0, &samp0, &ooff, &olen}, dp));
+    c->k5_out_off = dp[7];
+    c->k5_out_len = dp[8];
+    AUS_TRY(c->misc.ensure(ns * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, ns * sizeof(unsigned long long), c->stream));     // maxval = 0.0, fft.rs:255
     IstftParams<T> p;
     memset(&p, 0, sizeof(p));
     p.spec = d_spec;
@@ -1020,10 +1083,13 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     p.seg_a = dp[1];
     p.seg_b = dp[2];
     p.file_first = dp[3];
-    p.file_out_off = dp[4];
+    p.file_frames = dp[4];
+    p.file_row0 = dp[5];
+    p.file_samp0 = dp[6];
+    p.file_out_off = dp[7];
     p.file_max_bits = (unsigned long long *)c->misc.p;
-    p.n_seg = nseg;
-    p.total_rows = F;
+    p.n_seg = sfile.size();
+    p.total_rows = total_rows;
     p.hop = (int)hop;
     p.hop_magic = hop == 1 ? 0xffffffffu : (unsigned)((1ull << 32) / hop + 1);   // exact for x < 2^15 (hop == 1: see kernel)
     p.halo = (int)halo;
@@ -1041,8 +1107,8 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
             std::vector<T> rn(hop);
             for (size_t u = 0; u < hop; ++u) {
                 T acc = (T)0;
-                for (long long b = (long long)((N - 1 - u) / hop); b >= 0; --b) {
-                    const T wv = (T)w[u + (size_t)b * hop];
+                for (long long bb = (long long)((N - 1 - u) / hop); bb >= 0; --bb) {
+                    const T wv = (T)w[u + (size_t)bb * hop];
                     acc += wv * wv;
                 }
                 rn[u] = (T)1 / acc;
@@ -1062,15 +1128,34 @@ static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, siz
     p.fwd.twNt = (const Cx<T> *)tb->twNt;
     p.fwd.twN = (const Cx<T> *)tb->twN;
     p.fwd.npass = 2;
-    AUS_TRY(launch_istft<T>(c, lg, p));
+    return launch_istft<T>(c, lg, p);
+}
+// K5 over the shards of the last irstft_k4 call on this context: audio *= 10^(-6/20) / maxval (fft.rs:260-265), the
+// per-shard maxima taken from c->misc (a multi-device caller overwrites them with the whole file's maximum first).
+template <typename T> static int irstft_k5(aus_ctx *c, size_t n_shards, unsigned long long longest, T *d_out) {
+    const double level = std::pow(10.0, -6.0 / 20.0);                                  // fft.rs:261-262
+    dim3 grid((unsigned int)std::min<unsigned long long>((longest + 255) / 256, (unsigned long long)c->sm_count * 8), (unsigned int)n_shards);
+    peak_scale_kernel<T><<<grid, 256, 0, c->stream>>>(d_out, c->k5_out_off, c->k5_out_len, (const unsigned long long *)c->misc.p, level);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+template <typename T>
+static int irstft_shards_dev(aus_ctx *c, const Cx<T> *d_spec, unsigned long long total_rows, const std::vector<IShard> &sh, size_t N,
+                             size_t hop, int wtype, int normalize, int apply_window, T *d_out) {
+    AUS_TRY(irstft_k4<T>(c, d_spec, total_rows, sh, N, hop, wtype, apply_window, d_out));
     if (apply_window && normalize) {
-        const double level = std::pow(10.0, -6.0 / 20.0);                                  // fft.rs:261-262
-        dim3 grid((unsigned int)std::min<unsigned long long>((olen[0] + 255) / 256, (unsigned long long)c->sm_count * 8), 1);
-        peak_scale_kernel<T><<<grid, 256, 0, c->stream>>>(d_out, dp[4], dp[5], (const unsigned long long *)c->misc.p, level);
-        CUDA_TRY(cudaGetLastError());
-        c->launches++;
+        unsigned long long longest = 1;
+        for (const IShard &x : sh) longest = std::max(longest, x.out_len(N, hop));
+        AUS_TRY(irstft_k5<T>(c, sh.size(), longest, d_out));
     }
     return AUS_OK;
+}
+template <typename T>
+static int irstft_dev_t(aus_ctx *c, const Cx<T> *d_spec, size_t F, size_t N, size_t hop, int wtype, int normalize,
+                        int apply_window, T *d_out) {
+    const std::vector<IShard> one = {IShard{F, 0, 0, 0, F, 0}};
+    return irstft_shards_dev<T>(c, d_spec, F, one, N, hop, wtype, normalize, apply_window, d_out);
 }
 
 extern "C" int aus_spectral_features_generic(aus_ctx *c, const double *mags, size_t n_rows, size_t n_bins, const double *freqs,
@@ -1083,7 +1168,7 @@ extern "C" int aus_spectral_features_generic(aus_ctx *c, const double *mags, siz
     const double fund = (double)sr / ((double)(n_bins - 1) * 2.0);
     for (size_t b = 0; b < n_bands; ++b) {            // the reference slices power_spectrum[m_fl_ceil..m_fu_floor] and indexes
         const double m_fl = band_lo[b] / fund, m_fu = band_hi[b] / fund;      // [m_fu_ceil]: out of range -> it panics
-        if (!(m_fl >= 0.0) || !(m_fu >= m_fl) || !(std::ceil(m_fu) < (double)n_bins))
+        if (!(m_fl >= 0.0) || !(m_fu >= m_fl) || !(std::ceil(m_fu) < (double)n_bins) || std::ceil(m_fl) > std::floor(m_fu))
             return fail(AUS_ERR_INVALID, "slope band outside the spectrum (the reference panics: index out of bounds)");
     }
     for (size_t r = 0; r < n_roll; ++r)
@@ -1178,16 +1263,16 @@ extern "C" int aus_autocorrelation_batch(aus_ctx *c, const double *audio, size_t
     AUS_TRY(c->in64.ensure(nin * sizeof(double)));
     AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
     AUS_TRY(c->out64.ensure(npad * sizeof(double)));
-    AUS_TRY(c->pin64[0].ensure(npad * sizeof(double)));
+    AUS_TRY(c->acorr.ensure(npad * sizeof(double)));
     CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, nin * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const unsigned int grid = (unsigned int)std::min<size_t>((npad + 255) / 256, (size_t)c->sm_count * 16);
-    acorr_pad_kernel<<<grid, 256, 0, c->stream>>>((const double *)c->in64.p, (double *)c->pin64[0].p, n_chunks, (int)N);
+    acorr_pad_kernel<<<grid, 256, 0, c->stream>>>((const double *)c->in64.p, (double *)c->acorr.p, n_chunks, (int)N);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     Batch b;
     const uint64_t off0 = 0, len0 = npad;
     make_batch(b, &off0, &len0, 1, N2, N2);                    // n_chunks frames of exactly 2N samples
-    AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->pin64[0].p, b, N2, N2, AUS_WINDOW_RECTANGULAR, 44100, nullptr,
+    AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->acorr.p, b, N2, N2, AUS_WINDOW_RECTANGULAR, 44100, nullptr,
                                      (Cx<double> *)c->aux64.p));
     acorr_power_kernel<<<grid, 256, 0, c->stream>>>((double2 *)c->aux64.p, n_chunks * K2);
     CUDA_TRY(cudaGetLastError());
@@ -1308,8 +1393,54 @@ extern "C" int aus_plan_shards(const uint64_t *offsets, const uint64_t *lengths,
 
 // No collective: frames and files are independent.  Host threads, one per device, each running the batch
 // entry point on its run of virtual files; the ordered gather is the row offsets of the plan (like mp.rs:100-116).
+// Contexts are cached per (device, slot) and LOCKED for the whole call that uses them, so concurrent callers of the
+// multi-device entry points serialise per slot instead of sharing scratch buffers; aus_multi_shutdown() frees them.
+struct MultiSlot {
+    std::mutex mu;
+    aus_ctx *ctx = nullptr;
+};
 static std::mutex g_multi_mu;
-static std::map<std::pair<int, int>, aus_ctx *> g_multi_ctx;   // (device, slot): one context per host thread
+static std::map<std::pair<int, int>, MultiSlot *> g_multi_ctx;
+
+static MultiSlot *multi_slot(int dev, int slot) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    MultiSlot *&m = g_multi_ctx[{dev, slot}];
+    if (!m) m = new MultiSlot();
+    return m;
+}
+extern "C" int aus_multi_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    for (auto &kv : g_multi_ctx) {
+        std::lock_guard<std::mutex> lk2(kv.second->mu);
+        if (kv.second->ctx) aus_ctx_destroy(kv.second->ctx);
+        kv.second->ctx = nullptr;
+    }
+    return AUS_OK;
+}
+// runs fn(ctx, d) on one host thread per device slot with that slot's context locked; first error wins
+template <typename F> static int multi_run(const int *devices, int n_devices, F &&fn) {
+    if (n_devices < 1) return fail(AUS_ERR_INVALID, "n_devices must be >= 1");
+    std::vector<int> rc(n_devices, AUS_OK);
+    std::vector<std::string> msg(n_devices);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_devices; ++d) {
+        th.emplace_back([&, d]() {
+            const int dev = devices ? devices[d] : d;
+            MultiSlot *m = multi_slot(dev, d);
+            std::lock_guard<std::mutex> lk(m->mu);
+            if (!m->ctx) {
+                rc[d] = aus_ctx_create(dev, &m->ctx);
+                if (rc[d] != AUS_OK) { msg[d] = g_err; m->ctx = nullptr; return; }
+            }
+            rc[d] = fn(m->ctx, d);
+            if (rc[d] != AUS_OK) msg[d] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n_devices; ++d)
+        if (rc[d] != AUS_OK) return fail(rc[d], msg[d]);
+    return AUS_OK;
+}
 
 extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
                                        const uint64_t *lengths, size_t n_files, size_t N, size_t hop, int wtype, uint32_t sr,
@@ -1320,38 +1451,413 @@ extern "C" int aus_stft_features_multi(const int *devices, int n_devices, const 
     std::vector<int> vd(cap);
     size_t nv = 0;
     AUS_TRY(aus_plan_shards(offsets, lengths, n_files, N, hop, n_devices, vo.data(), vl.data(), vr.data(), vd.data(), cap, &nv));
-    std::vector<int> rc(n_devices, AUS_OK);
-    std::vector<std::string> msg(n_devices);
-    std::vector<std::thread> th;
-    for (int d = 0; d < n_devices; ++d) {
-        th.emplace_back([&, d]() {
-            size_t lo = nv, hi = 0;
-            for (size_t i = 0; i < nv; ++i)
-                if (vd[i] == d) { lo = std::min(lo, i); hi = std::max(hi, i + 1); }
-            if (lo >= hi) return;
-            const int dev = devices ? devices[d] : d;
-            aus_ctx *ctx = nullptr;
-            {
-                std::lock_guard<std::mutex> lk(g_multi_mu);
-                auto it = g_multi_ctx.find({dev, d});
-                if (it == g_multi_ctx.end()) {
-                    rc[d] = aus_ctx_create(dev, &ctx);
-                    if (rc[d] != AUS_OK) { msg[d] = g_err; return; }
-                    g_multi_ctx[{dev, d}] = ctx;
-                } else ctx = it->second;
-            }
-            uint64_t s0 = UINT64_MAX;                 // re-base the device's span to its first sample
-            for (size_t i = lo; i < hi; ++i) s0 = std::min(s0, vo[i]);
-            std::vector<uint64_t> o(hi - lo), l(hi - lo);
-            for (size_t i = lo; i < hi; ++i) { o[i - lo] = vo[i] - s0; l[i - lo] = vl[i]; }
-            rc[d] = aus_stft_features_batch(ctx, audio + s0, o.data(), l.data(), hi - lo, N, hop, wtype, sr, precision,
-                                            features + vr[lo] * 14, nullptr);
-            if (rc[d] != AUS_OK) msg[d] = g_err;
-        });
+    return multi_run(devices, n_devices, [&](aus_ctx *ctx, int d) -> int {
+        size_t lo = nv, hi = 0;
+        for (size_t i = 0; i < nv; ++i)
+            if (vd[i] == d) { lo = std::min(lo, i); hi = std::max(hi, i + 1); }
+        if (lo >= hi) return AUS_OK;
+        uint64_t s0 = UINT64_MAX;                 // re-base the device's span to its first sample
+        for (size_t i = lo; i < hi; ++i) s0 = std::min(s0, vo[i]);
+        std::vector<uint64_t> o(hi - lo), l(hi - lo);
+        for (size_t i = lo; i < hi; ++i) { o[i - lo] = vo[i] - s0; l[i - lo] = vl[i]; }
+        return aus_stft_features_batch(ctx, audio + s0, o.data(), l.data(), hi - lo, N, hop, wtype, sr, precision,
+                                       features + vr[lo] * 14, nullptr);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ irstft: batches and several devices
+// Several spectrograms (same fft_size / hop / window, any frame counts) in one K4 + one K5 launch: config 2's stereo pair
+// is one call.  Spectra rows and output signals are concatenated in file order.
+template <typename T>
+static int irstft_batch_dev_t(aus_ctx *c, const Cx<T> *d_spec, const uint64_t *n_frames, size_t n_files, size_t N, size_t hop,
+                              int wtype, int normalize, T *d_out) {
+    std::vector<IShard> sh;
+    unsigned long long row = 0, out = 0;
+    for (size_t i = 0; i < n_files; ++i) {
+        const unsigned long long F = n_frames[i];
+        sh.push_back(IShard{F, row, 0, 0, F, out});
+        row += F;
+        out += aus_irstft_len((size_t)F, N, hop);
     }
-    for (auto &t : th) t.join();
-    for (int d = 0; d < n_devices; ++d)
-        if (rc[d] != AUS_OK) return fail(rc[d], msg[d]);
+    return irstft_shards_dev<T>(c, d_spec, row, sh, N, hop, wtype, normalize, 1, d_out);
+}
+static int check_irstft_batch(aus_ctx *c, const uint64_t *n_frames, size_t n_files, size_t N, size_t hop, int wtype, int precision) {
+    AUS_TRY(check_common(c, N, hop, wtype, precision));
+    if (!n_frames || n_files == 0) return fail(AUS_ERR_INVALID, "no spectrograms");
+    for (size_t i = 0; i < n_files; ++i)
+        if (n_frames[i] == 0) return fail(AUS_ERR_INVALID, "empty spectrogram (the reference underflows at fft.rs:208)");
+    return AUS_OK;
+}
+extern "C" int aus_irstft_batch_dev(aus_ctx *c, const void *d_spec, const uint64_t *n_frames, size_t n_files, size_t N, size_t hop,
+                                    int wtype, int precision, int normalize, void *d_audio) {
+    AUS_TRY(check_irstft_batch(c, n_frames, n_files, N, hop, wtype, precision));
+    if (!d_spec || !d_audio) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_spec, precision, true, "d_spectra"));
+    AUS_TRY(check_dev_align(d_audio, precision, false, "d_audio"));
+    if (precision == AUS_F64) return irstft_batch_dev_t<double>(c, (const Cx<double> *)d_spec, n_frames, n_files, N, hop, wtype, normalize, (double *)d_audio);
+    return irstft_batch_dev_t<float>(c, (const Cx<float> *)d_spec, n_frames, n_files, N, hop, wtype, normalize, (float *)d_audio);
+}
+static int irstft_size_error(size_t N, size_t frame_len) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "The spectrum at frame %d has an incorrect length. It should be %zu, but it is actually %zu.",
+             0, N / 2 + 1, frame_len);                                               // fft.rs:218
+    return fail(AUS_ERR_SIZE, msg);
+}
+extern "C" int aus_irstft_batch(aus_ctx *c, const double *spectra, const uint64_t *n_frames, size_t n_files, size_t frame_len,
+                                size_t N, size_t hop, int wtype, int precision, int normalize, double *audio) {
+    AUS_TRY(check_irstft_batch(c, n_frames, n_files, N, hop, wtype, precision));
+    if (frame_len != N / 2 + 1) return irstft_size_error(N, frame_len);
+    if (!spectra || !audio) return fail(AUS_ERR_INVALID, "null argument");
+    const size_t K = N / 2 + 1;
+    size_t F = 0, nout = 0;
+    for (size_t i = 0; i < n_files; ++i) { F += n_frames[i]; nout += aus_irstft_len((size_t)n_frames[i], N, hop); }
+    const size_t nspec = F * K * 2;
+    AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
+    AUS_TRY(c->out64.ensure(nout * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->aux64.p, spectra, nspec * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (precision == AUS_F64) {
+        AUS_TRY(irstft_batch_dev_t<double>(c, (const Cx<double> *)c->aux64.p, n_frames, n_files, N, hop, wtype, normalize, (double *)c->out64.p));
+    } else {
+        AUS_TRY(c->aux32.ensure(nspec * sizeof(float)));
+        AUS_TRY(c->out32.ensure(nout * sizeof(float)));
+        AUS_TRY(cast_dev<double, float>(c, (const double *)c->aux64.p, (float *)c->aux32.p, nspec));
+        AUS_TRY(irstft_batch_dev_t<float>(c, (const Cx<float> *)c->aux32.p, n_frames, n_files, N, hop, wtype, normalize, (float *)c->out32.p));
+        AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nout));
+    }
+    CUDA_TRY(cudaMemcpyAsync(audio, c->out64.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+// irstft over several GPUs: every spectrogram is cut into contiguous frame ranges, one per device (whole
+// spectrograms per device when there are at least as many as devices).  A range recomputes the ceil(N/hop)-1 frames
+// before it (their rows are uploaded too) instead of exchanging partial sums; the one exchange step is the peak of
+// fft.rs:255-258: every device reports the signed max of its own samples, the host takes the max per spectrogram
+// (<= n_devices scalars each) and hands it back before the scale pass.  f64 only (the reference's arithmetic).
+extern "C" int aus_irstft_multi(const int *devices, int n_devices, const double *spectra, const uint64_t *n_frames, size_t n_files,
+                                size_t frame_len, size_t N, size_t hop, int wtype, int normalize, double *audio) {
+    if (n_devices < 1) return fail(AUS_ERR_INVALID, "n_devices must be >= 1");
+    AUS_TRY(check_fft_args(N, hop));
+    if (wtype < 0 || wtype > 4) return fail(AUS_ERR_INVALID, "unknown window type");
+    if (!n_frames || n_files == 0) return fail(AUS_ERR_INVALID, "no spectrograms");
+    for (size_t i = 0; i < n_files; ++i)
+        if (n_frames[i] == 0) return fail(AUS_ERR_INVALID, "empty spectrogram (the reference underflows at fft.rs:208)");
+    if (frame_len != N / 2 + 1) return irstft_size_error(N, frame_len);
+    if (!spectra || !audio) return fail(AUS_ERR_INVALID, "null argument");
+    const size_t K = N / 2 + 1;
+    const unsigned long long halo = (unsigned long long)((N + hop - 1) / hop) - 1;
+    // plan: (file, a, b) ranges in file order, then contiguous runs per device balanced by frame count
+    struct Range { size_t file; unsigned long long F, a, b, row_base, out_base; int dev; };
+    std::vector<Range> rg;
+    unsigned long long total = 0, row = 0, out = 0;
+    for (size_t i = 0; i < n_files; ++i) {
+        const unsigned long long F = n_frames[i];
+        const unsigned long long parts = (n_files >= (size_t)n_devices) ? 1 : std::min<unsigned long long>(F, (unsigned long long)n_devices);
+        for (unsigned long long s2 = 0; s2 < parts; ++s2) rg.push_back(Range{i, F, F * s2 / parts, F * (s2 + 1) / parts, row, out, 0});
+        total += F;
+        row += F;
+        out += aus_irstft_len((size_t)F, N, hop);
+    }
+    unsigned long long acc = 0;
+    for (Range &r : rg) {
+        const unsigned long long mid2 = 2 * acc + (r.b - r.a);
+        r.dev = (int)std::min<unsigned long long>((unsigned long long)n_devices - 1, mid2 * (unsigned long long)n_devices / (2 * total));
+        acc += r.b - r.a;
+    }
+    std::vector<std::vector<IShard>> dsh(n_devices);
+    std::vector<std::vector<size_t>> didx(n_devices);                 // indices into rg
+    for (size_t k = 0; k < rg.size(); ++k) {
+        const Range &r = rg[k];
+        std::vector<IShard> &v = dsh[r.dev];
+        unsigned long long ro = 0, oo = 0;
+        for (const IShard &x : v) { ro += x.b - x.row0; oo += x.out_len(N, hop); }
+        const unsigned long long r0 = r.a > halo ? r.a - halo : 0;
+        v.push_back(IShard{r.F, ro, r0, r.a, r.b, oo});
+        didx[r.dev].push_back(k);
+    }
+    std::vector<double> peaks(rg.size(), 0.0);
+    // phase 1: upload rows, K4, read back the per-range peaks
+    AUS_TRY(multi_run(devices, n_devices, [&](aus_ctx *c, int d) -> int {
+        const std::vector<IShard> &v = dsh[d];
+        if (v.empty()) return AUS_OK;
+        CUDA_TRY(cudaSetDevice(c->device));
+        unsigned long long rows = 0, outs = 0;
+        for (const IShard &x : v) { rows += x.b - x.row0; outs += x.out_len(N, hop); }
+        AUS_TRY(c->aux64.ensure(rows * K * 2 * sizeof(double)));
+        AUS_TRY(c->out64.ensure(outs * sizeof(double)));
+        for (size_t j = 0; j < v.size(); ++j) {
+            const Range &r = rg[didx[d][j]];
+            CUDA_TRY(cudaMemcpyAsync((double *)c->aux64.p + v[j].row_off * K * 2, spectra + (r.row_base + v[j].row0) * K * 2,
+                                     (v[j].b - v[j].row0) * K * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        AUS_TRY(irstft_k4<double>(c, (const Cx<double> *)c->aux64.p, rows, v, N, hop, wtype, 1, (double *)c->out64.p));
+        std::vector<unsigned long long> bits(v.size());
+        CUDA_TRY(cudaMemcpyAsync(bits.data(), c->misc.p, v.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (size_t j = 0; j < v.size(); ++j) memcpy(&peaks[didx[d][j]], &bits[j], sizeof(double));
+        return AUS_OK;
+    }));
+    // the exchange step: max per spectrogram over its ranges (positive doubles, 0.0 start: fft.rs:255-258)
+    std::vector<double> fpeak(n_files, 0.0);
+    for (size_t k = 0; k < rg.size(); ++k) fpeak[rg[k].file] = std::max(fpeak[rg[k].file], peaks[k]);
+    // phase 2: scale with the spectrogram's peak, download every range's own samples
+    return multi_run(devices, n_devices, [&](aus_ctx *c, int d) -> int {
+        const std::vector<IShard> &v = dsh[d];
+        if (v.empty()) return AUS_OK;
+        CUDA_TRY(cudaSetDevice(c->device));
+        if (normalize) {
+            std::vector<unsigned long long> bits(v.size());
+            unsigned long long longest = 1;
+            for (size_t j = 0; j < v.size(); ++j) {
+                memcpy(&bits[j], &fpeak[rg[didx[d][j]].file], sizeof(double));
+                longest = std::max(longest, v[j].out_len(N, hop));
+            }
+            CUDA_TRY(cudaMemcpyAsync(c->misc.p, bits.data(), v.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));           // bits is a temporary
+            AUS_TRY(irstft_k5<double>(c, v.size(), longest, (double *)c->out64.p));
+        }
+        for (size_t j = 0; j < v.size(); ++j) {
+            const Range &r = rg[didx[d][j]];
+            CUDA_TRY(cudaMemcpyAsync(audio + r.out_base + v[j].samp0(hop), (const double *)c->out64.p + v[j].out_off,
+                                     v[j].out_len(N, hop) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return AUS_OK;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ polar, device-resident
+// fft_tools.rs:21-55 / :131-188 on device pointers, stream-ordered: the edit loop of fft.rs:288-291
+// (rstft -> polar -> edit -> complex -> irstft) never leaves HBM.  f64, like the reference.
+extern "C" int aus_complex_to_polar_dev(aus_ctx *c, const void *d_spectra, size_t n, void *d_mag, void *d_ph) {
+    if (!c || !d_spectra || !d_mag) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_spectra, AUS_F64, true, "d_spectra"));
+    AUS_TRY(check_dev_align(d_mag, AUS_F64, false, "d_magnitudes"));
+    AUS_TRY(check_dev_align(d_ph, AUS_F64, false, "d_phases"));
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 16);
+    to_polar_kernel<<<grid, 256, 0, c->stream>>>((const double2 *)d_spectra, (double *)d_mag, (double *)d_ph, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+extern "C" int aus_polar_to_complex_dev(aus_ctx *c, const void *d_mag, const void *d_ph, size_t n, void *d_spectra) {
+    if (!c || !d_spectra || !d_mag || !d_ph) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_spectra, AUS_F64, true, "d_spectra"));
+    AUS_TRY(check_dev_align(d_mag, AUS_F64, false, "d_magnitudes"));
+    AUS_TRY(check_dev_align(d_ph, AUS_F64, false, "d_phases"));
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 16);
+    from_polar_kernel<<<grid, 256, 0, c->stream>>>((const double *)d_mag, (const double *)d_ph, (double2 *)d_spectra, n);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decoded PCM -> f64, mixdown
+// audiofile.rs:296-329: `sample as f64 / INTMAX` per channel; audiofile.rs:168-178 `mixdown`: channel 0 accumulates EVERY
+// channel including itself (so it is counted twice), in channel order, then divides by the channel count.  Both are
+// reproduced bit for bit (one thread per frame, the reference's operation order).
+template <typename I>
+__global__ void pcm_widen_kernel(const I *in, double *out, unsigned long long n_frames, int n_ch, int interleaved, int mix, double intmax) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        auto at = [&](int ch) -> double {
+            const I v = interleaved ? in[i * (unsigned long long)n_ch + ch] : in[(unsigned long long)ch * n_frames + i];
+            return (double)v / intmax;
+        };
+        if (!mix) {
+            for (int ch = 0; ch < n_ch; ++ch) out[(unsigned long long)ch * n_frames + i] = at(ch);
+        } else {
+            double s0 = at(0);
+            if (n_ch > 1) {                               // audiofile.rs:169: untouched when there is a single channel
+                for (int ch = 0; ch < n_ch; ++ch) s0 += at(ch);      // ch = 0 adds channel 0 to itself, :172
+                s0 /= (double)n_ch;                                   // :174
+            }
+            out[i] = s0;
+        }
+    }
+}
+__global__ void mixdown_kernel(const double *in, double *out, unsigned long long n_frames, int n_ch) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        double s0 = in[i];
+        if (n_ch > 1) {
+            for (int ch = 0; ch < n_ch; ++ch) s0 += in[(unsigned long long)ch * n_frames + i];
+            s0 /= (double)n_ch;
+        }
+        out[i] = s0;
+    }
+}
+static int pcm_intmax(int bits, double *intmax, size_t *bytes) {
+    switch (bits) {
+    case 8: *intmax = 127.0; *bytes = 1; return AUS_OK;                 // audiofile.rs:12 INTMAX8
+    case 16: *intmax = 32767.0; *bytes = 2; return AUS_OK;
+    case 24: *intmax = 8388607.0; *bytes = 4; return AUS_OK;
+    case 32: *intmax = 2147483647.0; *bytes = 4; return AUS_OK;
+    default: return fail(AUS_ERR_INVALID, "sample_bits must be 8 (int8_t), 16 (int16_t), 24 or 32 (int32_t)");
+    }
+}
+extern "C" int aus_pcm_to_f64_dev(aus_ctx *c, const void *d_pcm, int sample_bits, size_t n_frames, int n_channels,
+                                  int interleaved, int mixdown, void *d_out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    double intmax;
+    size_t bytes;
+    AUS_TRY(pcm_intmax(sample_bits, &intmax, &bytes));
+    if (n_channels < 1) return fail(AUS_ERR_INVALID, "n_channels must be >= 1");
+    if ((!d_pcm || !d_out) && n_frames) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_frames == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n_frames + 255) / 256, (size_t)c->sm_count * 16);
+    if (bytes == 1) pcm_widen_kernel<int8_t><<<grid, 256, 0, c->stream>>>((const int8_t *)d_pcm, (double *)d_out, n_frames, n_channels, interleaved, mixdown, intmax);
+    else if (bytes == 2) pcm_widen_kernel<int16_t><<<grid, 256, 0, c->stream>>>((const int16_t *)d_pcm, (double *)d_out, n_frames, n_channels, interleaved, mixdown, intmax);
+    else pcm_widen_kernel<int32_t><<<grid, 256, 0, c->stream>>>((const int32_t *)d_pcm, (double *)d_out, n_frames, n_channels, interleaved, mixdown, intmax);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+extern "C" int aus_pcm_to_f64(aus_ctx *c, const void *pcm, int sample_bits, size_t n_frames, int n_channels, int interleaved,
+                              int mixdown, double *out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    double intmax;
+    size_t bytes;
+    AUS_TRY(pcm_intmax(sample_bits, &intmax, &bytes));
+    if (n_channels < 1) return fail(AUS_ERR_INVALID, "n_channels must be >= 1");
+    if ((!pcm || !out) && n_frames) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_frames == 0) return AUS_OK;
+    const size_t nin = n_frames * (size_t)n_channels, nout = mixdown ? n_frames : nin;
+    AUS_TRY(c->ppcm[0].ensure(nin * bytes));
+    AUS_TRY(c->out64.ensure(nout * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->ppcm[0].p, pcm, nin * bytes, cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(aus_pcm_to_f64_dev(c, c->ppcm[0].p, sample_bits, n_frames, n_channels, interleaved, mixdown, c->out64.p));
+    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+// audiofile.rs:168-178 on f64 channels, planar [n_channels][n_frames] -> [n_frames]
+extern "C" int aus_mixdown_dev(aus_ctx *c, const void *d_channels, size_t n_frames, int n_channels, void *d_out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (n_channels < 1) return fail(AUS_ERR_INVALID, "n_channels must be >= 1");
+    if ((!d_channels || !d_out) && n_frames) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_frames == 0) return AUS_OK;
+    const unsigned int grid = (unsigned int)std::min<size_t>((n_frames + 255) / 256, (size_t)c->sm_count * 16);
+    mixdown_kernel<<<grid, 256, 0, c->stream>>>((const double *)d_channels, (double *)d_out, n_frames, n_channels);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+extern "C" int aus_mixdown(aus_ctx *c, const double *channels, size_t n_frames, int n_channels, double *out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (n_channels < 1) return fail(AUS_ERR_INVALID, "n_channels must be >= 1");
+    if ((!channels || !out) && n_frames) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_frames == 0) return AUS_OK;
+    AUS_TRY(c->in64.ensure(n_frames * (size_t)n_channels * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n_frames * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->in64.p, channels, n_frames * (size_t)n_channels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(aus_mixdown_dev(c, c->in64.p, n_frames, n_channels, c->out64.p));
+    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, n_frames * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-frame time-domain features
+// dc_bias, dbfs_max, energy, zero_crossing_rate (audio_analysis_tools.rs:22-108) of every STFT frame of a batch -- the
+// slice audio[h hop .. min(h hop + fft_size, len)) the frame loop of fft.rs:126-176 cuts -- in the row order of the
+// feature matrix.  One warp per frame, lanes stride the frame (coalesced), fixed shuffle tree: deterministic.
+__global__ void __launch_bounds__(256) frame_time_kernel(const double *audio, const unsigned long long *off, const unsigned long long *len,
+                                                         const unsigned long long *first, int n_files, unsigned long long total,
+                                                         int N, int hop, uint32_t sr, double *out) {
+    const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += warps) {
+        int lo = 0, hi = n_files - 1;                     // last file whose first frame is <= g (empty files own no frame)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (first[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const unsigned long long s = (g - first[lo]) * (unsigned long long)hop, n_all = len[lo];
+        const unsigned long long rem = n_all > s ? n_all - s : 0ull;
+        const int L = rem < (unsigned long long)N ? (int)rem : N;                  // fft.rs:130-144
+        const double *a = audio + off[lo] + s;
+        double sum = 0.0, sq = 0.0, mx = 0.0, zc = 0.0;
+        for (int i = lane; i < L; i += 32) {
+            const double x = a[i];
+            sum += x;
+            sq += x * x;
+            const double ax = fabs(x);
+            if (ax > mx) mx = ax;                         // NaN never wins, like `sample_abs > maxval`
+            if (i >= 1) {                                 // zero_crossing_rate's loop body, :100-106, inside the frame
+                if (a[i - 1] * x < 0.0) zc += 1.0;
+                else if (i + 1 < L && a[i + 1] < 0.0 && x == 0.0) zc += 1.0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const double m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+            mx = m2 > mx ? m2 : mx;
+            zc += __shfl_xor_sync(0xffffffffu, zc, o);
+        }
+        if (lane == 0) {
+            const double n = (double)L;
+            double *o4 = out + g * 4;
+            o4[0] = sum / n;                                                       // dc_bias, :22-28 (0/0 = NaN for an empty frame)
+            o4[1] = mx < 1e-20 ? -INFINITY : 20.0 * log10(mx);                     // dbfs_max, :55-65
+            o4[2] = L < 1 ? 0.0 : sqrt(1.0 / n * sq);                              // energy, :74-84
+            o4[3] = zc * (double)sr / n;                                           // zero_crossing_rate, :98-108
+        }
+    }
+}
+extern "C" int aus_time_features_frames_dev(aus_ctx *c, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
+                                            size_t n_files, size_t N, size_t hop, uint32_t sr, void *d_out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (hop == 0 || N == 0 || hop > N || N > (1u << 30)) return fail(AUS_ERR_INVALID, "bad frame size / hop");
+    if (!lengths || (!d_audio && n_files) || !d_out) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_audio, AUS_F64, false, "d_audio"));
+    AUS_TRY(check_dev_align(d_out, AUS_F64, false, "d_out"));
+    CUDA_TRY(cudaSetDevice(c->device));
+    Batch b;
+    make_batch(b, offsets, lengths, n_files, N, hop);
+    if (b.total_frames == 0) return AUS_OK;
+    std::vector<const unsigned long long *> dp;
+    AUS_TRY(upload_desc(c, c->desc, {&b.off, &b.len, &b.first}, dp));
+    const unsigned long long need = (b.total_frames + 7) / 8;
+    const unsigned int grid = (unsigned int)std::min<unsigned long long>(need, (unsigned long long)c->sm_count * 8);
+    frame_time_kernel<<<grid, 256, 0, c->stream>>>((const double *)d_audio, dp[0], dp[1], dp[2], (int)n_files, b.total_frames, (int)N,
+                                                   (int)hop, sr, (double *)d_out);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+extern "C" int aus_time_features_frames(aus_ctx *c, const double *audio, const uint64_t *offsets, const uint64_t *lengths,
+                                        size_t n_files, size_t N, size_t hop, uint32_t sr, double *out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (hop == 0 || N == 0 || hop > N || N > (1u << 30)) return fail(AUS_ERR_INVALID, "bad frame size / hop");
+    if (!lengths || (!audio && n_files) || !out) return fail(AUS_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Batch b;
+    make_batch(b, offsets, lengths, n_files, N, hop);
+    if (b.total_frames == 0) return AUS_OK;
+    AUS_TRY(c->in64.ensure(std::max<unsigned long long>(b.span, 1) * sizeof(double)));
+    AUS_TRY(c->out64.ensure(b.total_frames * 4 * sizeof(double)));
+    if (b.span) CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, b.span * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(aus_time_features_frames_dev(c, c->in64.p, offsets, lengths, n_files, N, hop, sr, c->out64.p));
+    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, b.total_frames * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+// host-pointer feature path: page-lock the caller's (pageable) input for the duration of the call so the chunked H2D
+// copies run as true asynchronous DMA (a Rust `Vec<f64>` is pageable memory).  -1 auto, 0 never, 1 always.
+extern "C" int aus_ctx_set_host_register(aus_ctx *c, int mode) {
+    if (!c || mode < -1 || mode > 1) return fail(AUS_ERR_INVALID, "bad argument");
+    c->hostreg_mode = mode;
     return AUS_OK;
 }
 

@@ -7,6 +7,7 @@
 #include "aus_stft_pc.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <string>
 
@@ -77,6 +78,11 @@ struct aus_ctx {
     void *log2tab = nullptr;               // LOG2_TAB x (1/c_i, -log2(1/c_i)) for the table-driven f64 log2
     DevBuf in64, in32, out64, out32, aux64, aux32, desc, misc, raw, normtab;
     long long normtab_key = -1;            // (fft_size, hop, window, precision) the reciprocal-norm table was built for
+    const unsigned long long *k5_out_off = nullptr, *k5_out_len = nullptr;   // K5 descriptors of the last irstft_k4 (in `desc`)
+    DevBuf acorr;                          // padded chunks of aus_autocorrelation_batch
+    void *hostreg_ptr = nullptr;           // caller buffer currently page-locked by the host pipeline (cudaHostRegister)
+    int hostreg_mode = -1;                 // -1 auto (register pageable inputs >= hostreg_min_bytes), 0 never, 1 always
+    size_t hostreg_min_bytes = (size_t)64 << 20;
     DevBuf pin64[2], pin32[2], pout64[2], pout32[2], ppcm[2];   // double buffers of the chunked host pipeline
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -85,7 +91,7 @@ struct aus_ctx {
 // ------------------------------------------------------------------------------------------------ launches
 template <typename T, int LG, bool RR, bool FEAT> int launch_stft_v(aus_ctx *c, const StftParams<T> &p) {
     using C = Cfg<T, LG, RR>;
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[64];
     auto kern = stft_kernel<T, LG, RR, FEAT>;
     const size_t smem = FEAT ? C::smem_bytes() : C::off_log();          // the spectra-only build carries no log2 table
     if (!attr_done[c->device & 63]) {
@@ -123,7 +129,7 @@ template <int LG> constexpr bool pc_built() { return LG == 11; }
 template <int LG> int launch_stft_pc(aus_ctx *c, const StftParams<double> &p) {
     if constexpr (pc_built<LG>()) {
         using C = CfgPC<LG>;
-        static bool attr_done[64] = {false};
+        static std::atomic<bool> attr_done[64];
         auto kern = stft_pc_kernel<LG>;
         const size_t smem = C::smem_bytes();
         if (!attr_done[c->device & 63]) {
@@ -151,7 +157,7 @@ template <typename T, int LG> int launch_stft_t(aus_ctx *c, const StftParams<T> 
 }
 template <typename T, int LG> int launch_analyzer_t(aus_ctx *c, const StftParams<T> &p) {
     using C = CfgA<T, LG>;
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[64];
     auto kern = analyzer_kernel<T, LG>;
     const size_t smem = C::smem_bytes();
     if (!attr_done[c->device & 63]) {
@@ -171,7 +177,7 @@ template <typename T, int LG> int launch_analyzer_t(aus_ctx *c, const StftParams
 }
 template <typename T, int LG> int launch_istft_t(aus_ctx *c, const IstftParams<T> &p) {
     using C = Cfg<T, LG>;
-    static bool attr_done[64] = {false};
+    static std::atomic<bool> attr_done[64];
     auto kern = istft_kernel<T, LG>;
     const size_t smem = C::off_log();                                     // no log2 table in the inverse kernel
     if (!attr_done[c->device & 63]) {

@@ -25,8 +25,14 @@ template <typename T> struct IstftParams {
     T *out;                                  // all files' outputs, contiguous
     const unsigned long long *seg_file;      // [n_seg] file index
     const unsigned long long *seg_a, *seg_b; // [n_seg] frame range inside the file
-    const unsigned long long *file_first;    // [n_files + 1] first global frame of each file
-    const unsigned long long *file_out_off;  // [n_files] first output sample of each file
+    // A "file" here is one spectrogram or one frame-range shard of it (multi-GPU irstft, aus_irstft_multi): rows
+    // [row0, ...) of the true spectrogram are present in `spec` starting at row file_first[file], and out[file_out_off]
+    // is output sample samp0 of the true signal.  Frame indices (seg_a, seg_b, h) are always those of the true file.
+    const unsigned long long *file_first;    // [n_files] row of `spec` that holds this file's frame row0
+    const unsigned long long *file_frames;   // [n_files] frames of the true spectrogram (fft.rs:208)
+    const unsigned long long *file_row0;     // [n_files] first frame present in `spec`
+    const unsigned long long *file_samp0;    // [n_files] output sample held by out[file_out_off[file]]
+    const unsigned long long *file_out_off;  // [n_files] first output sample of each file in `out`
     unsigned long long *file_max_bits;       // [n_files] bit pattern of max(out, 0.0) as f64 (fft.rs:255-258)
     unsigned long long n_seg;
     unsigned long long total_rows;           // rows of `spec` (f32: the array's last row is not over-read)
@@ -62,13 +68,16 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
         const bool seg_ok = sidx < p.n_seg;
         long long a = 0, b = 0, F = 0, h_begin = 0;
         unsigned long long gfirst = 0, ooff = 0;
+        long long row0 = 0, samp0 = 0;
         int file = 0;
         if (seg_ok) {
             file = (int)p.seg_file[sidx];
             a = (long long)p.seg_a[sidx];
             b = (long long)p.seg_b[sidx];
             gfirst = p.file_first[file];
-            F = (long long)(p.file_first[file + 1] - gfirst);
+            F = (long long)p.file_frames[file];
+            row0 = (long long)p.file_row0[file];
+            samp0 = (long long)p.file_samp0[file];
             ooff = p.file_out_off[file];
             h_begin = a - p.halo > 0 ? a - p.halo : 0;
         }
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
         for (long long st = 0; st < steps; ++st) {
             const long long h = h_begin + st;
             const bool active = seg_ok && h < b;
-            const Cx<T> *row = p.spec + (gfirst + (unsigned long long)(active ? h : 0)) * (unsigned long long)K;
+            const Cx<T> *row = p.spec + (gfirst + (unsigned long long)(active ? h - row0 : 0)) * (unsigned long long)K;
 #if AUS_L2_PREFETCH
             if (active && t == 0 && h + 1 < b && ((K * sizeof(Cx<T>)) % 16 == 0) && p.tma_ok)
                 prefetch_l2(row + K, (uint32_t)(K * sizeof(Cx<T>)));        // next frame of this segment -> L2
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             if constexpr (ROW16) {
                 use_tma = use_tma && (ra & 15) == 0;
             } else {
-                use_tma = use_tma && gfirst + (unsigned long long)h + 1 < p.total_rows;
+                use_tma = use_tma && gfirst + (unsigned long long)(h - row0) + 1 < p.total_rows;
                 if (use_tma) sh = (int)((ra & 15) >> 3);
             }
             constexpr uint32_t ROWB = (uint32_t)((K * sizeof(Cx<T>) + 15) & ~(size_t)15);     // f32: 8208 for either alignment
@@ -199,10 +208,10 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             // partial sum from earlier frames iff u < N - hop, complete after this frame iff u < hop -- so each pair is one
             // 16-byte read-modify-write, the window norm is a table multiply, and nothing is computed per sample.
             const bool fastf = active && p.fast_ok && h >= p.halo && h < F - 1 &&
-                               ((reinterpret_cast<uintptr_t>(p.out + ooff + h * hop) & (2 * sizeof(T) - 1)) == 0);
+                               ((reinterpret_cast<uintptr_t>(p.out + ooff + (h * hop - samp0)) & (2 * sizeof(T) - 1)) == 0);
             if (fastf) {
                 using V2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
-                T *outh = p.out + ooff + h * hop;
+                T *outh = p.out + ooff + (h * hop - samp0);
                 const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;     // owned range, relative (even)
                 const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);
                 const int nprev = N - p.hop;
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                     }
                 }
             } else if (active) {
-                T *outh = p.out + ooff + h * hop;
+                T *outh = p.out + ooff + (h * hop - samp0);
                 const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;
                 const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);
                 const bool first_frame = (h == 0), last_frame = (h == F - 1);

@@ -17,8 +17,12 @@
 //
 // Arithmetic differences to the single-role kernel (all inside the 1e-9 contract, tests/test_gpu_parity.py):
 //   * entropy and log-mean come from  S = sum p log2 p  and  L = sum log2 p  (no division by P per bin):
-//     sum q log2 q = S / P - log2 P,  sum log2 q = L - K log2 P;
-//   * log2 uses the same 128-entry table with a degree-3 minimax polynomial (|err| < 2e-11 per bin, unbiased);
+//     sum q log2 q = S / P - log2 P,  sum log2 q = L - K log2 P.  The difference carries an ABSOLUTE error of ~4e-15
+//     bits, so the 1e-9 relative contract holds for entropies above ~4e-6 bits (a frame whose power sits in one bin to
+//     better than -120 dB falls below that; the single-role kernels form q log2 q per bin and have no such floor) --
+//     one more reason this build is opt-in;
+//     (a degree-3 log2 polynomial, two FP64 operations per bin cheaper, was tried and dropped: its 1.5e-11 error per
+//     bin breaks the contract for entropies below ~0.01 bits; tools/fit_log2_poly.py has the fit);
 //   * sum p k comes from the first central moment: sum p k = sum p (k - kappa) + kappa P;
 //   * roll-off: the running sum at chunk ends lives in registers (warp scan); a threshold's chunk is found with two
 //     ballots, then one lane walks that chunk's 16 bins.  Knife edges fall back to the reference's own sequential
@@ -91,26 +95,6 @@ template <int NREG> __device__ __forceinline__ void reg_alloc() {
 }
 template <int NREG> __device__ __forceinline__ void reg_dealloc() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG));
-}
-
-// log2 of a positive normal double: table on the top 7 mantissa bits as in Mth<double>::log2_, degree-3 minimax
-// polynomial of log2(1 + r) / r on |r| <= 2^-8 (max |err| 1.5e-11; entropy and log-mean are sums over
-// 1025 bins compared at 1e-9 relative).  Two FP64 operations shorter than the degree-5 version, and ~50 cycles off the
-// dependency chain of every bin.
-static __constant__ double c_log2_d3[3] = {0.4809045735119559,       // r^2 of log2(1 + r) / r, minimax fit on |r| <= 2^-8
-                                           -0.7213520797435149,      // r^1
-                                           1.4426950408611363};      // r^0   (fit: tools/fit_log2_poly.py)
-__device__ __forceinline__ double log2_d3(double x, const double2 *tab) {
-    const unsigned hi = (unsigned)__double2hiint(x);
-    const double2 tc = tab[((hi >> 13) & (LOG2_TAB - 1)) * 8];
-    const double z = __hiloint2double((int)((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
-    const double ed = __hiloint2double(0x43300000, (int)(((hi >> 20) - 1023u) ^ 0x80000000u)) - c_log2_k[5];
-    const double r = fma(z, tc.x, -1.0);
-    double pl = fma(r, c_log2_d3[0], c_log2_d3[1]);
-    pl = fma(pl, r, c_log2_d3[2]);
-    // fit error of r * poly(r) against log2(1 + r): max 1.5e-11, mean -6e-12 (tools/fit_log2_poly.py); entropy and
-    // flatness are compared at 1e-9 relative
-    return fma(pl, r, ed + tc.y);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -347,7 +331,7 @@ __device__ __forceinline__ void pc_consumer(const double *pwb, const double2 *lo
 #pragma unroll
         for (int c = 0; c < PW; ++c) pv[c] = src[c * step];
 #pragma unroll
-        for (int c = 0; c < PW; ++c) l[c] = log2_d3(pv[c], ltab);
+        for (int c = 0; c < PW; ++c) l[c] = Mth<double>::log2_(pv[c], ltab);
 #pragma unroll
         for (int c = 0; c < PW; ++c) {
             const double d = d0 + (double)c;
@@ -376,7 +360,7 @@ __device__ __forceinline__ void pc_consumer(const double *pwb, const double2 *lo
         mid = pwb[C::MID];
         const double d = (double)(M / 2) - kappa;
         const double dd = d * d, w2 = dd * mid;
-        const double l = log2_d3(mid, ltab);
+        const double l = Mth<double>::log2_(mid, ltab);
         d1s = fma(mid, d, d1s);
         d2s += w2;
         d3s = fma(w2, d, d3s);

@@ -92,11 +92,16 @@ uint64_t aus_ctx_launch_count(const aus_ctx *ctx);
 int aus_ctx_set_direct_load(aus_ctx *ctx, int on);
 /* forward-kernel variant: -1 (default) = chosen per fft_size / precision / outputs from B200 measurements,
  * 0 = shared-memory tail, 1 = register-resident tail (last FFT pass, real-FFT split and |X|^2 stay in registers; spectra
- * are stored straight from them).  Results agree to rounding (same arithmetic, different summation grouping).
- * The environment variable AUS_B200_RR=0|1 sets the initial value. */
+ * are stored straight from them), 2 = producer/consumer warps for f64 features at fft_size 2048 (FFT warps hand the power
+ * row to feature warps; measured slower than mode 0, kept as a documented experiment).  Results agree to rounding (same
+ * arithmetic, different summation grouping).  The environment variable AUS_B200_RR=0|1|2 sets the initial value. */
 int aus_ctx_set_forward_variant(aus_ctx *ctx, int mode);
 /* granularity (samples) of the host-pointer feature path's copy/compute pipeline; default 32 Mi samples (256 MB f64) */
 int aus_ctx_set_chunk_samples(aus_ctx *ctx, uint64_t n_samples);
+/* host-pointer feature calls (mp.rs:26 hands over a pageable `Vec<f64>`): page-lock a pageable input for the duration of
+ * the call (cudaHostRegister) so the chunked H2D copies are asynchronous DMA.  -1 (default) = inputs of at least 64 MB,
+ * 0 = never (the driver stages through its own pinned buffers), 1 = always.  Already pinned inputs are used as they are. */
+int aus_ctx_set_host_register(aus_ctx *ctx, int mode);
 
 /* ---- pure host helpers ------------------------------------------------------------------------------- */
 /* frame count of the loop in spectrum/fft.rs:126-176 (strict `<` at :131; len <= fft_size -> 1 frame) */
@@ -129,10 +134,10 @@ int aus_stft_features_batch(aus_ctx *ctx, const double *audio, const uint64_t *o
 int aus_stft_features_batch_dev(aus_ctx *ctx, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
                                 size_t n_files, size_t fft_size, size_t hop, int window_type, uint32_t sample_rate,
                                 int precision, void *d_features, void *d_spectra);
-/* SURVEY 8(f) item 4 -- decoded integer PCM straight from the codec: the samples are uploaded as they are (2 or 4
+/* SURVEY 8(f) item 4 -- decoded integer PCM straight from the codec: the samples are uploaded as they are (1, 2 or 4
  * bytes each) and widened on the device exactly like the reader does, `sample as f64 / INTMAX` with INTMAX = 2^(bits-1)-1
- * (audiofile.rs:12-15, :296-329).  sample_bits 16: `pcm` is int16_t[]; 24 or 32: int32_t[].  Same batch layout and
- * output as aus_stft_features_batch. */
+ * (audiofile.rs:12-15, :296-329).  sample_bits 8: `pcm` is int8_t[]; 16: int16_t[]; 24 or 32: int32_t[].  Same batch
+ * layout and output as aus_stft_features_batch. */
 int aus_stft_features_batch_pcm(aus_ctx *ctx, const void *pcm, int sample_bits, const uint64_t *offsets,
                                 const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop, int window_type,
                                 uint32_t sample_rate, int precision, double *features, uint64_t *frame_starts);
@@ -144,6 +149,10 @@ uint64_t aus_batch_num_frames(const uint64_t *lengths, size_t n_files, size_t ff
 int aus_stft_features_multi(const int *devices, int n_devices, const double *audio, const uint64_t *offsets,
                             const uint64_t *lengths, size_t n_files, size_t fft_size, size_t hop, int window_type,
                             uint32_t sample_rate, int precision, double *features);
+
+/* the multi-device entry points (aus_stft_features_multi, aus_irstft_multi) cache one context per (device, slot) and hold
+ * its lock for the duration of a call; this frees them (call it when no multi-device call is in flight). */
+int aus_multi_shutdown(void);
 
 /* pure host: the shard plan aus_stft_features_multi uses (also for callers that drive the devices themselves, e.g. one
  * process per GPU).  Virtual file v = samples [vf_off[v], vf_off[v]+vf_len[v]) of the caller's buffer; its frames are
@@ -166,6 +175,11 @@ int aus_rfft(aus_ctx *ctx, const double *audio, size_t fft_size, int precision, 
 /* ---- polar conversion on device (spectrum/fft_tools.rs:21-55, :131-188) ------------------------------- */
 int aus_complex_to_polar(aus_ctx *ctx, const double *spectra, size_t n_bins_total, double *magnitudes, double *phases);
 int aus_polar_to_complex(aus_ctx *ctx, const double *magnitudes, const double *phases, size_t n_bins_total, double *spectra);
+/* device-pointer variants (f64, stream-ordered, no sync; d_phases may be NULL in the forward direction): the edit loop of
+ * spectrum/fft.rs:288-291 -- rstft -> complex_to_polar_rstft -> (edit) -> polar_to_complex_rstft -> irstft -- stays in HBM
+ * between aus_rstft_dev and aus_irstft_dev. */
+int aus_complex_to_polar_dev(aus_ctx *ctx, const void *d_spectra, size_t n_bins_total, void *d_magnitudes, void *d_phases);
+int aus_polar_to_complex_dev(aus_ctx *ctx, const void *d_magnitudes, const void *d_phases, size_t n_bins_total, void *d_spectra);
 
 /* ---- features from caller-supplied magnitude spectra (kernel K3) ------------------------------------- */
 /* analysis/analyzer.rs:41 `analyzer` over a batch of rows; each row has fft_size/2+1 magnitudes */
@@ -195,6 +209,19 @@ int aus_irstft(aus_ctx *ctx, const double *spectra, size_t n_frames, size_t fram
                int window_type, int precision, int normalize, double *audio /* aus_irstft_len */);
 int aus_irstft_dev(aus_ctx *ctx, const void *d_spectra, size_t n_frames, size_t fft_size, size_t hop,
                    int window_type, int precision, int normalize, void *d_audio);
+/* several spectrograms of the same fft_size / hop / window in one launch (config 2's stereo pair): rows and output signals
+ * are concatenated in order; spectrogram i has n_frames[i] rows and yields aus_irstft_len(n_frames[i]) samples, each
+ * peak-normalised on its own (fft.rs:255-265). */
+int aus_irstft_batch(aus_ctx *ctx, const double *spectra, const uint64_t *n_frames, size_t n_spectrograms, size_t frame_len,
+                     size_t fft_size, size_t hop, int window_type, int precision, int normalize, double *audio);
+int aus_irstft_batch_dev(aus_ctx *ctx, const void *d_spectra, const uint64_t *n_frames, size_t n_spectrograms, size_t fft_size,
+                         size_t hop, int window_type, int precision, int normalize, void *d_audio);
+/* irstft sharded over several GPUs of one box: contiguous frame ranges (whole spectrograms when there are at least as many
+ * as devices); a range recomputes the ceil(fft_size/hop)-1 frames before it instead of exchanging partial sums, and the
+ * only exchange is the host-side max over the ranges' peaks before the scale pass (fft.rs:255-265).  f64.
+ * devices == NULL -> devices 0..n_devices-1.  Same layout as aus_irstft_batch. */
+int aus_irstft_multi(const int *devices, int n_devices, const double *spectra, const uint64_t *n_frames, size_t n_spectrograms,
+                     size_t frame_len, size_t fft_size, size_t hop, int window_type, int normalize, double *audio);
 /* spectrum/fft.rs:66 `irfft` (output is fft_size x the signal: rustfft does not normalise) */
 int aus_irfft(aus_ctx *ctx, const double *spectrum, size_t spectrum_len, size_t fft_size, int precision,
               double *audio /* fft_size */);
@@ -208,6 +235,26 @@ int aus_autocorrelation_batch(aus_ctx *ctx, const double *audio, size_t n_chunks
  * zero_crossing_rate} */
 int aus_time_features_batch(aus_ctx *ctx, const double *audio, const uint64_t *offsets, const uint64_t *lengths,
                             size_t n_files, uint32_t sample_rate, double *out /* n_files x 4 */);
+
+/* the same four scalars of every STFT frame of a batch -- the slice audio[h*hop .. min(h*hop + fft_size, len)) that the
+ * frame loop of spectrum/fft.rs:126-176 cuts -- in the row order of the feature matrix: out[frame] = {dc_bias, dbfs_max,
+ * energy, zero_crossing_rate}. */
+int aus_time_features_frames(aus_ctx *ctx, const double *audio, const uint64_t *offsets, const uint64_t *lengths, size_t n_files,
+                             size_t fft_size, size_t hop, uint32_t sample_rate, double *out /* total_frames x 4 */);
+int aus_time_features_frames_dev(aus_ctx *ctx, const void *d_audio, const uint64_t *offsets, const uint64_t *lengths,
+                                 size_t n_files, size_t fft_size, size_t hop, uint32_t sample_rate, void *d_out);
+/* SURVEY 8(f) item 4, input side: decoded integer PCM -> f64 channels as the reader does (audiofile.rs:296-329,
+ * `sample as f64 / INTMAX`; sample_bits 8 / 16 / 24 / 32 as above), from interleaved ([frame][channel]) or planar
+ * ([channel][frame]) samples, and `mixdown` (audiofile.rs:168-178) fused in when mixdown != 0: channel 0 accumulates
+ * every channel INCLUDING ITSELF, in channel order, then divides by the channel count (the reference's arithmetic, bit
+ * for bit; a single channel is left untouched).  out: planar [n_channels][n_frames], or [n_frames] after mixdown. */
+int aus_pcm_to_f64(aus_ctx *ctx, const void *pcm, int sample_bits, size_t n_frames, int n_channels, int interleaved,
+                   int mixdown, double *out);
+int aus_pcm_to_f64_dev(aus_ctx *ctx, const void *d_pcm, int sample_bits, size_t n_frames, int n_channels, int interleaved,
+                       int mixdown, void *d_out);
+/* audiofile.rs:168-178 `mixdown` on f64 channels, planar [n_channels][n_frames] -> [n_frames] */
+int aus_mixdown(aus_ctx *ctx, const double *channels, size_t n_frames, int n_channels, double *out);
+int aus_mixdown_dev(aus_ctx *ctx, const void *d_channels, size_t n_frames, int n_channels, void *d_out);
 
 /* ---- synthetic input generator used by the benchmark (synthesis.rs:50-59 sine + counter noise) --- */
 int aus_synth_dev(aus_ctx *ctx, void *d_audio, uint64_t n_samples, uint64_t n0, uint32_t sample_rate, double freq,

@@ -466,6 +466,42 @@ def zero_crossing_rate(audio, sample_rate: int) -> float:
     return float(num) * float(sample_rate) / float(n)
 
 
+# ------------------------------------------------------------------------------------------------ audiofile.rs (input side)
+INTMAX = {8: float(2 ** 7 - 1), 16: float(2 ** 15 - 1), 24: float(2 ** 23 - 1), 32: float(2 ** 31 - 1)}   # audiofile.rs:12-15
+
+
+def pcm_to_f64(pcm, sample_bits: int) -> np.ndarray:
+    """audiofile.rs:296-329: ``sample as f64 / INTMAX`` (IEEE division), any array shape."""
+    return np.asarray(pcm).astype(np.float64) / INTMAX[int(sample_bits)]
+
+
+def mixdown(channels) -> np.ndarray:
+    """audiofile.rs:168-178 on ``[n_channels][n_frames]``: with more than one channel, channel 0 accumulates EVERY channel
+    in channel order -- itself included, so it is counted twice -- and is then divided by the channel count."""
+    ch = np.asarray(channels, dtype=np.float64)
+    if ch.ndim == 1:
+        ch = ch[None, :]
+    out = ch[0].copy()
+    if ch.shape[0] > 1:                                   # :169
+        for c in range(ch.shape[0]):                      # :171-173 (c = 0 adds channel 0 to itself)
+            out = out + ch[c]
+        out = out / float(ch.shape[0])                    # :174
+    return out
+
+
+def time_features_frames(audio, fft_size: int, hop_size: int, sample_rate: int) -> np.ndarray:
+    """dc_bias, dbfs_max, energy, zero_crossing_rate (audio_analysis_tools.rs:22-108) of every slice the frame loop of
+    fft.rs:126-176 cuts: ``audio[h*hop : min(h*hop + fft_size, len)]`` -> ``[frames, 4]``."""
+    x = np.asarray(audio, dtype=np.float64)
+    F = num_frames(x.size, fft_size, hop_size)
+    out = np.empty((F, 4))
+    with np.errstate(all="ignore"):
+        for h in range(F):
+            seg = x[h * hop_size: h * hop_size + fft_size]
+            out[h] = (dc_bias(seg) if seg.size else np.nan, dbfs_max(seg), energy(seg),
+                      zero_crossing_rate(seg, sample_rate) if seg.size else np.nan)
+    return out
+
 # --------------------------------------------------------------------------- synthetic inputs (SURVEY 8d)
 _M64 = (1 << 64) - 1
 

@@ -471,11 +471,12 @@ def test_randomised_parameter_sweep(ctx, orc):
                 assert np.max(np.abs(got32 - ref)) <= RTOL32 * max(np.max(np.abs(ref)), 1e-300), what + " f32"
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("fft_size,hop", [(64, 16), (128, 32), (256, 64), (512, 128), (1024, 256), (2048, 512), (2048, 300),
                                           (4096, 1024), (8192, 2048), (16384, 4096)])
 def test_forward_kernel_variants(ctx, orc, variant, fft_size, hop):
-    """Both forward kernels -- shared-memory tail (0) and register-resident tail (1, aus_stft_r.cuh) -- against the
+    """The forward kernels -- shared-memory tail (0), register-resident tail (1, aus_stft_r.cuh) and the producer/consumer
+    build (2, aus_stft_pc.cuh: f64 features-only launches at fft_size 2048, the default choice elsewhere) -- against the
     oracle, f64 and f32, features + spectra in one call, ragged files incl. silence and a short last frame."""
     import torch
     ctx.use_torch_stream()
@@ -658,3 +659,220 @@ def test_device_entry_points_stay_inside_their_buffers(ctx, orc, prec, fft_size,
         ctx.irstft_dev(odd, F, N, hop, orc.HAMMING, prec, view["rec"], True)
     with pytest.raises(Exception, match="aligned"):
         ctx.stft_features_batch_dev(view["audio"], [0], [n], N, hop, orc.HAMMING, SR, prec, None, odd)
+
+
+# ------------------------------------------------------------------------------------------------ round 2 additions
+def test_producer_consumer_kernel_edge_cases(aus, orc):
+    """aus_stft_pc.cuh on its own context (variant 2): every window, odd hops / unaligned starts (cooperative staging),
+    silence, zero bins, a short last frame, one-frame files, and roll-off knife edges through the fused path."""
+    c = aus.Context(0)
+    c.set_forward_variant(2)
+    try:
+        for window in range(5):
+            x = orc.synth_signal(40000 + 17 * window, SR, seed=51, file_id=window)
+            assert_features(c.stft_features(x, 2048, 512, window, SR), orc.stft_features(x, 2048, 512, window, SR), RTOL64,
+                            f"pc window {window}")
+        for hop, n in ((511, 30001), (1, 2300), (2048, 10000), (300, 2047), (512, 2049)):
+            x = orc.synth_signal(n, SR, seed=52, file_id=hop)
+            S = orc.rstft(x, 2048, hop, orc.HAMMING)
+            sc = cancellation_scales(np.abs(np.nan_to_num(S)), 2048, SR)
+            assert_features(c.stft_features(x, 2048, hop, orc.HAMMING, SR), orc.stft_features(x, 2048, hop, orc.HAMMING, SR), RTOL64,
+                            f"pc hop {hop}", scales=sc)
+        x = np.zeros(9000)
+        x[6000:] = orc.synth_signal(3000, SR, seed=53)
+        assert_features(c.stft_features(x, 2048, 512, orc.HANNING, SR), orc.stft_features(x, 2048, 512, orc.HANNING, SR), RTOL64, "pc silence")
+        # a tone on a bin centre with a rectangular window over a -50 dB floor: one bin carries nearly all the power (entropy
+        # ~1e-4 bits: this kernel forms it as log2 P - S / P, whose absolute error is ~4e-15, see aus_stft_pc.cuh)
+        n = np.arange(8192)
+        tone = np.sin(2 * np.pi * 64 * n / 2048) + 3e-2 * orc.synth_signal(8192, SR, seed=54)
+        ref = orc.stft_features(tone, 2048, 512, orc.RECTANGULAR, SR)
+        got = c.stft_features(tone, 2048, 512, orc.RECTANGULAR, SR)
+        sc = cancellation_scales(np.abs(orc.rstft(tone, 2048, 512, orc.RECTANGULAR)), 2048, SR)
+        assert np.array_equal(got[:, ROLL], ref[:, ROLL])
+        assert_features(got, ref, RTOL64, "pc tone over a floor", scales=sc)
+        lens = [2048, 0, 1, 2049, 5000, 2047]
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        a = orc.synth_signal(sum(lens), SR, seed=55)
+        got, starts = c.stft_features_batch(a, offs, lens, 2048, 512, orc.BLACKMAN, SR)
+        for i, (o, ln) in enumerate(zip(offs, lens)):
+            S = orc.rstft(a[o:o + ln], 2048, 512, orc.BLACKMAN)
+            sc = cancellation_scales(np.abs(np.nan_to_num(S)), 2048, SR)
+            assert_features(got[starts[i]:starts[i + 1]], orc.stft_features(a[o:o + ln], 2048, 512, orc.BLACKMAN, SR), RTOL64,
+                            f"pc file {i}", scales=sc)
+    finally:
+        c.close()
+
+
+def test_irstft_batch_and_frame_range_shards(ctx, aus, orc):
+    """aus_irstft_batch (several spectrograms, one launch; config 2's stereo pair) and aus_irstft_multi (frame-range shards
+    with recomputed halo + host max over the shard peaks).  On a 1-GPU box every slot maps to device 0; the
+    shard arithmetic is the same."""
+    import torch
+    have = torch.cuda.device_count()
+    for N, hop, window in ((4096, 1024, orc.HAMMING), (2048, 512, orc.HANNING), (1024, 1000, orc.HAMMING), (256, 64, orc.BARTLETT)):
+        xs = [orc.synth_signal(n, SR, seed=61, file_id=i) for i, n in enumerate((37 * hop + N + 5, N, 9 * N + 1))]
+        S = [orc.rstft(x, N, hop, window) for x in xs]
+        ref = [orc.irstft(s, N, hop, window) for s in S]
+        got = ctx.irstft_batch(S, N, hop, window)
+        for g, r in zip(got, ref):
+            assert g.shape == r.shape and np.array_equal(np.isnan(g), np.isnan(r))
+            fin = np.isfinite(r)
+            assert np.max(np.abs(g[fin] - r[fin])) <= RTOL64 * np.max(np.abs(r[fin]))
+        for n_dev in (1, 2, 3, 5):
+            devices = [i % have for i in range(n_dev)]
+            for specs, refs in ((S[:1], ref[:1]), (S, ref)):               # one long file by frame range; a batch
+                got = aus.irstft_multi(devices, specs, N, hop, window)
+                for g, r in zip(got, refs):
+                    assert g.shape == r.shape and np.array_equal(np.isnan(g), np.isnan(r)), (N, n_dev)
+                    fin = np.isfinite(r)
+                    assert np.max(np.abs(g[fin] - r[fin])) <= RTOL64 * np.max(np.abs(r[fin])), (N, n_dev)
+        # the un-normalised output of a sharded run is BIT-identical to the single-device one (same frames, same order)
+        one = aus.irstft_multi([0], S[:1], N, hop, window, normalize=False)[0]
+        four = aus.irstft_multi([i % have for i in range(4)], S[:1], N, hop, window, normalize=False)[0]
+        assert np.array_equal(one, four, equal_nan=True)
+    aus.multi_shutdown()
+
+
+def test_multi_gpu_entry_points_on_distinct_devices(aus, orc):
+    """The product's own multi-GPU entry points with every slot on a DIFFERENT device (skipped on a 1-GPU box): row order
+    across devices, frame-range halo, host gather."""
+    import torch
+    have = torch.cuda.device_count()
+    if have < 2:
+        pytest.skip("needs at least 2 GPUs")
+    devices = list(range(min(have, 8)))
+    x = orc.synth_signal(40 * 4096 + 1234, SR, seed=71)
+    got = aus.stft_features_multi(devices, x, [0], [x.size], 16384, 4096, orc.HANNING, SR)            # config-4 shape, by frame range
+    assert_features(got, orc.stft_features(x, 16384, 4096, orc.HANNING, SR), RTOL64, "multi single file, distinct devices")
+    lens = [30 * 441, 0, 12000, 2048, 30000, 5, 44100, 7000, 1024, 9999]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    audio = orc.synth_signal(sum(lens), SR, seed=72)
+    got = aus.stft_features_multi(devices, audio, offs, lens, 1024, 256, orc.HANNING, SR)                  # config-3 shape, by file
+    ref = np.concatenate([orc.stft_features(audio[o:o + n], 1024, 256, orc.HANNING, SR) for o, n in zip(offs, lens)])
+    assert_features(got, ref, RTOL64, "multi batch, distinct devices")
+    S = [orc.rstft(orc.synth_signal(50 * 1024 + 4096, SR, seed=73, file_id=ch), 4096, 1024, orc.HAMMING) for ch in range(2)]
+    for specs in (S[:1], S):
+        got = aus.irstft_multi(devices, specs, 4096, 1024, orc.HAMMING)
+        for g, s in zip(got, specs):
+            r = orc.irstft(s, 4096, 1024, orc.HAMMING)
+            assert np.max(np.abs(g - r)) <= RTOL64 * np.max(np.abs(r))
+    aus.multi_shutdown()
+
+
+def test_polar_edit_loop_stays_on_device(ctx, orc):
+    """rstft -> complex_to_polar -> edit -> polar_to_complex -> irstft (fft.rs:288-291) with device pointers
+    only; the one host copy is the final comparison."""
+    import torch
+    ctx.use_torch_stream()
+    N, hop = 1024, 256
+    x = orc.synth_signal(30000, SR, seed=81)
+    F, K = orc.num_frames(x.size, N, hop), N // 2 + 1
+    d_x = torch.from_numpy(x).cuda()
+    spec = torch.empty((F, K, 2), dtype=torch.float64, device="cuda")
+    mag, ph = (torch.empty((F, K), dtype=torch.float64, device="cuda") for _ in range(2))
+    ctx.stft_features_batch_dev(d_x, [0], [x.size], N, hop, orc.HAMMING, SR, "f64", None, spec)
+    ctx.complex_to_polar_dev(spec, mag, ph)
+    gain = torch.linspace(1.0, 0.25, K, dtype=torch.float64, device="cuda")
+    mag *= gain                                                        # the "edit": a spectral tilt, on the device
+    spec2 = torch.empty_like(spec)
+    ctx.polar_to_complex_dev(mag, ph, spec2)
+    y = torch.empty(N + hop * (F - 1), dtype=torch.float64, device="cuda")
+    ctx.irstft_dev(spec2, F, N, hop, orc.HAMMING, "f64", y, True)
+    torch.cuda.synchronize()
+    S = orc.rstft(x, N, hop, orc.HAMMING)
+    m_ref, p_ref = orc.complex_to_polar_rstft(S)
+    assert np.max(np.abs(ph.cpu().numpy() - p_ref)) <= 1e-12
+    ref = orc.irstft(orc.polar_to_complex_rstft(m_ref * np.linspace(1.0, 0.25, K), p_ref), N, hop, orc.HAMMING)
+    assert np.max(np.abs(y.cpu().numpy() - ref)) <= RTOL64 * np.max(np.abs(ref))
+    mag_only = torch.empty_like(mag)
+    ctx.complex_to_polar_dev(spec, mag_only, None)                     # phases are optional (the analyzer path drops them)
+    torch.cuda.synchronize()
+    assert np.max(np.abs(mag_only.cpu().numpy() - m_ref)) <= RTOL64 * np.max(m_ref)
+
+
+def test_pcm_widths_and_mixdown_are_bit_exact(ctx, orc):
+    """`sample as f64 / INTMAX` for S8 / S16 / S24 / S32 (audiofile.rs:296-329) and `mixdown` with the
+    reference's double count of channel 0 (audiofile.rs:168-178): integer -> f64 division and the adds are exact ops, so
+    the device must reproduce the oracle bit for bit."""
+    rng = np.random.default_rng(91)
+    for dtype, bits in ((np.int8, 8), (np.int16, 16), (np.int32, 24), (np.int32, 32)):
+        lim = 2 ** (bits - 1)
+        for n_ch in (1, 2, 3, 6):
+            pcm = rng.integers(-lim, lim, size=(4097, n_ch)).astype(dtype)           # interleaved [frame][channel]
+            wide = orc.pcm_to_f64(pcm.T, bits)
+            assert np.array_equal(ctx.pcm_to_f64(pcm, n_ch, True, False, sample_bits=bits), wide)
+            assert np.array_equal(ctx.pcm_to_f64(np.ascontiguousarray(pcm.T), n_ch, False, False, sample_bits=bits), wide)
+            assert np.array_equal(ctx.pcm_to_f64(pcm, n_ch, True, True, sample_bits=bits), orc.mixdown(wide))
+            assert np.array_equal(ctx.mixdown(wide), orc.mixdown(wide))
+    two = np.array([[0.25, -0.5, 1.0], [0.5, 0.25, -1.0]])
+    assert np.array_equal(ctx.mixdown(two), (two[0] + two[0] + two[1]) / 2.0)          # channel 0 twice, as in the reference
+    assert np.array_equal(ctx.mixdown(two[0]), two[0])                                  # a single channel is left alone
+    # S8 through the fused feature path
+    x = orc.synth_signal(20000, SR, seed=92)
+    pcm8 = np.round(x * 127).astype(np.int8)
+    got, _ = ctx.stft_features_batch_pcm(pcm8, [0], [pcm8.size], 1024, 256, orc.HANNING, SR)
+    assert_features(got, orc.stft_features(orc.pcm_to_f64(pcm8, 8), 1024, 256, orc.HANNING, SR), RTOL64, "pcm8")
+
+
+def test_time_features_per_frame(ctx, orc):
+    """dc_bias / dbfs_max / energy / zero_crossing_rate of every STFT frame (the slice the frame loop cuts),
+    rows aligned with the feature matrix; ragged batch, short last frames, exact zeros, silence, many files."""
+    lens = [9000, 0, 2048, 2049, 1, 30000, 777]
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    a = orc.synth_signal(sum(lens), SR, seed=95)
+    a[offs[5] + 100:offs[5] + 140] = 0.0                     # exact zeros: second zero-crossing rule, dbfs of silence
+    a[offs[5] + 140] = -0.2
+    a[offs[5] + 4096:offs[5] + 4096 + 2048] = 0.0            # a silent frame: dbfs_max = -inf
+    for N, hop in ((2048, 512), (1024, 1024), (4096, 1000)):
+        got = ctx.time_features_frames(a, offs, lens, N, hop, SR)
+        ref = np.concatenate([orc.time_features_frames(a[o:o + n], N, hop, SR) for o, n in zip(offs, lens)])
+        assert got.shape == ref.shape
+        assert np.array_equal(got[:, 3], ref[:, 3], equal_nan=True)              # counts: exact
+        assert np.array_equal(np.isinf(got[:, 1]), np.isinf(ref[:, 1]))
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        fin = np.isfinite(ref)
+        assert np.all(np.abs(got[fin] - ref[fin]) <= RTOL64 * np.maximum(np.abs(ref[fin]), 1e-300) + 1e-18)
+    many = 3000
+    ln = np.full(many, 300, dtype=np.uint64)
+    of = np.arange(many, dtype=np.uint64) * np.uint64(300)
+    b = orc.synth_signal(many * 300, SR, seed=96)
+    got = ctx.time_features_batch(b, of, ln, SR)                                   # binary search over 3000 files
+    for i in (0, 1, 1499, 2999):
+        seg = b[i * 300:(i + 1) * 300]
+        assert got[i, 3] == orc.zero_crossing_rate(seg, SR) and got[i, 2] == pytest.approx(orc.energy(seg), rel=RTOL64)
+
+
+def test_wrapper_rejects_descriptors_past_the_buffer(ctx, aus, orc):
+    """the batch ABI takes offsets / lengths but no total size, so the wrappers check them (a bad descriptor
+    would make the H2D copy read past the caller's array), and `out` arrays are validated for every batch call."""
+    x = orc.synth_signal(5000, SR, seed=97)
+    with pytest.raises(ValueError):
+        ctx.stft_features_batch(x, [0, 4000], [4000, 1001], 1024, 256, 2, SR)
+    with pytest.raises(ValueError):
+        ctx.time_features_batch(x, [10], [4991], SR)
+    with pytest.raises(ValueError):
+        aus.stft_features_multi([0], x, [1], [5000], 1024, 256, 2, SR)
+    pcm = np.zeros(5000, dtype=np.int16)
+    with pytest.raises(ValueError):
+        ctx.stft_features_batch_pcm(pcm, [0], [5001], 1024, 256, 2, SR)
+    with pytest.raises(ValueError):
+        ctx.stft_features_batch_pcm(pcm, [0], [5000], 1024, 256, 2, SR, out=np.empty((3, 14), dtype=np.float32))
+    with pytest.raises(ValueError):
+        ctx.stft_features_batch_pcm(pcm.astype(np.int32), [0], [5000], 1024, 256, 2, SR, sample_bits=20)
+    with pytest.raises(aus.AusError):                              # generic wrapper: ceil(m_fl) > floor(m_fu) panics upstream
+        aus.analysis.spectral_slope_region(np.ones(1025), orc.rfftfreq(2048, SR), 100.0, 101.0, SR)
+
+
+def test_host_register_modes_agree(aus, orc):
+    """aus_ctx_set_host_register: pageable input page-locked for the call (1), never (0), auto (-1): identical bits."""
+    c = aus.Context(0)
+    x = orc.synth_signal(300000, SR, seed=98)
+    res = []
+    for mode in (0, 1, -1):
+        c.set_host_register(mode)
+        res.append(c.stft_features(x, 2048, 512, orc.HANNING, SR))
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
+    with pytest.raises(aus.AusError):
+        c.stft_features(x, 2048, 512, orc.HANNING, 8000)            # band above Nyquist: rejected before any copy is queued
+    assert np.array_equal(c.stft_features(x, 2048, 512, orc.HANNING, SR), res[0])      # ... and the context is still usable
+    c.close()
