@@ -332,7 +332,8 @@ class Context:
         return list(np.split(out, np.cumsum(lens)[:-1]))
 
     def set_host_register(self, mode: int):
-        """Page-lock pageable inputs of the host-pointer feature calls: -1 auto (>= 64 MB), 0 never, 1 always."""
+        """Pageable inputs of the host-pointer feature calls: 0 driver staging, 1 cudaHostRegister around the call, 2 own
+        pinned staging ring filled by several host threads, -1 auto (mode 2 from 64 MB)."""
         _lib.check(self._lib.aus_ctx_set_host_register(self._h, int(mode)))
 
     # ---- device-pointer API (torch CUDA tensors; stream-ordered, no sync)

@@ -141,6 +141,10 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
     for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw, &c->normtab, &c->acorr,
                       &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1], &c->ppcm[0], &c->ppcm[1]})
         b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (c->hstage[i]) cudaFreeHost(c->hstage[i]);
+        if (c->hout[i]) cudaFreeHost(c->hout[i]);
+    }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     for (int i = 0; i < 2; ++i)
@@ -781,7 +785,25 @@ static int ensure_pipeline(aus_ctx *c) {
 
 // pcm_bits: 0 = the host buffer is f64 samples; 8 = int8_t PCM; 16 = int16_t PCM; 24 / 32 = int32_t PCM (24-bit samples in 32-bit words)
 static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
-                                             int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples);
+                                             int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples,
+                                             bool stage);
+
+// pageable -> pinned with several host threads (one memcpy thread tops out near 10 GB/s, PCIe takes ~55)
+static void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads) {
+    if (threads <= 1 || bytes < ((size_t)4 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes / threads) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < threads; ++i) {
+        const size_t lo = (size_t)i * per;
+        if (lo >= bytes) break;
+        const size_t n = std::min(per, bytes - lo);
+        th.emplace_back([=]() { memcpy((char *)dst + lo, (const char *)src + lo, n); });
+    }
+    for (auto &t : th) t.join();
+}
 
 // Error exits of the pipeline must not leave DMA running on the caller's buffers: whatever happens, all three streams are
 // drained before the call returns.  A pageable input (what a Rust Vec<f64> is) is page-locked for the duration of the
@@ -791,17 +813,19 @@ static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_b
     AUS_TRY(ensure_pipeline(c));
     const size_t in_bytes_ = pcm_bits == 0 ? sizeof(double) : (pcm_bits == 8 ? 1 : (pcm_bits == 16 ? 2 : 4));
     const size_t bytes = (size_t)b.span * in_bytes_;
-    bool registered = false;
+    bool registered = false, stage = false;
     if (c->hostreg_mode != 0 && audio && bytes) {
         cudaPointerAttributes at;
         const bool pageable = cudaPointerGetAttributes(&at, audio) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
         (void)cudaGetLastError();
-        if (pageable && (c->hostreg_mode == 1 || bytes >= c->hostreg_min_bytes)) {
+        if (pageable && c->hostreg_mode == 1) {
             registered = cudaHostRegister(const_cast<void *>(audio), bytes, cudaHostRegisterDefault) == cudaSuccess;
             (void)cudaGetLastError();                           // registration is an optimisation: failure falls back to staging
+        } else if (pageable && (c->hostreg_mode == 2 || bytes >= c->hostreg_min_bytes)) {
+            stage = true;                                       // measured fastest (bench.py e2e_pageable)
         }
     }
-    const int rc = stft_features_host_pipelined_body(c, audio, pcm_bits, b, N, hop, wtype, sr, precision, features, chunk_samples);
+    const int rc = stft_features_host_pipelined_body(c, audio, pcm_bits, b, N, hop, wtype, sr, precision, features, chunk_samples, stage);
     const std::string msg = g_err;
     if (rc != AUS_OK) {
         (void)cudaStreamSynchronize(c->s_in);
@@ -818,7 +842,28 @@ static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_b
 }
 
 static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
-                                             int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples) {
+                                             int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples,
+                                             bool stage) {
+    unsigned copy_threads = std::max(1u, std::min(6u, std::thread::hardware_concurrency() / 2));   // measured on a 16-core host: 2/3/4/6/8 threads -> 22/31/36/42/20 GB/s
+    if (const char *e = getenv("AUS_B200_COPY_THREADS")) copy_threads = (unsigned)std::max(1, atoi(e));
+    // A device -> PAGEABLE host copy returns only when it has completed, which would serialise the pipeline (the host could
+    // not stage chunk i+1 while chunk i computes).  Pageable outputs therefore also go through a small pinned ring and are
+    // copied to the caller's array two chunks later (or at the end).
+    bool out_pageable = false;
+    {
+        cudaPointerAttributes at;
+        out_pageable = cudaPointerGetAttributes(&at, features) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+        (void)cudaGetLastError();
+    }
+    struct Pending { double *dst = nullptr; size_t n = 0; } pending[2];
+    auto flush_out = [&](int bb) -> int {
+        if (pending[bb].dst) {
+            CUDA_TRY(cudaEventSynchronize(c->ev_out[bb]));
+            memcpy(pending[bb].dst, c->hout[bb], pending[bb].n * sizeof(double));
+            pending[bb].dst = nullptr;
+        }
+        return AUS_OK;
+    };
     const size_t in_bytes = pcm_bits == 0 ? sizeof(double) : (pcm_bits == 8 ? 1 : (pcm_bits == 16 ? 2 : 4));
     const double intmax = pcm_bits == 8 ? 127.0 : pcm_bits == 16 ? 32767.0 : (pcm_bits == 24 ? 8388607.0 : 2147483647.0);   // audiofile.rs:12-15
     // virtual files no longer than a chunk
@@ -861,11 +906,28 @@ static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int 
             AUS_TRY(c->ppcm[bb].ensure(std::max<uint64_t>(ch.span, 4) * in_bytes));
             h2d_dst = c->ppcm[bb].p;
         }
+        const void *h2d_src = (const char *)audio + ch.s0 * in_bytes;
+        if (stage && ch.span) {
+            // pageable input: this chunk goes through one of two pinned staging buffers, filled by several host threads while
+            // the previous chunk's DMA and kernels run (the buffer's last DMA, two chunks ago, must have finished)
+            if (ci >= 2) CUDA_TRY(cudaEventSynchronize(c->ev_in[bb]));
+            const size_t need = ch.span * in_bytes;
+            if (c->hstage_cap[bb] < need) {
+                if (c->hstage[bb]) CUDA_TRY(cudaFreeHost(c->hstage[bb]));
+                c->hstage[bb] = nullptr;
+                c->hstage_cap[bb] = 0;
+                CUDA_TRY(cudaHostAlloc(&c->hstage[bb], need + need / 8, cudaHostAllocDefault));
+                c->hstage_cap[bb] = need + need / 8;
+            }
+            parallel_memcpy(c->hstage[bb], h2d_src, need, copy_threads);
+            h2d_src = c->hstage[bb];
+        }
         if (ch.span)
-            CUDA_TRY(cudaMemcpyAsync(h2d_dst, (const char *)audio + ch.s0 * in_bytes, ch.span * in_bytes, cudaMemcpyHostToDevice, c->s_in));
+            CUDA_TRY(cudaMemcpyAsync(h2d_dst, h2d_src, ch.span * in_bytes, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaEventRecord(c->ev_in[bb], c->s_in));
         CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in[bb], 0));
         if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_out[bb], 0));             // D2H of chunk ci-2 released pout[bb]
+        AUS_TRY(flush_out(bb));                                                       // ... and its staged output goes to the caller
         Batch cb;
         cb.off.resize(ch.hi - ch.lo); cb.len.resize(ch.hi - ch.lo); cb.first.resize(ch.hi - ch.lo + 1);
         uint64_t f = 0;
@@ -887,10 +949,24 @@ static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int 
         }
         CUDA_TRY(cudaEventRecord(c->ev_done[bb], st));
         CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_done[bb], 0));
-        if (nfeat)
+        if (nfeat && out_pageable) {
+            if (c->hout_cap[bb] < nfeat * sizeof(double)) {
+                if (c->hout[bb]) CUDA_TRY(cudaFreeHost(c->hout[bb]));
+                c->hout[bb] = nullptr;
+                c->hout_cap[bb] = 0;
+                CUDA_TRY(cudaHostAlloc(&c->hout[bb], nfeat * sizeof(double) * 9 / 8 + 256, cudaHostAllocDefault));
+                c->hout_cap[bb] = nfeat * sizeof(double) * 9 / 8 + 256;
+            }
+            CUDA_TRY(cudaMemcpyAsync(c->hout[bb], c->pout64[bb].p, nfeat * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+            pending[bb].dst = features + vf[ch.lo].row * 14;
+            pending[bb].n = nfeat;
+        } else if (nfeat) {
             CUDA_TRY(cudaMemcpyAsync(features + vf[ch.lo].row * 14, c->pout64[bb].p, nfeat * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+        }
         CUDA_TRY(cudaEventRecord(c->ev_out[bb], c->s_out));
     }
+    AUS_TRY(flush_out(0));
+    AUS_TRY(flush_out(1));
     CUDA_TRY(cudaStreamSynchronize(c->s_out));
     CUDA_TRY(cudaStreamSynchronize(st));
     return AUS_OK;
@@ -1853,10 +1929,11 @@ extern "C" int aus_time_features_frames(aus_ctx *c, const double *audio, const u
     return AUS_OK;
 }
 
-// host-pointer feature path: page-lock the caller's (pageable) input for the duration of the call so the chunked H2D
-// copies run as true asynchronous DMA (a Rust `Vec<f64>` is pageable memory).  -1 auto, 0 never, 1 always.
+// host-pointer feature path, pageable input (a Rust `Vec<f64>`): 0 = hand it to cudaMemcpyAsync (the driver stages it),
+// 1 = page-lock it for the duration of the call (cudaHostRegister), 2 = copy it chunk by chunk into the pipeline's own
+// pinned buffers with several host threads, -1 (default) = 2 for inputs of at least 64 MB, 0 below.
 extern "C" int aus_ctx_set_host_register(aus_ctx *c, int mode) {
-    if (!c || mode < -1 || mode > 1) return fail(AUS_ERR_INVALID, "bad argument");
+    if (!c || mode < -1 || mode > 2) return fail(AUS_ERR_INVALID, "bad argument");
     c->hostreg_mode = mode;
     return AUS_OK;
 }

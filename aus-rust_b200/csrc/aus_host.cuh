@@ -81,7 +81,12 @@ struct aus_ctx {
     const unsigned long long *k5_out_off = nullptr, *k5_out_len = nullptr;   // K5 descriptors of the last irstft_k4 (in `desc`)
     DevBuf acorr;                          // padded chunks of aus_autocorrelation_batch
     void *hostreg_ptr = nullptr;           // caller buffer currently page-locked by the host pipeline (cudaHostRegister)
-    int hostreg_mode = -1;                 // -1 auto (register pageable inputs >= hostreg_min_bytes), 0 never, 1 always
+    int hostreg_mode = -1;                 // pageable inputs: -1 auto (2 when >= hostreg_min_bytes), 0 driver staging, 1 cudaHostRegister,
+                                           // 2 own pinned staging ring filled by several host threads
+    void *hstage[2] = {nullptr, nullptr};  // the staging ring (pinned host memory)
+    size_t hstage_cap[2] = {0, 0};
+    void *hout[2] = {nullptr, nullptr};    // pinned ring for feature rows on their way to a pageable output array
+    size_t hout_cap[2] = {0, 0};
     size_t hostreg_min_bytes = (size_t)64 << 20;
     DevBuf pin64[2], pin32[2], pout64[2], pout32[2], ppcm[2];   // double buffers of the chunked host pipeline
     cudaStream_t s_in = nullptr, s_out = nullptr;

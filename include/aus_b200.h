@@ -98,9 +98,10 @@ int aus_ctx_set_direct_load(aus_ctx *ctx, int on);
 int aus_ctx_set_forward_variant(aus_ctx *ctx, int mode);
 /* granularity (samples) of the host-pointer feature path's copy/compute pipeline; default 32 Mi samples (256 MB f64) */
 int aus_ctx_set_chunk_samples(aus_ctx *ctx, uint64_t n_samples);
-/* host-pointer feature calls (mp.rs:26 hands over a pageable `Vec<f64>`): page-lock a pageable input for the duration of
- * the call (cudaHostRegister) so the chunked H2D copies are asynchronous DMA.  -1 (default) = inputs of at least 64 MB,
- * 0 = never (the driver stages through its own pinned buffers), 1 = always.  Already pinned inputs are used as they are. */
+/* host-pointer feature calls on PAGEABLE input (mp.rs:26 hands over a `Vec<f64>`): 0 = give it to cudaMemcpyAsync (the
+ * driver stages it, ~11 GB/s), 1 = page-lock it for the duration of the call (cudaHostRegister), 2 = copy it chunk by chunk
+ * into the pipeline's own pinned buffers with several host threads while the previous chunk is in flight, -1 (default) =
+ * mode 2 for inputs of at least 64 MB.  Already pinned inputs are used as they are (bench.py e2e vs e2e_pageable). */
 int aus_ctx_set_host_register(aus_ctx *ctx, int mode);
 
 /* ---- pure host helpers ------------------------------------------------------------------------------- */

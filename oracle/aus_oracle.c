@@ -9,8 +9,9 @@
  *   - complex_to_polar_rstft: sqrt AND atan2 per bin, phases discarded          (fft_tools.rs:41-55, mp.rs:43)
  *   - analyzer: ~14 passes, per-frame allocations, pow() calls                  (analyzer.rs:41-81)
  *   - stft_analysis: serial STFT + polar, row copies, analyzer on a thread pool (mp.rs:26-119)
- * rustfft itself is replaced by a table-driven iterative radix-2 FFT (forward sign e^{-2 pi i jk/N},
- * un-normalised in both directions, as rustfft documents).  Paths are relative to /root/reference/src.
+ * rustfft itself is replaced by a table-driven iterative radix-4 FFT (forward sign e^{-2 pi i jk/N},
+ * un-normalised in both directions, as rustfft documents; radix 4 so that the timed CPU baseline is not a
+ * strawman next to rustfft's radix-4 / radix-8 butterflies -- no SIMD intrinsics here, gcc -O3 only).  Paths are relative to /root/reference/src.
  */
 #include <math.h>
 #include <pthread.h>
@@ -81,16 +82,38 @@ static void fft_process(const fft_plan *p, cplx *x, int inverse) {
         return;
     }
     for (size_t i = 0; i < n; ++i) { size_t r = p->rev[i]; if (i < r) { cplx t = x[i]; x[i] = x[r]; x[r] = t; } }
-    for (size_t len = 2; len <= n; len <<= 1) {
-        size_t half = len >> 1, step = n / len;
-        for (size_t i = 0; i < n; i += len)
-            for (size_t j = 0; j < half; ++j) {
-                cplx w = p->tw[j * step];
-                double wi = inverse ? -w.im : w.im;
-                cplx a = x[i + j], b = x[i + j + half];
-                double tr = b.re * w.re - b.im * wi, ti = b.re * wi + b.im * w.re;
-                x[i + j].re = a.re + tr; x[i + j].im = a.im + ti;
-                x[i + j + half].re = a.re - tr; x[i + j + half].im = a.im - ti;
+    /* radix-4 decimation in time on the bit-reversed data (two radix-2 stages merged: three twiddle products per four
+     * points, half the sweeps over the array), after one plain radix-2 stage when log2 n is odd.  The transform is the
+     * one rustfft documents -- forward sign, no scaling; only the summation grouping differs (~1e-16). */
+    size_t m = 1;                                    /* size of the finished sub-transforms */
+    int lg = 0; while (((size_t)1 << lg) < n) ++lg;
+    if (lg & 1) {
+        for (size_t i = 0; i < n; i += 2) {
+            cplx a = x[i], b = x[i + 1];
+            x[i].re = a.re + b.re; x[i].im = a.im + b.im;
+            x[i + 1].re = a.re - b.re; x[i + 1].im = a.im - b.im;
+        }
+        m = 2;
+    }
+    const double sgn = inverse ? -1.0 : 1.0;         /* twiddle conjugation and the sign of the +-i rotation */
+    for (; m < n; m <<= 2) {
+        size_t step = n / (4 * m);
+        for (size_t i = 0; i < n; i += 4 * m)
+            for (size_t j = 0; j < m; ++j) {
+                cplx w1 = p->tw[j * step], w2 = p->tw[2 * j * step], w3 = p->tw[3 * j * step];
+                w1.im *= sgn; w2.im *= sgn; w3.im *= sgn;
+                cplx a = x[i + j], b = x[i + j + m], c = x[i + j + 2 * m], d = x[i + j + 3 * m];
+                double Br = b.re * w2.re - b.im * w2.im, Bi = b.re * w2.im + b.im * w2.re;
+                double Cr = c.re * w1.re - c.im * w1.im, Ci = c.re * w1.im + c.im * w1.re;
+                double Dr = d.re * w3.re - d.im * w3.im, Di = d.re * w3.im + d.im * w3.re;
+                double a1r = a.re + Br, a1i = a.im + Bi, b1r = a.re - Br, b1i = a.im - Bi;
+                double sr = Cr + Dr, si = Ci + Di, dr = Cr - Dr, di = Ci - Di;
+                /* (-i)(dr + i di) = di - i dr  (forward);  (+i)(dr + i di) = -di + i dr  (inverse) */
+                double vr = sgn * di, vi = -sgn * dr;
+                x[i + j].re = a1r + sr;         x[i + j].im = a1i + si;
+                x[i + j + 2 * m].re = a1r - sr; x[i + j + 2 * m].im = a1i - si;
+                x[i + j + m].re = b1r + vr;     x[i + j + m].im = b1i + vi;
+                x[i + j + 3 * m].re = b1r - vr; x[i + j + 3 * m].im = b1i - vi;
             }
     }
 }

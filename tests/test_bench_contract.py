@@ -30,6 +30,18 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["files_per_gpu"] == 4 and "1-hour" in d["cpu_baseline"]["sample"]      # same `config` object as the GPU arm
+
+
+def test_reference_arm_never_loads_the_product():
+    """the reference arm mapped libaus_b200.so through g.build().  It must load the oracle library only."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    ref = src[src.index("def run_reference"):src.index("# --------------------------------------------------------------------------------------------- GPU plumbing")]
+    assert "__graft_entry__" not in ref and "aus_rust_b200" not in ref and "load_library" not in ref
+    port = src[src.index("def _oracle_lib"):src.index("def cpu_port_rate")]
+    assert "__graft_entry__" not in port and "libaus_oracle.so" in port
+    gpu = src[src.index("def run_ours"):src.index("def run_config")]
+    assert "aus_oracle" not in gpu and "import aus_oracle" not in src            # the GPU arm imports nothing from oracle/
 
 
 def test_reference_arm_other_ranks_stay_silent():
@@ -53,3 +65,18 @@ def test_gpu_arm_line():
     assert d["e2e_pcm16"]["h2d_bytes_per_step"] == 3600 * 44100 * 2 and d["e2e_pcm16"]["value"] > d["e2e"]["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["value"] > 100 * d["cpu_baseline"]["value"]
+    e = d["e2e"]
+    assert e["platform_h2d_gbs"] > 1 and 0 < e["frac_of_platform_h2d"] <= 1.05        # the call cannot beat a bare pinned copy
+    assert d["e2e_pageable"]["value"] > 0 and d["e2e_pageable"]["value"] <= 1.05 * e["value"]
+    assert d["other_precision"]["dtype"] == "f32" and d["other_precision"]["value"] > d["value"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_gpu_arm_other_baseline_configs(cfg):
+    d = _run(["--config", str(cfg), "--steps", "3", "--warmup", "3"], 580)
+    assert d["config"]["baseline_config"] == cfg and d["value"] > 0 and 0 < d["roofline"]["frac"] < 1.2
+    assert d["clocks"] is not None and d["gpu_launches"] >= 3
+    if cfg == 2:
+        assert d["reconstruction_max_abs_error_body"] < 1e-9 and abs(d["peak_after_normalisation"] - 10 ** (-6 / 20)) < 1e-12
