@@ -163,6 +163,7 @@ extern "C" int aus_ctx_set_stream(aus_ctx *c, void *s) {
     }
     c->stream = (cudaStream_t)s;
     c->own_stream = false;
+    c->desc_valid = false;                  // the cached descriptor image was uploaded in the old stream's order
     return AUS_OK;
 }
 extern "C" int aus_ctx_synchronize(aus_ctx *c) {
@@ -363,8 +364,18 @@ template <typename A, typename B> static int cast_dev(aus_ctx *c, const A *in, B
 template <typename T> static int launch_finalize(aus_ctx *c, const StftParams<T> &p, size_t N) {
     if (p.total_frames == 0) return AUS_OK;
     const unsigned int grid = (unsigned int)((p.total_frames + 255) / 256);
-    finalize_kernel<T><<<grid, 256, 0, c->stream>>>(p, (int)(N / 2 + 1));
-    CUDA_TRY(cudaGetLastError());
+    // programmatic dependent launch: the grid may be scheduled while the feature kernel drains (its threads wait in
+    // griddepcontrol.wait until that kernel's writes are visible), which hides the launch gap of this tiny kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, finalize_kernel<T>, p, (int)(N / 2 + 1)));
     c->launches++;
     return AUS_OK;
 }
@@ -605,16 +616,31 @@ static void make_batch(Batch &b, const uint64_t *offsets, const uint64_t *length
     b.span = span;
 }
 // descriptor arrays -> device (pageable source: cudaMemcpyAsync returns after staging, so the vectors may die)
+// Descriptor arrays -> device, packed into ONE copy (pageable source: cudaMemcpyAsync returns after staging).  The packed
+// image of the last upload is kept, and an identical descriptor -- the same file lengths again, e.g. a caller analysing
+// equally long clips one call at a time, or the benchmark loop -- is not copied again: a 60 s file is then one K1 launch,
+// one finalize launch and no copy (config 1 is launch / latency bound: DESIGN.md section 7).
 static int upload_desc(aus_ctx *c, DevBuf &buf, const std::vector<const std::vector<unsigned long long> *> &arrs,
                        std::vector<const unsigned long long *> &dptr) {
     size_t total = 0;
     for (auto *a : arrs) total += a->size();
+    std::vector<unsigned long long> &img = c->desc_stage;
+    img.clear();
+    img.reserve(total);
+    for (auto *a : arrs) img.insert(img.end(), a->begin(), a->end());
+    const void *before = buf.p;
     AUS_TRY(buf.ensure(std::max<size_t>(total, 1) * sizeof(unsigned long long)));
     unsigned long long *d = (unsigned long long *)buf.p;
+    const bool same = &buf == &c->desc && before == buf.p && c->desc_valid && img == c->desc_last;
+    if (!same && total) {
+        CUDA_TRY(cudaMemcpyAsync(d, img.data(), total * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        if (&buf == &c->desc) {
+            c->desc_last.swap(img);
+            c->desc_valid = true;
+        }
+    }
     dptr.clear();
     for (auto *a : arrs) {
-        if (!a->empty())
-            CUDA_TRY(cudaMemcpyAsync(d, a->data(), a->size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         dptr.push_back(d);
         d += a->size();
     }

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <map>
 #include <string>
+#include <vector>
 
 using namespace aus;
 
@@ -80,6 +81,8 @@ struct aus_ctx {
     long long normtab_key = -1;            // (fft_size, hop, window, precision) the reciprocal-norm table was built for
     const unsigned long long *k5_out_off = nullptr, *k5_out_len = nullptr;   // K5 descriptors of the last irstft_k4 (in `desc`)
     DevBuf acorr;                          // padded chunks of aus_autocorrelation_batch
+    std::vector<unsigned long long> desc_stage, desc_last;   // packed descriptor image being built / last uploaded to `desc`
+    bool desc_valid = false;
     void *hostreg_ptr = nullptr;           // caller buffer currently page-locked by the host pipeline (cudaHostRegister)
     int hostreg_mode = -1;                 // pageable inputs: -1 auto (2 when >= hostreg_min_bytes), 0 driver staging, 1 cudaHostRegister,
                                            // 2 own pinned staging ring filled by several host threads
@@ -103,9 +106,13 @@ template <typename T, int LG, bool RR, bool FEAT> int launch_stft_v(aus_ctx *c, 
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[c->device & 63] = true;
     }
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
-    if (occ < 1) return fail(AUS_ERR_CUDA, "stft kernel does not fit on an SM");
+    static std::atomic<int> occ_cache[64];
+    int occ = occ_cache[c->device & 63].load();
+    if (occ < 1) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+        if (occ < 1) return fail(AUS_ERR_CUDA, "stft kernel does not fit on an SM");
+        occ_cache[c->device & 63].store(occ);
+    }
     const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
     const unsigned long long cap = (unsigned long long)c->sm_count * occ;
     const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
@@ -169,9 +176,13 @@ template <typename T, int LG> int launch_analyzer_t(aus_ctx *c, const StftParams
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[c->device & 63] = true;
     }
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
-    if (occ < 1) return fail(AUS_ERR_CUDA, "analyzer kernel does not fit on an SM");
+    static std::atomic<int> occ_cache[64];
+    int occ = occ_cache[c->device & 63].load();
+    if (occ < 1) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+        if (occ < 1) return fail(AUS_ERR_CUDA, "analyzer kernel does not fit on an SM");
+        occ_cache[c->device & 63].store(occ);
+    }
     const unsigned long long need = (p.total_frames + C::FPB - 1) / C::FPB;
     const unsigned long long cap = (unsigned long long)c->sm_count * occ;
     const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));
@@ -189,9 +200,13 @@ template <typename T, int LG> int launch_istft_t(aus_ctx *c, const IstftParams<T
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[c->device & 63] = true;
     }
-    int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
-    if (occ < 1) return fail(AUS_ERR_CUDA, "istft kernel does not fit on an SM");
+    static std::atomic<int> occ_cache[64];
+    int occ = occ_cache[c->device & 63].load();
+    if (occ < 1) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::BLOCK, smem));
+        if (occ < 1) return fail(AUS_ERR_CUDA, "istft kernel does not fit on an SM");
+        occ_cache[c->device & 63].store(occ);
+    }
     const unsigned long long need = (p.n_seg + C::FPB - 1) / C::FPB;
     const unsigned long long cap = (unsigned long long)c->sm_count * occ;
     const unsigned int grid = (unsigned int)std::max<unsigned long long>(1, std::min(need, cap));

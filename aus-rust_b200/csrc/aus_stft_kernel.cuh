@@ -511,6 +511,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
 // One thread per frame: raw record -> the 14 features in the declaration order of analyzer.rs:10-23.
 template <typename T>
 __global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, int K) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // launched as a programmatic dependent of the feature kernel
     const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= p.total_frames) return;
     const double *rec = p.raw + g * (unsigned long long)RAW_N;

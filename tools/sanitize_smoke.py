@@ -27,3 +27,18 @@ lens = [0, 5, 700, 3000]
 offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
 print(ctx.stft_features_batch(orc.synth_signal(sum(lens)), offs, lens, 256, 64, 2, SR)[0].shape)
 print("sanitize smoke done")
+# round-2 entry points: producer/consumer variant, irstft batch / shards, per-frame time features, PCM + mixdown, polar
+c2 = aus.Context(0)
+c2.set_forward_variant(2)
+x = orc.synth_signal(9000, SR, seed=5)
+print("pc", c2.stft_features(x, 2048, 512, 2, SR).shape, c2.stft_features(x[1:], 2048, 511, 1, SR).shape)
+S = [ctx.rstft(orc.synth_signal(n, SR, seed=6), 1024, 256, 3) for n in (5000, 1024, 9001)]
+print("irstft_batch", [y.shape for y in ctx.irstft_batch(S, 1024, 256, 3)])
+print("irstft_multi", [y.shape for y in aus.irstft_multi([0, 0, 0], S, 1024, 256, 3)])
+print("time frames", ctx.time_features_frames(x, [0, 4000], [4000, 5000], 1024, 256, SR).shape)
+pcm = (x[:4000].reshape(-1, 2) * 127).astype(np.int8)
+print("pcm", ctx.pcm_to_f64(pcm, 2, True, True).shape, ctx.mixdown(np.stack([x[:100], x[100:200], x[200:300]])).shape)
+mag, ph = ctx.complex_to_polar(S[0])
+print("polar", ctx.polar_to_complex(mag, ph).shape)
+aus.multi_shutdown()
+print("sanitize smoke (round 2) done")
