@@ -127,6 +127,9 @@ extern "C" int aus_ctx_create(int device, aus_ctx **out) {
 
 extern "C" void aus_ctx_destroy(aus_ctx *c) {
     if (!c) return;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);                  // destroying a context must not move the caller's current device
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->tables) {
@@ -144,6 +147,8 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
     for (int i = 0; i < 2; ++i) {
         if (c->hstage[i]) cudaFreeHost(c->hstage[i]);
         if (c->hout[i]) cudaFreeHost(c->hout[i]);
+        if (c->xstage[i]) cudaFreeHost(c->xstage[i]);
+        if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
     }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -647,6 +652,76 @@ static int upload_desc(aus_ctx *c, DevBuf &buf, const std::vector<const std::vec
     return AUS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ big host <-> device moves
+// Host-pointer entry points get whatever memory the caller has -- for the Rust shim a pageable Vec.  The driver stages
+// pageable copies through its own bounce buffers at ~11 GB/s; a 2 x 64 MB pinned ring filled / drained by several host
+// threads while the previous piece is on the wire reaches 35-45 GB/s (tools/pageable_probe.py).  Pinned or small buffers
+// take the plain asynchronous copy.  Both calls are ordered on c->stream; xfer_d2h returns when the data is in `dst`.
+static void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads);
+static bool host_pageable(const void *p) {
+    cudaPointerAttributes at;
+    const bool pg = cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+    (void)cudaGetLastError();
+    return pg;
+}
+static unsigned copy_threads() {
+    unsigned t = std::max(1u, std::min(6u, std::thread::hardware_concurrency() / 2));   // 16-core host: 2/3/4/6/8 threads -> 22/31/36/42/20 GB/s
+    if (const char *e = getenv("AUS_B200_COPY_THREADS")) t = (unsigned)std::max(1, atoi(e));
+    return t;
+}
+static int xfer_ring(aus_ctx *c) {
+    for (int i = 0; i < 2; ++i) {
+        if (!c->xstage[i]) CUDA_TRY(cudaHostAlloc(&c->xstage[i], aus_ctx::XSTAGE_BYTES, cudaHostAllocDefault));
+        if (!c->ev_x[i]) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_x[i], cudaEventDisableTiming));
+    }
+    return AUS_OK;
+}
+static int xfer_h2d(aus_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return AUS_OK;
+    if (c->hostreg_mode == 0 || bytes < c->hostreg_min_bytes || !host_pageable(src)) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        return AUS_OK;
+    }
+    AUS_TRY(xfer_ring(c));
+    const unsigned th = copy_threads();
+    size_t done = 0;
+    for (int k = 0; done < bytes; ++k) {
+        const int bb = k & 1;
+        const size_t n = std::min(bytes - done, aus_ctx::XSTAGE_BYTES);
+        if (k >= 2) CUDA_TRY(cudaEventSynchronize(c->ev_x[bb]));          // the ring slot's previous DMA has finished
+        parallel_memcpy(c->xstage[bb], (const char *)src + done, n, th);
+        CUDA_TRY(cudaMemcpyAsync((char *)dst + done, c->xstage[bb], n, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_x[bb], c->stream));
+        done += n;
+    }
+    CUDA_TRY(cudaEventSynchronize(c->ev_x[0]));                            // leave the ring idle for the next user
+    CUDA_TRY(cudaEventSynchronize(c->ev_x[1]));
+    return AUS_OK;
+}
+static int xfer_d2h(aus_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return AUS_OK;
+    if (c->hostreg_mode == 0 || bytes < c->hostreg_min_bytes || !host_pageable(dst)) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return AUS_OK;
+    }
+    AUS_TRY(xfer_ring(c));
+    const unsigned th = copy_threads();
+    const size_t pieces = (bytes + aus_ctx::XSTAGE_BYTES - 1) / aus_ctx::XSTAGE_BYTES;
+    for (size_t k = 0; k <= pieces; ++k) {
+        if (k < pieces) {                                                  // piece k on the wire ...
+            const size_t off = k * aus_ctx::XSTAGE_BYTES, n = std::min(bytes - off, aus_ctx::XSTAGE_BYTES);
+            CUDA_TRY(cudaMemcpyAsync(c->xstage[k & 1], (const char *)src + off, n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaEventRecord(c->ev_x[k & 1], c->stream));
+        }
+        if (k >= 1) {                                                      // ... while piece k - 1 goes to the caller
+            const size_t off = (k - 1) * aus_ctx::XSTAGE_BYTES, n = std::min(bytes - off, aus_ctx::XSTAGE_BYTES);
+            CUDA_TRY(cudaEventSynchronize(c->ev_x[(k - 1) & 1]));
+            parallel_memcpy((char *)dst + off, c->xstage[(k - 1) & 1], n, th);
+        }
+    }
+    return AUS_OK;
+}
+
 // features and/or spectra of a batch already resident on the device, in compute type T
 template <typename T>
 static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t N, size_t hop, int wtype, uint32_t sr,
@@ -755,7 +830,7 @@ static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offs
     const size_t K = N / 2 + 1;
     const unsigned long long nfeat = b.total_frames * 14ull, nspec = b.total_frames * K * 2ull;
     AUS_TRY(c->in64.ensure(std::max<size_t>(b.span, 2) * sizeof(double)));
-    if (b.span) CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, b.span * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (b.span) AUS_TRY(xfer_h2d(c, c->in64.p, audio, b.span * sizeof(double)));
     if (features) AUS_TRY(c->out64.ensure(nfeat * sizeof(double)));
     if (spectra) AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
     if (precision == AUS_F64) {
@@ -771,8 +846,8 @@ static int stft_batch_host(aus_ctx *c, const double *audio, const uint64_t *offs
         if (features) AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nfeat));
         if (spectra) AUS_TRY(cast_dev<float, double>(c, (const float *)c->aux32.p, (double *)c->aux64.p, nspec));
     }
-    if (features) CUDA_TRY(cudaMemcpyAsync(features, c->out64.p, nfeat * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (spectra) CUDA_TRY(cudaMemcpyAsync(spectra, c->aux64.p, nspec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (features) AUS_TRY(xfer_d2h(c, features, c->out64.p, nfeat * sizeof(double)));
+    if (spectra) AUS_TRY(xfer_d2h(c, spectra, c->aux64.p, nspec * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -870,8 +945,7 @@ static int stft_features_host_pipelined(aus_ctx *c, const void *audio, int pcm_b
 static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int pcm_bits, const Batch &b, size_t N, size_t hop,
                                              int wtype, uint32_t sr, int precision, double *features, uint64_t chunk_samples,
                                              bool stage) {
-    unsigned copy_threads = std::max(1u, std::min(6u, std::thread::hardware_concurrency() / 2));   // measured on a 16-core host: 2/3/4/6/8 threads -> 22/31/36/42/20 GB/s
-    if (const char *e = getenv("AUS_B200_COPY_THREADS")) copy_threads = (unsigned)std::max(1, atoi(e));
+    const unsigned n_copy_threads = copy_threads();
     // A device -> PAGEABLE host copy returns only when it has completed, which would serialise the pipeline (the host could
     // not stage chunk i+1 while chunk i computes).  Pageable outputs therefore also go through a small pinned ring and are
     // copied to the caller's array two chunks later (or at the end).
@@ -945,7 +1019,7 @@ static int stft_features_host_pipelined_body(aus_ctx *c, const void *audio, int 
                 CUDA_TRY(cudaHostAlloc(&c->hstage[bb], need + need / 8, cudaHostAllocDefault));
                 c->hstage_cap[bb] = need + need / 8;
             }
-            parallel_memcpy(c->hstage[bb], h2d_src, need, copy_threads);
+            parallel_memcpy(c->hstage[bb], h2d_src, need, n_copy_threads);
             h2d_src = c->hstage[bb];
         }
         if (ch.span)
@@ -1057,14 +1131,14 @@ extern "C" int aus_complex_to_polar(aus_ctx *c, const double *spectra, size_t n,
     if (n == 0) return AUS_OK;
     AUS_TRY(c->aux64.ensure(n * 2 * sizeof(double)));
     AUS_TRY(c->out64.ensure(n * 2 * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->aux64.p, spectra, n * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->aux64.p, spectra, n * 2 * sizeof(double)));
     double *dm = (double *)c->out64.p, *dp = ph ? dm + n : nullptr;
     const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 16);
     to_polar_kernel<<<grid, 256, 0, c->stream>>>((const double2 *)c->aux64.p, dm, dp, n);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
-    CUDA_TRY(cudaMemcpyAsync(mag, dm, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (ph) CUDA_TRY(cudaMemcpyAsync(ph, dp, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, mag, dm, n * sizeof(double)));
+    if (ph) AUS_TRY(xfer_d2h(c, ph, dp, n * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1075,13 +1149,13 @@ extern "C" int aus_polar_to_complex(aus_ctx *c, const double *mag, const double 
     AUS_TRY(c->aux64.ensure(n * 2 * sizeof(double)));
     AUS_TRY(c->out64.ensure(n * 2 * sizeof(double)));
     double *dm = (double *)c->out64.p, *dp = dm + n;
-    CUDA_TRY(cudaMemcpyAsync(dm, mag, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(dp, ph, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, dm, mag, n * sizeof(double)));
+    AUS_TRY(xfer_h2d(c, dp, ph, n * sizeof(double)));
     const unsigned int grid = (unsigned int)std::min<size_t>((n + 255) / 256, (size_t)c->sm_count * 16);
     from_polar_kernel<<<grid, 256, 0, c->stream>>>(dm, dp, (double2 *)c->aux64.p, n);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
-    CUDA_TRY(cudaMemcpyAsync(spectra, c->aux64.p, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, spectra, c->aux64.p, n * 2 * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1117,7 +1191,7 @@ extern "C" int aus_analyzer_batch(aus_ctx *c, const double *mags, size_t F, size
     const size_t K = N / 2 + 1, nm = F * K, nf = F * 14;
     AUS_TRY(c->in64.ensure(nm * sizeof(double)));
     AUS_TRY(c->out64.ensure(nf * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->in64.p, mags, nm * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->in64.p, mags, nm * sizeof(double)));
     if (precision == AUS_F64) {
         AUS_TRY(analyzer_dev_t<double>(c, (const double *)c->in64.p, F, N, sr, (double *)c->out64.p));
     } else {
@@ -1127,7 +1201,7 @@ extern "C" int aus_analyzer_batch(aus_ctx *c, const double *mags, size_t F, size
         AUS_TRY(analyzer_dev_t<float>(c, (const float *)c->in32.p, F, N, sr, (float *)c->out32.p));
         AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nf));
     }
-    CUDA_TRY(cudaMemcpyAsync(features, c->out64.p, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, features, c->out64.p, nf * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1313,7 +1387,7 @@ static int irstft_host(aus_ctx *c, const double *spectra, size_t F, size_t N, si
     const size_t K = N / 2 + 1, nspec = F * K * 2, nout = aus_irstft_len(F, N, hop);
     AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
     AUS_TRY(c->out64.ensure(nout * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->aux64.p, spectra, nspec * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->aux64.p, spectra, nspec * sizeof(double)));
     if (precision == AUS_F64) {
         AUS_TRY(irstft_dev_t<double>(c, (const Cx<double> *)c->aux64.p, F, N, hop, wtype, normalize, apply_window, (double *)c->out64.p));
     } else {
@@ -1323,7 +1397,7 @@ static int irstft_host(aus_ctx *c, const double *spectra, size_t F, size_t N, si
         AUS_TRY(irstft_dev_t<float>(c, (const Cx<float> *)c->aux32.p, F, N, hop, wtype, normalize, apply_window, (float *)c->out32.p));
         AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nout));
     }
-    CUDA_TRY(cudaMemcpyAsync(audio, c->out64.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, audio, c->out64.p, nout * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1366,7 +1440,7 @@ extern "C" int aus_autocorrelation_batch(aus_ctx *c, const double *audio, size_t
     AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
     AUS_TRY(c->out64.ensure(npad * sizeof(double)));
     AUS_TRY(c->acorr.ensure(npad * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, nin * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->in64.p, audio, nin * sizeof(double)));
     const unsigned int grid = (unsigned int)std::min<size_t>((npad + 255) / 256, (size_t)c->sm_count * 16);
     acorr_pad_kernel<<<grid, 256, 0, c->stream>>>((const double *)c->in64.p, (double *)c->acorr.p, n_chunks, (int)N);
     CUDA_TRY(cudaGetLastError());
@@ -1383,7 +1457,7 @@ extern "C" int aus_autocorrelation_batch(aus_ctx *c, const double *audio, size_t
     acorr_slice_kernel<<<grid, 256, 0, c->stream>>>((const double *)c->out64.p, (double *)c->in64.p, n_chunks, (int)N);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
-    CUDA_TRY(cudaMemcpyAsync(out, c->in64.p, nin * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, out, c->in64.p, nin * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1412,7 +1486,7 @@ extern "C" int aus_time_features_batch(aus_ctx *c, const double *audio, const ui
     AUS_TRY(c->in64.ensure(std::max<unsigned long long>(span, 1) * sizeof(double)));
     AUS_TRY(c->aux64.ensure(std::max<unsigned long long>(chunks, 1) * 4 * sizeof(double)));
     AUS_TRY(c->out64.ensure(n_files * 4 * sizeof(double)));
-    if (span) CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, span * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (span) AUS_TRY(xfer_h2d(c, c->in64.p, audio, span * sizeof(double)));
     std::vector<const unsigned long long *> dp;
     AUS_TRY(upload_desc(c, c->desc, {&off, &len, &cf}, dp));
     if (chunks) {
@@ -1616,7 +1690,7 @@ extern "C" int aus_irstft_batch(aus_ctx *c, const double *spectra, const uint64_
     const size_t nspec = F * K * 2;
     AUS_TRY(c->aux64.ensure(nspec * sizeof(double)));
     AUS_TRY(c->out64.ensure(nout * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->aux64.p, spectra, nspec * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->aux64.p, spectra, nspec * sizeof(double)));
     if (precision == AUS_F64) {
         AUS_TRY(irstft_batch_dev_t<double>(c, (const Cx<double> *)c->aux64.p, n_frames, n_files, N, hop, wtype, normalize, (double *)c->out64.p));
     } else {
@@ -1626,7 +1700,7 @@ extern "C" int aus_irstft_batch(aus_ctx *c, const double *spectra, const uint64_
         AUS_TRY(irstft_batch_dev_t<float>(c, (const Cx<float> *)c->aux32.p, n_frames, n_files, N, hop, wtype, normalize, (float *)c->out32.p));
         AUS_TRY(cast_dev<float, double>(c, (const float *)c->out32.p, (double *)c->out64.p, nout));
     }
-    CUDA_TRY(cudaMemcpyAsync(audio, c->out64.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, audio, c->out64.p, nout * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1833,9 +1907,9 @@ extern "C" int aus_pcm_to_f64(aus_ctx *c, const void *pcm, int sample_bits, size
     const size_t nin = n_frames * (size_t)n_channels, nout = mixdown ? n_frames : nin;
     AUS_TRY(c->ppcm[0].ensure(nin * bytes));
     AUS_TRY(c->out64.ensure(nout * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->ppcm[0].p, pcm, nin * bytes, cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->ppcm[0].p, pcm, nin * bytes));
     AUS_TRY(aus_pcm_to_f64_dev(c, c->ppcm[0].p, sample_bits, n_frames, n_channels, interleaved, mixdown, c->out64.p));
-    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, nout * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, out, c->out64.p, nout * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1860,9 +1934,9 @@ extern "C" int aus_mixdown(aus_ctx *c, const double *channels, size_t n_frames, 
     if (n_frames == 0) return AUS_OK;
     AUS_TRY(c->in64.ensure(n_frames * (size_t)n_channels * sizeof(double)));
     AUS_TRY(c->out64.ensure(n_frames * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(c->in64.p, channels, n_frames * (size_t)n_channels * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    AUS_TRY(xfer_h2d(c, c->in64.p, channels, n_frames * (size_t)n_channels * sizeof(double)));
     AUS_TRY(aus_mixdown_dev(c, c->in64.p, n_frames, n_channels, c->out64.p));
-    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, n_frames * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, out, c->out64.p, n_frames * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }
@@ -1948,9 +2022,9 @@ extern "C" int aus_time_features_frames(aus_ctx *c, const double *audio, const u
     if (b.total_frames == 0) return AUS_OK;
     AUS_TRY(c->in64.ensure(std::max<unsigned long long>(b.span, 1) * sizeof(double)));
     AUS_TRY(c->out64.ensure(b.total_frames * 4 * sizeof(double)));
-    if (b.span) CUDA_TRY(cudaMemcpyAsync(c->in64.p, audio, b.span * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (b.span) AUS_TRY(xfer_h2d(c, c->in64.p, audio, b.span * sizeof(double)));
     AUS_TRY(aus_time_features_frames_dev(c, c->in64.p, offsets, lengths, n_files, N, hop, sr, c->out64.p));
-    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, b.total_frames * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    AUS_TRY(xfer_d2h(c, out, c->out64.p, b.total_frames * 4 * sizeof(double)));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return AUS_OK;
 }

@@ -88,6 +88,9 @@ struct aus_ctx {
                                            // 2 own pinned staging ring filled by several host threads
     void *hstage[2] = {nullptr, nullptr};  // the staging ring (pinned host memory)
     size_t hstage_cap[2] = {0, 0};
+    static constexpr size_t XSTAGE_BYTES = (size_t)64 << 20;
+    void *xstage[2] = {nullptr, nullptr};  // pinned ring of the generic big host <-> device moves (xfer_h2d / xfer_d2h)
+    cudaEvent_t ev_x[2] = {nullptr, nullptr};
     void *hout[2] = {nullptr, nullptr};    // pinned ring for feature rows on their way to a pageable output array
     size_t hout_cap[2] = {0, 0};
     size_t hostreg_min_bytes = (size_t)64 << 20;

@@ -566,12 +566,17 @@ def run_multi(args):
     counts = [c for c in (1, 2, 4, 8) if c <= min(have, args.gpus if args.gpus > 1 else have)]
     ctx = aus.Context(0)
 
-    def host_signal(n_files, n):
+    def host_signal(n_files, n, pinned):
+        """synthetic files as one host array: pageable (a numpy array = what a Rust Vec is) or pinned"""
         d = torch.empty(n_files * n, dtype=torch.float64, device="cuda:0")
         for i in range(n_files):
             ctx.synth_dev(d[i * n:(i + 1) * n], 0, SR, file_freq(i), 0, i, "f64")
         torch.cuda.synchronize()
-        return d.cpu().numpy()
+        if pinned:
+            h = torch.empty(n_files * n, dtype=torch.float64, pin_memory=True)
+            h.copy_(d)
+            return h.numpy(), h
+        return d.cpu().numpy(), None
 
     def best_of(fn, reps=3):
         fn()
@@ -585,43 +590,44 @@ def run_multi(args):
     out = {"metric": "multi_gpu_strong_scaling_frames_per_sec", "unit": "frames/s", "devices_visible": have, "n_gpus": max(counts),
            "entry_points": "aus_stft_features_multi / aus_irstft_multi (one process, one host thread + context per device)",
            "data": "synthetic", "higher_is_better": True, "workloads": {}}
-    # config 4: one 1-hour file, fft 16384 / hop 4096, split by frame range with an fft_size - hop sample halo
-    x = host_signal(1, 3600 * SR)
-    F4 = _frames(x.size, 16384, 4096)
-    ref = None
-    res = {}
-    for c in counts:
-        devs = list(range(c))
-        t = best_of(lambda: aus.stft_features_multi(devs, x, [0], [x.size], 16384, 4096, WINDOW, SR))
-        got = aus.stft_features_multi(devs, x, [0], [x.size], 16384, 4096, WINDOW, SR)
-        if ref is None:
-            ref = got
-        assert np.array_equal(got, ref, equal_nan=True), "sharded result differs from the single-device one"
-        res[str(c)] = F4 / t
-    out["workloads"]["config4_one_1h_file_fft16384_hop4096_by_frame_range"] = {"frames": F4, "frames_per_sec": res,
-                                                                               "h2d_bytes": x.size * 8, "bit_identical_across_device_counts": True}
-    del x
-    # config 3: 1000 x 30 s clips, fft 1024 / hop 256, whole files per device
-    n = 30 * SR
-    x = host_signal(1000, n)
-    lens = np.full(1000, n, dtype=np.uint64)
-    offs = np.arange(1000, dtype=np.uint64) * np.uint64(n)
-    F3 = _frames(n, 1024, 256) * 1000
-    ref, res = None, {}
-    for c in counts:
-        devs = list(range(c))
-        t = best_of(lambda: aus.stft_features_multi(devs, x, offs, lens, 1024, 256, WINDOW, SR))
-        got = aus.stft_features_multi(devs, x, offs, lens, 1024, 256, WINDOW, SR)
-        if ref is None:
-            ref = got
-        assert np.array_equal(got, ref, equal_nan=True)
-        res[str(c)] = F3 / t
-    out["workloads"]["config3_1000x30s_fft1024_hop256_by_file"] = {"frames": F3, "frames_per_sec": res, "h2d_bytes": x.size * 8,
-                                                                   "bit_identical_across_device_counts": True}
-    del x
-    # config 2: irstft of a 10-minute stereo pair, fft 4096 / hop 1024, by frame range (or by channel at 2 devices)
+    for pinned in (False, True):
+        tag = "pinned_host" if pinned else "pageable_host"
+        # config 4: one 1-hour file, fft 16384 / hop 4096, split by frame range with an fft_size - hop sample halo
+        x, keep = host_signal(1, 3600 * SR, pinned)
+        F4 = _frames(x.size, 16384, 4096)
+        ref, res = None, {}
+        for c in counts:
+            devs = list(range(c))
+            t = best_of(lambda: aus.stft_features_multi(devs, x, [0], [x.size], 16384, 4096, WINDOW, SR))
+            got = aus.stft_features_multi(devs, x, [0], [x.size], 16384, 4096, WINDOW, SR)
+            if ref is None:
+                ref = got
+            assert np.array_equal(got, ref, equal_nan=True), "sharded result differs from the single-device one"
+            res[str(c)] = F4 / t
+        out["workloads"].setdefault("config4_one_1h_file_fft16384_hop4096_by_frame_range", {"frames": F4, "h2d_bytes": x.size * 8,
+                                    "bit_identical_across_device_counts": True})[tag] = res
+        del x, keep
+        # config 3: 1000 x 30 s clips, fft 1024 / hop 256, whole files per device
+        n = 30 * SR
+        x, keep = host_signal(1000, n, pinned)
+        lens = np.full(1000, n, dtype=np.uint64)
+        offs = np.arange(1000, dtype=np.uint64) * np.uint64(n)
+        F3 = _frames(n, 1024, 256) * 1000
+        ref, res = None, {}
+        for c in counts:
+            devs = list(range(c))
+            t = best_of(lambda: aus.stft_features_multi(devs, x, offs, lens, 1024, 256, WINDOW, SR))
+            got = aus.stft_features_multi(devs, x, offs, lens, 1024, 256, WINDOW, SR)
+            if ref is None:
+                ref = got
+            assert np.array_equal(got, ref, equal_nan=True)
+            res[str(c)] = F3 / t
+        out["workloads"].setdefault("config3_1000x30s_fft1024_hop256_by_file", {"frames": F3, "h2d_bytes": x.size * 8,
+                                    "bit_identical_across_device_counts": True})[tag] = res
+        del x, keep
+    # config 2: irstft of a 10-minute stereo pair, fft 4096 / hop 1024, by frame range (by channel at 2 devices); pageable
     n = 600 * SR
-    xs = host_signal(2, n)
+    xs, _ = host_signal(2, n, False)
     S = [ctx.rstft(xs[i * n:(i + 1) * n], 4096, 1024, 3) for i in range(2)]
     Fc = S[0].shape[0]
     ref, res = None, {}
@@ -634,8 +640,9 @@ def run_multi(args):
         err = max(float(np.max(np.abs(a - b))) for a, b in zip(got, ref))
         assert err <= 1e-12, err                     # only the peak factor's last bits may differ between shardings
         res[str(c)] = 2 * Fc / t
-    out["workloads"]["config2_irstft_10min_stereo_fft4096_hop1024"] = {"frames": 2 * Fc, "frames_per_sec": res,
-                                                                       "h2d_bytes": int(sum(s.nbytes for s in S))}
+    out["workloads"]["config2_irstft_10min_stereo_fft4096_hop1024"] = {"frames": 2 * Fc, "pageable_host": res,
+                                                                       "h2d_bytes": int(sum(s.nbytes for s in S)),
+                                                                       "note": "includes the Python-side concatenation of the two spectrograms"}
     aus.multi_shutdown()
     print(json.dumps(out))
 
