@@ -295,13 +295,33 @@ __device__ __forceinline__ void post_twiddle(Cx<T> A, Cx<T> B, Cx<T> W, Cx<T> &X
 // Per-thread running sums of the first feature pass (arithmetic type T; cross-thread combination is always double).
 template <typename T> struct FeatAcc {
     T s_m = 0, s_mk = 0, s_pk = 0, lo_sum = 0, hi_sum = 0, mid = 0;
+    T s_m2 = 0, s_mk2 = 0, s_pk2 = 0;                 // second accumulator set (the high bins): halves the add chains
     unsigned pmin = 0x7ff00000u;                      // smallest power bin, as the high word of its f64 pattern (f32: bits >> 1)
     __device__ __forceinline__ void add(T kf, T m, T pw) {
         s_m += m;
         s_mk += m * kf;
         s_pk += pw * kf;
     }
+    __device__ __forceinline__ void add2(T kf, T m, T pw) {
+        s_m2 += m;
+        s_mk2 += m * kf;
+        s_pk2 += pw * kf;
+    }
+    __device__ __forceinline__ void merge() { s_m += s_m2; s_mk += s_mk2; s_pk += s_pk2; }
 };
+#ifndef AUS_SPLIT_TAIL_ACC
+#define AUS_SPLIT_TAIL_ACC 0     // measured neutral at fft 2048 (1.277e8 vs 1.281e8 frames/s)
+#endif
+#ifndef AUS_TAIL_PAIRS
+#define AUS_TAIL_PAIRS 4         // pairs (k, M - k) per trip of the first feature pass
+#endif
+#ifndef AUS_EARLY_TMA
+#define AUS_EARLY_TMA 0          // frame_features32: issue the next frame's bulk copy as soon as the group buffer is free.
+                                 // Measured SLOWER (1.23e8 vs 1.27e8 frames/s, twice, also with a load-free locate): off
+#endif
+#ifndef AUS_SWEEP_W
+#define AUS_SWEEP_W 4            // bins per trip of frame_features32's sweep
+#endif
 
 // Slot of bin b in the group buffer ("Z layout").
 __device__ __forceinline__ int zslot(int b) { return b + (b >> 4); }
@@ -508,6 +528,323 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     }
 }
 
+#ifndef AUS_FEAT32
+#define AUS_FEAT32 1             // f64, one warp per frame: latency-trimmed second half of the feature computation (below)
+#endif
+
+// Sum of NV <= 16 doubles over a warp with 16 instead of 5 NV 64-bit shuffles (recursive halving): every step a lane keeps
+// the half of the values its lane bit selects and adds the partner's copy; afterwards lane t holds the total of value
+// t >> 1 (values >= NV are zero).  Fixed order -> deterministic.
+template <int NV> __device__ __forceinline__ double warp_reduce_scatter(const double (&in)[NV], int t) {
+    static_assert(NV <= 16, "at most 16 values");
+    double v8[8];
+    {
+        const bool h = (t & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const double lo = in[i], hi = i + 8 < NV ? in[i + 8] : 0.0;
+            const double keep = h ? hi : lo, send = h ? lo : hi;
+            v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    double v4[4];
+    {
+        const bool h = (t & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double keep = h ? v8[i + 4] : v8[i], send = h ? v8[i] : v8[i + 4];
+            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    double v2[2];
+    {
+        const bool h = (t & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double keep = h ? v4[i + 2] : v4[i], send = h ? v4[i] : v4[i + 2];
+            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool h = (t & 2) != 0;
+    const double keep = h ? v2[1] : v2[0], send = h ? v2[0] : v2[1];
+    double v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+    return v1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// frame_features() for f64 frame groups of exactly one warp (fft_size 2048), rewritten around what the clock64() phase
+// timings of profiles/r2_k1_pc_experiment.md showed: a warp spends most of this half waiting on dependency chains (a
+// dependent FP64 operation is ~25 cycles away, a dependent shared-memory load ~60), not on any pipe.  Same arithmetic per
+// bin (q = p / P, table log2, central moments about the magnitude centroid), but
+//   * no per-bin running sum is stored: the chunk sums of the first pass, scanned over the lanes, give the running sum at
+//     the 64 chunk ends in registers; two ballots per threshold find the chunk, a sum tree over its 16 bins finds the bin
+//     (was: 32 dependent adds + stores per thread, then a 10-step binary search of dependent loads by four lanes);
+//   * the sub-band sums load eight bins at once and add them as a tree (was: a rolled loop of dependent load -> multiply -> add);
+//   * two accumulator sets in the per-bin sweep (halves the add chains), sums combined by recursive halving and a scan
+//     (39 instead of 85 64-bit shuffles), the record written by the lanes that hold the values.
+// Knife-edge thresholds fall back to the reference's own sequential arithmetic exactly like frame_features().
+template <int LOG2N>
+__device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double> &acc, const double2 *logtab,
+                                                 const StftParams<double> &p, unsigned long long g, bool active, int t,
+                                                 const double *next_src, uint64_t *bar) {
+    using T = double;
+    using C = Cfg<T, LOG2N>;
+    constexpr int M = C::M, K = C::K, TPF = C::TPF;
+    static_assert(TPF == 32, "one warp per frame");
+    const unsigned FULL = 0xffffffffu;
+    T *const bufT = reinterpret_cast<T *>(buf);
+    const int hp = hpar<T>(t);
+    // power of bin 16 c + i (low chunk of lane c) / bin M - 16 c - i (its high chunk), i = 0..15
+    auto lo_ptr = [&](int c) { return bufT + 2 * (17 * c) + hpar<T>(c); };                  // element i at [2 i]
+    auto hi_at = [&](int c, int i) -> T {
+        const int h0c = zslot(M - 16 * c);
+        return bufT[2 * (i == 0 ? h0c : h0c - 1 - i) + hpar<T>(c)];
+    };
+    // ---- zero / subnormal / non-finite power somewhere: magnitudes again with the exact square root (cold)
+    const bool bad_p = !power_is_normal<T>(acc.pmin) || !(acc.lo_sum + acc.hi_sum + acc.mid < (T)INFINITY);
+    if (__any_sync(FULL, bad_p)) {
+        acc.s_m = 0;
+        acc.s_mk = 0;
+#pragma unroll 1
+        for (int u = 0; u < 33; ++u) {
+            if (u == 32 && t != TPF - 1) break;
+            const int b = u < 16 ? 16 * t + u : (u < 32 ? M - 16 * t - 15 + (u - 16) : M / 2);
+            const T m = sqrt(pow_of<T, M, TPF>(buf, b));
+            acc.s_m += m;
+            acc.s_mk += m * (T)b;
+        }
+    }
+    __syncwarp();                                     // every power bin visible to the whole warp
+
+    // ---- sub-band sums (s_a_t.rs:190-230), eight bins per trip: loads first, independent products, tree sums
+    T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
+#pragma unroll 1
+    for (int b0 = p.r_lo[0] + t; b0 < p.r_hi[1]; b0 += 8 * TPF) {
+        T pv[8], a1[8], k1[8], a2[8], k2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = b0 + j * TPF;
+            pv[j] = b < p.r_hi[1] ? pow_of<T, M, TPF>(buf, b) : (T)0;
+        }
+        const T bf0 = (T)b0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = b0 + j * TPF;
+            const T pk = pv[j] * (bf0 + (T)(j * TPF));
+            const bool in1 = b < p.r_hi[0], in2 = b >= p.r_lo[1];
+            a1[j] = in1 ? pv[j] : (T)0; k1[j] = in1 ? pk : (T)0;
+            a2[j] = in2 ? pv[j] : (T)0; k2[j] = in2 ? pk : (T)0;
+        }
+        auto tree8 = [](const T (&x)[8]) { return ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7])); };
+        b1p += tree8(a1); b1pk += tree8(k1); b2p += tree8(a2); b2pk += tree8(k2);
+    }
+    // ---- totals every lane needs: magnitude sums (butterfly), chunk sums (inclusive scan; its last lane has the totals)
+    T sm2[2] = {acc.s_m, acc.s_mk};
+    T inc_lo = acc.lo_sum, inc_hi = acc.hi_sum;
+    unsigned gpmin = acc.pmin;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        sm2[0] += __shfl_xor_sync(FULL, sm2[0], off);
+        sm2[1] += __shfl_xor_sync(FULL, sm2[1], off);
+        const T ua = __shfl_up_sync(FULL, inc_lo, off), ub = __shfl_up_sync(FULL, inc_hi, off);
+        if (t >= off) { inc_lo += ua; inc_hi += ub; }
+        gpmin = min(gpmin, __shfl_xor_sync(FULL, gpmin, off));
+    }
+    const T S_m = sm2[0], S_mk = sm2[1];
+    const T tot_lo = __shfl_sync(FULL, inc_lo, 31), tot_hi = __shfl_sync(FULL, inc_hi, 31), tot_mid = __shfl_sync(FULL, acc.mid, 31);
+    const T P = tot_lo + tot_mid + tot_hi;
+    const T kappa = S_mk / S_m;
+    const T inv_p = 1.0 / P;
+    const bool badq = !power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) ||
+                      abnormal((T)(power_from_hi<T>(gpmin) * inv_p));
+
+    // ---- roll-off (s_a_t.rs:137-145): index = number of bins whose inclusive running sum is below theta * P.  Chunk ends in
+    //      ascending bin order: low chunks of lanes 0..31, bin M/2, high chunks of lanes 31..0.  Lane 2 q + 1 settles
+    //      threshold q: two ballots find the chunk, a sum tree over the chunk's 16 bins finds the bin.
+    const T base_lo = inc_lo - acc.lo_sum;                               // running sum before this lane's low chunk
+    const T base_hi = tot_lo + tot_mid + (tot_hi - inc_hi);              // ... before its high chunk
+    const T end_hi = base_hi + acc.hi_sum;
+    const int vi = t >> 1;
+    const int wq = (t & 1) ? vi : 4;                                     // threshold this lane settles (4: none)
+    int n_lo = 0, n_hi = 0;
+    T my_th = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const T th = (q == 0 ? 0.5 : q == 1 ? 0.75 : q == 2 ? 0.9 : 0.95) * P;
+        const int nl = __popc(__ballot_sync(FULL, inc_lo < th));        // NaN compares false: 0, walk chunk 0
+        const int nh = __popc(__ballot_sync(FULL, end_hi < th));
+        if (wq == q) { n_lo = nl; n_hi = nh; my_th = th; }
+    }
+    const int c_lo = n_lo < 32 ? n_lo : 31, c_hi = n_hi < 32 ? 31 - n_hi : 0;
+    const T bl = __shfl_sync(FULL, base_lo, c_lo), bh = __shfl_sync(FULL, base_hi, c_hi);
+    int roll_res = 0;
+    if (wq < 4) {
+        int res = 0, first = 0;
+        bool walk = false, high = false, amb = false;
+        T base = 0.0, c_at = 0.0, c_prev = 0.0;
+        if (n_lo < 32) {                                                 // crossing inside low chunk n_lo
+            first = 16 * c_lo; base = bl; walk = true;
+        } else if (!(tot_lo + tot_mid < my_th)) {                        // bin M/2
+            res = M / 2; c_at = tot_lo + tot_mid; c_prev = tot_lo;
+        } else if (n_hi < 32) {                                          // high chunk of lane c_hi, ascending bins
+            first = M - 16 * c_hi - 15; base = bh; walk = true; high = true;
+        } else {                                                         // even the last bin stays below (rounding): K
+            res = K; c_prev = P;
+        }
+        if (walk) {
+            T x[16];                                                     // the chunk's powers in ascending bin order
+            if (!high) {
+                const T *const lp = lo_ptr(c_lo);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) x[e] = lp[2 * e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) x[e] = hi_at(c_hi, 15 - e);
+            }
+            T s2[8], s4[4];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s2[e] = x[2 * e] + x[2 * e + 1];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s4[e] = s2[2 * e] + s2[2 * e + 1];
+            const T s8 = s4[0] + s4[1];
+            T run = base;
+            int j = 0;
+            T c = run + s8;                                              // bins 0..7 of the chunk
+            if (c < my_th) { run = c; j = 8; }
+            c = run + (j == 8 ? s4[2] : s4[0]);
+            if (c < my_th) { run = c; j += 4; }
+            c = run + (j == 12 ? s2[6] : j == 8 ? s2[4] : j == 4 ? s2[2] : s2[0]);
+            if (c < my_th) { run = c; j += 2; }
+            T xa = x[0], xb = x[1];
+#pragma unroll
+            for (int e = 2; e < 16; e += 2)
+                if (j == e) { xa = x[e]; xb = x[e + 1]; }
+            c = run + xa;
+            if (c < my_th) { run = c; j += 1; c = run + xb; }
+            if (c < my_th) amb = true;                                   // the chunk ends and this tree disagree by rounding
+            res = first + j;
+            c_at = c;
+            c_prev = run;
+        }
+        // Knife edge: the threshold sits within rounding distance of a running sum, where the reference's own arithmetic
+        // -- a sequential sum of p[i] / P compared with theta -- decides.  Redo it exactly that way (rare).
+        const double tol = 1e-12 * P;
+        if (!amb && res < K) amb = fabs(c_at - my_th) <= tol || (res >= 1 && fabs(my_th - c_prev) <= tol);
+        if (!amb && res == K) amb = fabs(my_th - c_prev) <= tol;
+        if (amb) {
+            const double theta = wq == 0 ? 0.5 : wq == 1 ? 0.75 : wq == 2 ? 0.9 : 0.95;
+            double pseq = 0.0;                                           // power_spectrum.iter().sum(), analyzer.rs:44
+            for (int i = 0; i < K; ++i) pseq += pow_of<T, M, TPF>(buf, i);
+            double csum = 0.0;
+            int i = -1;
+            while (csum < theta && i < K - 1) {
+                ++i;
+                csum += pow_of<T, M, TPF>(buf, i) / pseq;
+            }
+            res = i;
+        }
+        roll_res = res;
+    }
+    // the six bins the sub-band interpolation picks (s_a_t.rs:198-201), fetched now: nothing may read the buffer after the sweep
+    T pick_val = 0.0;
+    if ((t & 1) && t >= 9 && t < 21) pick_val = pow_of<T, M, TPF>(buf, p.pick[(t - 9) / 2]);
+    // ---- the per-bin sweep: central moments about the centroid (in bins), q log2 q, log2 q; two accumulator sets
+    const double2 *const ltab = logtab + (threadIdx.x & 7);
+    T d2s[2] = {0, 0}, d3s[2] = {0, 0}, d4s[2] = {0, 0}, ent[2] = {0, 0}, slq[2] = {0, 0};
+    constexpr int SW = AUS_SWEEP_W;
+    auto sweep4 = [&](const T (&pv)[SW], T d0) {
+        T q[SW], l[SW];
+#pragma unroll
+        for (int c = 0; c < SW; ++c) q[c] = pv[c] * inv_p;                // make_spectrum_pmf, s_a_t.rs:284-290
+#pragma unroll
+        for (int c = 0; c < SW; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
+#pragma unroll
+        for (int c = 0; c < SW; ++c) {
+            const T d = d0 + (T)c;
+            const T dd = d * d;
+            const T w2 = dd * pv[c];
+            d2s[c & 1] += w2;
+            d3s[c & 1] = fma(w2, d, d3s[c & 1]);
+            d4s[c & 1] = fma(w2, dd, d4s[c & 1]);
+            ent[c & 1] = fma(q[c], l[c], ent[c & 1]);
+            slq[c & 1] += l[c];
+        }
+    };
+    {
+        const T *const lp = lo_ptr(t);
+        T dlo = (T)(16 * t) - kappa;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += SW, dlo += (T)SW) {
+            T pv[SW];
+#pragma unroll
+            for (int c = 0; c < SW; ++c) pv[c] = lp[2 * (i0 + c)];
+            sweep4(pv, dlo);
+        }
+        // high chunk, ascending bins M - 16 t - 15 + u  <->  element i = 15 - u (i = 0 sits one slot apart)
+        const int h0 = zslot(M - 16 * t);
+        T dhi = (T)(M - 16 * t - 15) - kappa;
+#pragma unroll 1
+        for (int u0 = 0; u0 < 16; u0 += SW, dhi += (T)SW) {
+            T pv[SW];
+#pragma unroll
+            for (int c = 0; c < SW; ++c) {
+                const int i = 15 - u0 - c;
+                pv[c] = bufT[2 * (i == 0 ? h0 : h0 - 1 - i) + hp];
+            }
+            sweep4(pv, dhi);
+        }
+        if (t == TPF - 1) {                             // bin M/2 sits between the low and the high chunks
+            const T pw = acc.mid;
+            const T d = (T)(M / 2) - kappa;
+            const T dd = d * d, w2 = dd * pw;
+            const T q = pw * inv_p;
+            const T l = Mth<T>::log2_(q, ltab);
+            d2s[0] += w2;
+            d3s[0] = fma(w2, d, d3s[0]);
+            d4s[0] = fma(w2, dd, d4s[0]);
+            ent[0] = fma(q, l, ent[0]);
+            slq[0] += l;
+        }
+    }
+    T e_sum = ent[0] + ent[1], l_sum = slq[0] + slq[1];
+    if (badq) {                                          // warp-uniform, cold: library log2 (0 * -inf = NaN, sum = -inf)
+        e_sum = 0;
+        l_sum = 0;
+#pragma unroll 1
+        for (int u = 0; u < 33; ++u) {
+            if (u == 32 && t != TPF - 1) break;
+            const int b = u < 16 ? 16 * t + u : (u < 32 ? M - 16 * t - 15 + (u - 16) : M / 2);
+            const T q = pow_of<T, M, TPF>(buf, b) * inv_p;
+            const T l = log2(q);
+            e_sum += q * l;
+            l_sum += l;
+        }
+    }
+    // ---- nothing reads the group buffer any more: the next frame's bulk copy starts now and overlaps the reduction, the
+    //      record stores and the set-up of the next iteration (its latency, ~1 000 cycles, used to be waited for in full)
+    fence_proxy_async();
+    __syncwarp();
+    if (next_src != nullptr && t == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(C::N * sizeof(T)));
+        tma_load_1d(buf, next_src, (uint32_t)(C::N * sizeof(T)), bar);
+    }
+    // ---- ten sums by recursive halving: lane t ends up with the total of value t >> 1
+    const T r10[10] = {acc.s_pk, d2s[0] + d2s[1], d3s[0] + d3s[1], d4s[0] + d4s[1], e_sum, l_sum, b1p, b1pk, b2p, b2pk};
+    const T tot = warp_reduce_scatter<10>(r10, t);
+    double *rec = p.raw + g * (unsigned long long)RAW_N;
+    const bool wr = active && p.raw != nullptr;
+    if (wr) {
+        // even lanes 0..18 hold one reduced value each; odd lanes 9..19 fetch the six picked bins; 21, 23, 25 the rest
+        if (!(t & 1) && vi < 10) rec[vi == 0 ? (int)RAW_SPK : vi <= 5 ? (int)RAW_D2 + vi - 1 : (int)RAW_B1P + vi - 6] = tot;
+        if (wq < 4) rec[RAW_ROLL0 + wq] = (double)roll_res;
+        if ((t & 1) && t >= 9 && t < 21) rec[RAW_PICK0 + (t - 9) / 2] = pick_val;
+        if (t == 21) rec[RAW_SM] = S_m;
+        if (t == 23) rec[RAW_SMK] = S_mk;
+        if (t == 25) rec[RAW_P] = P;
+    }
+}
+
 // One thread per frame: raw record -> the 14 features in the declaration order of analyzer.rs:10-23.
 template <typename T>
 __global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, int K) {
@@ -552,8 +889,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const StftParams<T> p, in
 // ---------------------------------------------------------------------------------------------------------
 // Shared-memory tail of the forward kernel (every fft_size): on entry buf holds Z' in the Z layout (frame_fft()).
 template <typename T, int LOG2N>
-__device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const double2 *logtab, const StftParams<T> &p,
-                                             unsigned long long g, bool active, int t, int grp, bool want_feat) {
+__device__ __forceinline__ bool frame_tail_s(Cx<T> *buf, double *scratch, const double2 *logtab, const StftParams<T> &p,
+                                             unsigned long long g, bool active, int t, int grp, bool want_feat,
+                                             const T *next_src = nullptr, uint64_t *bar = nullptr) {
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, K = C::K, TPF = C::TPF;
     // ---- post-twiddle + power + first feature pass; |X|^2 replaces Z in place (each thread touches only its slots)
@@ -566,21 +904,22 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
     const int hp = hpar<T>(t);
     // bin numbers as running floating-point values: converted from the thread index once, not per bin (I2F.F64 is slow)
     T klo_run = (T)(16 * t), khi_run = (T)(M - 16 * t);
+    constexpr int PT = (sizeof(T) == 8 && TPF == 32) ? AUS_TAIL_PAIRS : 4;
 #pragma unroll 1
-    for (int i0 = 0; i0 < 16; i0 += 4, klo_run += (T)4, khi_run -= (T)4) {
-        Cx<T> A[4], B[4], W[4];
+    for (int i0 = 0; i0 < 16; i0 += PT, klo_run += (T)PT, khi_run -= (T)PT) {
+        Cx<T> A[PT], B[PT], W[PT];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PT; ++c) {
             const int i = i0 + c;
             A[c] = buf[17 * t + i];
             B[c] = buf[(c == 0 && i0 == 0) ? (t == 0 ? 0 : h0) : h0 - 1 - i];      // k = 0 pairs with itself
             W[c] = ldg_cx(&p.twNt[i * TPF + t]);
         }
-        T plo[4], phi[4];
+        T plo[PT], phi[PT];
         if (!want_feat) {
             // K2 (spectra only): X replaces Z in place, then the whole row leaves in coalesced stores below
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < PT; ++c) {
                 const int i = i0 + c;
                 Cx<T> Xlo, Xhi;
                 post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
@@ -590,33 +929,34 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
             continue;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PT; ++c) {
             Cx<T> Xlo, Xhi;
             post_twiddle(A[c], B[c], W[c], Xlo, Xhi);
             plo[c] = Xlo.x * Xlo.x + Xlo.y * Xlo.y;
             phi[c] = Xhi.x * Xhi.x + Xhi.y * Xhi.y;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < PT; ++c) {
             const int i = i0 + c;
             bufT[2 * (17 * t + i) + hp] = plo[c];
             bufT[2 * ((c == 0 && i0 == 0) ? h0 : h0 - 1 - i) + hp] = phi[c];
         }
         {
-            T mlo[4], mhi[4];
+            T mlo[PT], mhi[PT];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < PT; ++c) {
                 acc.pmin = min(acc.pmin, min(power_hi(plo[c]), power_hi(phi[c])));
                 mlo[c] = Mth<T>::sqrt_(plo[c]);
                 mhi[c] = Mth<T>::sqrt_(phi[c]);
             }
             const T klo = klo_run, khi = khi_run;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < PT; ++c) {
                 acc.lo_sum += plo[c];
                 acc.hi_sum += phi[c];
                 acc.add(klo + (T)c, mlo[c], plo[c]);
-                acc.add(khi - (T)c, mhi[c], phi[c]);
+                if constexpr (AUS_SPLIT_TAIL_ACC) acc.add2(khi - (T)c, mhi[c], phi[c]);
+                else acc.add(khi - (T)c, mhi[c], phi[c]);
             }
         }
     }
@@ -639,7 +979,16 @@ __device__ __forceinline__ void frame_tail_s(Cx<T> *buf, double *scratch, const 
         acc.pmin = min(acc.pmin, power_hi(pm));
         if (want_feat) acc.add((T)(M / 2), Mth<T>::sqrt_(pm), pm);
     }
-    if (want_feat) frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, true);
+    if (want_feat) acc.merge();
+    if (want_feat) {
+        if constexpr (AUS_FEAT32 && sizeof(T) == 8 && TPF == 32) {
+            frame_features32<LOG2N>(buf, acc, logtab, p, g, active, t, next_src, bar);
+            return next_src != nullptr;                 // the next frame's bulk copy is already in flight
+        } else {
+            frame_features<T, LOG2N>(buf, acc, scratch, logtab, p, g, active, t, grp, true);
+        }
+    }
+    return false;
 }
 
 // register-resident variants, defined in aus_stft_r.cuh
@@ -677,16 +1026,23 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
     const bool want_feat = FEAT && p.raw != nullptr;
     int f = 0;
     // frame g of the batch -> its samples: file (frames only move forward, so the search resumes at fq), start, length
+    // (first frame, first frame of the next file, length, base pointer) of the file the last located frame lies in: the next
+    // frame of this group is located from them without touching the descriptor arrays again when it is in the same file
+    unsigned long long cur_first = 0, cur_next = 0, cur_len = 0;
+    const T *cur_base = p.audio;
     auto locate = [&](unsigned long long gq, int &fq, const T *&srcq, int &Lq) -> bool {
         srcq = p.audio;
         Lq = 0;
         if (gq >= p.total_frames) return false;
         while (gq >= p.file_first[fq + 1]) ++fq;
-        const unsigned long long s = (gq - p.file_first[fq]) * (unsigned long long)p.hop;
-        const unsigned long long len = p.file_len[fq];
-        const unsigned long long rem = len > s ? len - s : 0ull;
+        cur_first = p.file_first[fq];
+        cur_next = p.file_first[fq + 1];
+        cur_len = p.file_len[fq];
+        cur_base = p.audio + p.file_off[fq];
+        const unsigned long long s = (gq - cur_first) * (unsigned long long)p.hop;
+        const unsigned long long rem = cur_len > s ? cur_len - s : 0ull;
         Lq = rem < (unsigned long long)N ? (int)rem : N;                // fft.rs:130-144
-        srcq = p.audio + p.file_off[fq] + s;
+        srcq = cur_base + s;
         return true;
     };
     bool staged = false;                                                // this iteration's bulk copy was issued early (below)
@@ -783,10 +1139,25 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
             }
         } else {
             frame_fft<T, LOG2N>(buf, p, t, grp, prewindowed, direct ? reinterpret_cast<const Cx<T> *>(src) : nullptr, v, wpre);
-            frame_tail_s<T, LOG2N>(buf, scratch, logtab, p, g, active, t, grp, want_feat);
+            const T *next_src = nullptr;
+            if constexpr (AUS_FEAT32 && AUS_EARLY_TMA && sizeof(T) == 8 && TPF == 32) {
+                // the next frame of this warp, located now: the feature pass issues its bulk copy the moment the buffer is free
+                const unsigned long long g2 = g + stride;
+                if (want_feat && active && g2 < cur_next && p.tma_ok && !p.direct) {       // same file: no descriptor loads
+                    const unsigned long long s2 = (g2 - cur_first) * (unsigned long long)p.hop;
+                    const T *srcn = cur_base + s2;
+                    if (s2 + N <= cur_len && (reinterpret_cast<uintptr_t>(srcn) & 15) == 0) next_src = srcn;
+                }
+            }
+            staged = frame_tail_s<T, LOG2N>(buf, scratch, logtab, p, g, active, t, grp, want_feat, next_src, bar);
         }
-        fence_proxy_async();                                            // generic accesses to buf before the next TMA write
-        group_sync<TPF, C::BLOCK>(grp);
+#ifndef AUS_EXP_NOFENCE
+#define AUS_EXP_NOFENCE 0        // timing experiment only (violates the proxy ordering rules): no fence at the loop end
+#endif
+        if (!(AUS_EXP_NOFENCE || (!RR && staged))) {                    // (already fenced where the early copy was issued)
+            fence_proxy_async();                                        // generic accesses to buf before the next TMA write
+            group_sync<TPF, C::BLOCK>(grp);
+        }
         if constexpr (RR && TPF > 32) {
             if (half2 != nullptr && t == 0)                             // second half of the early copy (see above)
                 tma_load_1d(reinterpret_cast<T *>(buf) + N / 2, half2, (uint32_t)((N / 2) * sizeof(T)), bar);

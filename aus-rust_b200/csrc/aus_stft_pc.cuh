@@ -234,47 +234,6 @@ __device__ __forceinline__ void pc_producer_tail(Cx<double> *buf, double *pwb, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Sum of NV <= 16 values over the warp with 16 instead of 5 NV 64-bit shuffles: recursive halving.  Every step a lane
-// keeps the half of the values its lane bit selects and adds the partner's copy of that half; after the five steps lane t
-// holds the warp total of value t >> 1 (values >= NV are zero).  Fixed order -> deterministic.
-template <int NV> __device__ __forceinline__ double warp_reduce_scatter(const double (&in)[NV], int t) {
-    static_assert(NV <= 16, "at most 16 values");
-    double v8[8];
-    {
-        const bool h = (t & 16) != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const double lo = in[i], hi = i + 8 < NV ? in[i + 8] : 0.0;
-            const double keep = h ? hi : lo, send = h ? lo : hi;
-            v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    double v4[4];
-    {
-        const bool h = (t & 8) != 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double keep = h ? v8[i + 4] : v8[i], send = h ? v8[i] : v8[i + 4];
-            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    double v2[2];
-    {
-        const bool h = (t & 4) != 0;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const double keep = h ? v4[i + 2] : v4[i], send = h ? v4[i] : v4[i + 2];
-            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    const bool h = (t & 2) != 0;
-    const double keep = h ? v2[1] : v2[0], send = h ? v2[0] : v2[1];
-    double v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-    return v1;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // Consumer: the 14 features' raw record from one power row (analyzer.rs:41-81).  Thread t owns the low chunk
 // [16 t, 16 t + 16) and the high chunk (M - 16 t - 16, M - 16 t]; lane 31 also bin M/2.
 template <int LOG2N>
