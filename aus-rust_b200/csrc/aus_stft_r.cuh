@@ -427,6 +427,297 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
     }
 }
 
+#ifndef AUS_FEATR32
+#define AUS_FEATR32 1            // one-warp frame groups: latency-trimmed frame_features_r (see frame_features_r32)
+#endif
+
+// warp_reduce_scatter for the kernel's arithmetic type (float shuffles are one instruction, double ones two)
+template <int NV, typename R> __device__ __forceinline__ R warp_reduce_scatter_t(const R (&in)[NV], int t) {
+    static_assert(NV <= 16, "at most 16 values");
+    R v8[8];
+    {
+        const bool h = (t & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const R lo = in[i], hi = i + 8 < NV ? in[i + 8] : (R)0;
+            const R keep = h ? hi : lo, send = h ? lo : hi;
+            v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    R v4[4];
+    {
+        const bool h = (t & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const R keep = h ? v8[i + 4] : v8[i], send = h ? v8[i] : v8[i + 4];
+            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    R v2[2];
+    {
+        const bool h = (t & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const R keep = h ? v4[i + 2] : v4[i], send = h ? v4[i] : v4[i + 2];
+            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool h = (t & 2) != 0;
+    const R keep = h ? v2[1] : v2[0], send = h ? v2[0] : v2[1];
+    R v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+    return v1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// frame_features_r() for frame groups of exactly one warp (fft_size 2048; f64 and f32), with the dependency chains of
+// the general version cut the way frame_features32() does it for the shared-memory tail (profiles/r2_k1_pc_experiment.md:
+// a warp spends this half of the work waiting on dependent operations, not on a pipe):
+//   * the running sum at the 32 chunk ends comes from a warp scan of the chunk sums and stays in registers; one ballot per
+//     roll-off threshold finds the chunk and a sum tree over its 32 bins finds the bin (was: chunk ends published to
+//     shared memory, a 5-step binary search of dependent loads, then 32 dependent adds or a 5-step search of stored sums);
+//   * no per-bin running sum is stored even in the forward kernels (STORE_CUM builds);
+//   * sub-band sums load eight bins at once and add them as trees; ten sums are combined by recursive halving.
+// Same arithmetic per bin; knife-edge thresholds fall back to the reference's sequential arithmetic (f64) as before.
+template <typename T, int LOG2N, typename C>
+__device__ __forceinline__ void frame_features_r32(T *pw, T s_m, T s_mk, T s_pk, T p_part, unsigned pmin, const double2 *logtab,
+                                                   const StftParams<T> &p, unsigned long long g, bool active, int t,
+                                                   bool mags_from_sqrt) {
+    constexpr int M = C::M, K = C::K, TPF = C::TPF;
+    static_assert(TPF == 32, "one warp per frame");
+    const unsigned FULL = 0xffffffffu;
+    const int c0 = 33 * t;                              // slot of bin 32 t
+    const int cnt = (t == TPF - 1) ? 33 : 32;           // bins in this thread's chunk (bin M: slot c0 + 32)
+    __syncwarp();                                       // every power bin visible to the whole warp
+
+    // zero / subnormal / non-finite power somewhere: magnitudes again with the exact square root (cold)
+    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt && (!power_is_normal<T>(pmin) || !(p_part < (T)INFINITY));
+    if (__any_sync(FULL, bad_p)) {
+        s_m = 0;
+        s_mk = 0;
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) {
+            const T m = Mth<T>::sqrt_exact(pw[c0 + j]);
+            s_m += m;
+            s_mk += m * (T)(32 * t + j);
+        }
+    }
+    // ---- sub-band sums (s_a_t.rs:190-230), eight bins per trip: loads first, independent products, tree sums
+    T b1p = 0, b1pk = 0, b2p = 0, b2pk = 0;
+#pragma unroll 1
+    for (int b0 = p.r_lo[0] + t; b0 < p.r_hi[1]; b0 += 8 * TPF) {
+        T pv[8], a1[8], k1[8], a2[8], k2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = b0 + j * TPF;
+            pv[j] = b < p.r_hi[1] ? pw[pslot<M>(b)] : (T)0;
+        }
+        const T bf0 = (T)b0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = b0 + j * TPF;
+            const T pk = pv[j] * (bf0 + (T)(j * TPF));
+            const bool in1 = b < p.r_hi[0], in2 = b >= p.r_lo[1];
+            a1[j] = in1 ? pv[j] : (T)0; k1[j] = in1 ? pk : (T)0;
+            a2[j] = in2 ? pv[j] : (T)0; k2[j] = in2 ? pk : (T)0;
+        }
+        auto tree8 = [](const T (&x)[8]) { return ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7])); };
+        b1p += tree8(a1); b1pk += tree8(k1); b2p += tree8(a2); b2pk += tree8(k2);
+    }
+    // ---- totals every lane needs: sum m, sum m k, P (butterfly), smallest power (f64)
+    T r3[3] = {s_m, s_mk, p_part};
+    unsigned gpmin = pmin;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r3[i] += __shfl_xor_sync(FULL, r3[i], off);
+        if constexpr (sizeof(T) == 8) gpmin = min(gpmin, __shfl_xor_sync(FULL, gpmin, off));
+    }
+    const double S_m = (double)r3[0], S_mk = (double)r3[1], P = (double)r3[2];
+    const T kappa = (T)(S_mk / S_m);
+    const T inv_p = (T)(1.0 / P);
+    bool badq = false;                                   // (f32 uses lg2.approx, which handles every argument)
+    if constexpr (sizeof(T) == 8)
+        badq = !power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) || abnormal((T)(power_from_hi<T>(gpmin) * inv_p));
+
+    // ---- the per-bin sweep over this thread's 32 consecutive bins: central moments, q log2 q, log2 q, chunk sum
+    const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);
+    T d2s[2] = {0, 0}, d3s[2] = {0, 0}, d4s[2] = {0, 0}, ent[2] = {0, 0}, slq[2] = {0, 0}, cs[2] = {0, 0};
+    {
+        T dj = (T)(32 * t) - kappa;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += 4, dj += (T)4) {
+            T pv[4], q[4], l[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pv[c] = pw[c0 + j0 + c];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[c] = pv[c] * inv_p;               // make_spectrum_pmf, s_a_t.rs:284-290
+#pragma unroll
+            for (int c = 0; c < 4; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const T d = dj + (T)c;
+                const T dd = d * d;
+                const T w2 = dd * pv[c];
+                d2s[c & 1] += w2;
+                d3s[c & 1] += w2 * d;
+                d4s[c & 1] += w2 * dd;
+                ent[c & 1] += q[c] * l[c];
+                slq[c & 1] += l[c];
+                cs[c & 1] += pv[c];
+            }
+        }
+    }
+    T p_last = (T)0;                                     // bin M closes the last chunk
+    if (t == TPF - 1) {
+        p_last = pw[c0 + 32];
+        const T d = (T)M - kappa;
+        const T dd = d * d;
+        const T w2 = dd * p_last;
+        const T q = p_last * inv_p;
+        const T l = Mth<T>::log2_(q, ltab);
+        d2s[0] += w2;
+        d3s[0] += w2 * d;
+        d4s[0] += w2 * dd;
+        ent[0] += q * l;
+        slq[0] += l;
+    }
+    T e_sum = ent[0] + ent[1], l_sum = slq[0] + slq[1];
+    if (badq) {                                          // warp-uniform, cold: library log2 (0 * -inf = NaN, sum = -inf)
+        e_sum = 0;
+        l_sum = 0;
+#pragma unroll 1
+        for (int j = 0; j < cnt; ++j) {
+            const T q = pw[c0 + j] * inv_p;
+            const T l = Mth<T>::log2_exact(q);
+            e_sum += q * l;
+            l_sum += l;
+        }
+    }
+    // ---- running sum at the chunk ends: inclusive scan of the chunk sums of bins [32 t, 32 t + 32)
+    const T csum = cs[0] + cs[1];
+    T inc = csum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const T u = __shfl_up_sync(FULL, inc, off);
+        if (t >= off) inc += u;
+    }
+    const T base = inc - csum;                           // running sum before this lane's chunk
+    // ---- roll-off (s_a_t.rs:137-145): lane 2 q + 1 settles threshold q
+    const int vi = t >> 1;
+    const int wq = (t & 1) ? vi : 4;
+    int n_below = 0;
+    T my_th = (T)0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const T th = (T)((q == 0 ? 0.5 : q == 1 ? 0.75 : q == 2 ? 0.9 : 0.95) * P);
+        const int nb = __popc(__ballot_sync(FULL, inc < th));            // chunks that end below the threshold
+        if (wq == q) { n_below = nb; my_th = th; }
+    }
+    const int cidx = n_below < 32 ? n_below : 31;
+    const T cbase = __shfl_sync(FULL, base, cidx);
+    const T tot32 = __shfl_sync(FULL, inc, 31);                          // running sum through bin M - 1
+    const T pM = __shfl_sync(FULL, p_last, 31);
+    int roll_res = 0;
+    if (wq < 4) {
+        int res;
+        T c_at = (T)0, c_prev = (T)0;
+        bool amb = false;
+        if (n_below < 32) {
+            const T *const pl = pw + 33 * cidx;
+            T x[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = pl[e];
+            T s2[16], s4[8], s8[4], s16[2];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) s2[e] = x[2 * e] + x[2 * e + 1];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s4[e] = s2[2 * e] + s2[2 * e + 1];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s8[e] = s4[2 * e] + s4[2 * e + 1];
+            s16[0] = s8[0] + s8[1];
+            s16[1] = s8[2] + s8[3];
+            T run = cbase;
+            int j = 0;
+            T c = run + s16[0];
+            if (c < my_th) { run = c; j = 16; }
+            T sel = s8[0];
+#pragma unroll
+            for (int e = 1; e < 4; ++e) if (j == 8 * e) sel = s8[e];
+            c = run + sel;
+            if (c < my_th) { run = c; j += 8; }
+            sel = s4[0];
+#pragma unroll
+            for (int e = 1; e < 8; ++e) if (j == 4 * e) sel = s4[e];
+            c = run + sel;
+            if (c < my_th) { run = c; j += 4; }
+            sel = s2[0];
+#pragma unroll
+            for (int e = 1; e < 16; ++e) if (j == 2 * e) sel = s2[e];
+            c = run + sel;
+            if (c < my_th) { run = c; j += 2; }
+            T xa = x[0], xb = x[1];
+#pragma unroll
+            for (int e = 2; e < 32; e += 2) if (j == e) { xa = x[e]; xb = x[e + 1]; }
+            c = run + xa;
+            if (c < my_th) { run = c; j += 1; c = run + xb; }
+            res = 32 * cidx + j;
+            if (c < my_th) {                                             // nothing in this chunk reaches the threshold
+                if (cidx == TPF - 1) {                                   // ... the last chunk also holds bin M
+                    run = c;
+                    c = run + pM;
+                    res = M;
+                    if (c < my_th) { res = K; run = c; }                 // even bin M stays below (the reference answers K - 1)
+                } else {
+                    amb = true;                                          // scan and tree disagree by rounding
+                }
+            }
+            c_at = c;
+            c_prev = run;
+        } else {                                                         // all 32 chunk ends below: bin M or beyond
+            const T c = tot32 + pM;
+            res = M;
+            c_at = c;
+            c_prev = tot32;
+            if (c < my_th) { res = K; c_prev = c; }
+        }
+        if constexpr (sizeof(T) == 8) {
+            // Knife edge: the threshold sits within rounding distance of a running sum, where the reference's own arithmetic
+            // -- a sequential sum of p[i] / P compared with theta (s_a_t.rs:137-145) -- decides (rare)
+            const double tol = 1e-12 * P;
+            if (!amb && res < K) amb = fabs((double)c_at - (double)my_th) <= tol || (res >= 1 && fabs((double)my_th - (double)c_prev) <= tol);
+            if (!amb && res == K) amb = fabs((double)my_th - (double)c_prev) <= tol;
+            if (amb) {
+                const double theta = wq == 0 ? 0.5 : wq == 1 ? 0.75 : wq == 2 ? 0.9 : 0.95;
+                double pseq = 0.0;                                       // power_spectrum.iter().sum(), analyzer.rs:44
+                for (int i = 0; i < K; ++i) pseq += (double)pw[pslot<M>(i)];
+                double csq = 0.0;
+                int i = -1;
+                while (csq < theta && i < K - 1) {
+                    ++i;
+                    csq += (double)pw[pslot<M>(i)] / pseq;
+                }
+                res = i;
+            }
+        }
+        roll_res = res;
+    }
+    T pick_val = (T)0;
+    if ((t & 1) && t >= 9 && t < 21) pick_val = pw[pslot<M>(p.pick[(t - 9) / 2])];
+    // ---- ten sums by recursive halving: lane t ends up with the total of value t >> 1
+    const T r10[10] = {s_pk, d2s[0] + d2s[1], d3s[0] + d3s[1], d4s[0] + d4s[1], e_sum, l_sum, b1p, b1pk, b2p, b2pk};
+    const T tot = warp_reduce_scatter_t<10, T>(r10, t);
+    if (active && p.raw != nullptr) {
+        double *rec = p.raw + g * (unsigned long long)RAW_N;
+        if (!(t & 1) && vi < 10) rec[vi == 0 ? (int)RAW_SPK : vi <= 5 ? (int)RAW_D2 + vi - 1 : (int)RAW_B1P + vi - 6] = (double)tot;
+        if (wq < 4) rec[RAW_ROLL0 + wq] = (double)roll_res;
+        if ((t & 1) && t >= 9 && t < 21) rec[RAW_PICK0 + (t - 9) / 2] = (double)pick_val;
+        if (t == 21) rec[RAW_SM] = S_m;
+        if (t == 23) rec[RAW_SMK] = S_mk;
+        if (t == 25) rec[RAW_P] = P;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Real-FFT split + power + first feature pass straight from the registers left by frame_fft_keep().
 template <typename T, int LOG2N, typename C, bool SHFL, bool FEAT>
@@ -546,7 +837,10 @@ __device__ __forceinline__ void frame_tail_r(Cx<T> (&v)[32], Cx<T> *buf, double 
     const T s_mk = (tf * s_lo + c_lo) + (mt * s_hi - c_hi);
     const T s_pk = (tf * p_lo + pc_lo) + (mt * p_hi - pc_hi);
     const T p_part = p_lo + p_hi;
-    if (want_feat) frame_features_r<T, LOG2N, C, true>(pw, pw + RLay<M>::CO, s_m, s_mk, s_pk, p_part, pmin, scratch, logtab, p, g, active, t, grp, true);
+    if (want_feat) {
+        if constexpr (AUS_FEATR32 && TPF == 32) frame_features_r32<T, LOG2N, C>(pw, s_m, s_mk, s_pk, p_part, pmin, logtab, p, g, active, t, true);
+        else frame_features_r<T, LOG2N, C, true>(pw, pw + RLay<M>::CO, s_m, s_mk, s_pk, p_part, pmin, scratch, logtab, p, g, active, t, grp, true);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -630,7 +924,8 @@ __global__ void __maxnreg__((CfgA<T, LOG2N>::MAXREG)) analyzer_kernel(const Stft
             s_p += pv;
             s_pk += pv * (T)M;
         }
-        frame_features_r<T, LOG2N, C, false>(pw, nullptr, s_m, s_mk, s_pk, s_p, pmin, scratch, logtab, p, g, active, t, grp, false);
+        if constexpr (AUS_FEATR32 && TPF == 32) frame_features_r32<T, LOG2N, C>(pw, s_m, s_mk, s_pk, s_p, pmin, logtab, p, g, active, t, false);
+        else frame_features_r<T, LOG2N, C, false>(pw, nullptr, s_m, s_mk, s_pk, s_p, pmin, scratch, logtab, p, g, active, t, grp, false);
         group_sync<TPF, C::BLOCK>(grp);                    // the searches are done before the next row overwrites pw
     }
 }
