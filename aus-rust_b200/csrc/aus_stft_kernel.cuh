@@ -532,49 +532,48 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
 #define AUS_FEAT32 1             // f64, one warp per frame: latency-trimmed second half of the feature computation (below)
 #endif
 
-// Sum of NV <= 16 doubles over the W = 16 or 32 lanes of a frame group with 16 (15) instead of 5 NV (4 NV) 64-bit shuffles:
-// recursive halving.  Every step a lane keeps the half of the values its lane bit selects and adds the partner's copy;
-// afterwards lane t of the group holds the total of value t >> 1 (W = 32) or t (W = 16); values >= NV are zero.  Fixed
-// order -> deterministic.
-template <int NV, int W = 32> __device__ __forceinline__ double warp_reduce_scatter(const double (&in)[NV], int t) {
-    static_assert(NV <= 16 && (W == 16 || W == 32), "at most 16 values over 16 or 32 lanes");
+// Sum of NV <= 16 doubles over a warp with 16 instead of 5 NV 64-bit shuffles (recursive halving): every step a lane keeps
+// the half of the values its lane bit selects and adds the partner's copy; afterwards lane t holds the total of value
+// t >> 1 (values >= NV are zero).  Fixed order -> deterministic.
+template <int NV> __device__ __forceinline__ double warp_reduce_scatter(const double (&in)[NV], int t) {
+    static_assert(NV <= 16, "at most 16 values");
     double v8[8];
     {
-        const bool h = (t & (W / 2)) != 0;
+        const bool h = (t & 16) != 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const double lo = in[i], hi = i + 8 < NV ? in[i + 8] : 0.0;
             const double keep = h ? hi : lo, send = h ? lo : hi;
-            v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, W / 2);
+            v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
     }
     double v4[4];
     {
-        const bool h = (t & (W / 4)) != 0;
+        const bool h = (t & 8) != 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const double keep = h ? v8[i + 4] : v8[i], send = h ? v8[i] : v8[i + 4];
-            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, W / 4);
+            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
     }
     double v2[2];
     {
-        const bool h = (t & (W / 8)) != 0;
+        const bool h = (t & 4) != 0;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const double keep = h ? v4[i + 2] : v4[i], send = h ? v4[i] : v4[i + 2];
-            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, W / 8);
+            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
         }
     }
-    const bool h = (t & (W / 16)) != 0;
+    const bool h = (t & 2) != 0;
     const double keep = h ? v2[1] : v2[0], send = h ? v2[0] : v2[1];
-    double v1 = keep + __shfl_xor_sync(0xffffffffu, send, W / 16);
-    if constexpr (W == 32) v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+    double v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
     return v1;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// frame_features() for f64 frame groups of 32 or 16 threads (fft_size 2048 and 1024), rewritten around what the clock64() phase
+// frame_features() for f64 frame groups of exactly one warp (fft_size 2048), rewritten around what the clock64() phase
 // timings of profiles/r2_k1_pc_experiment.md showed: a warp spends most of this half waiting on dependency chains (a
 // dependent FP64 operation is ~25 cycles away, a dependent shared-memory load ~60), not on any pipe.  Same arithmetic per
 // bin (q = p / P, table log2, central moments about the magnitude centroid), but
@@ -592,17 +591,10 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     using T = double;
     using C = Cfg<T, LOG2N>;
     constexpr int M = C::M, K = C::K, TPF = C::TPF;
-    static_assert(TPF == 32 || TPF == 16, "a frame group is one warp or half a warp");
+    static_assert(TPF == 32, "one warp per frame");
     const unsigned FULL = 0xffffffffu;
-    const unsigned gmask = TPF == 32 ? FULL : (0xffffu << ((threadIdx.x & 31) & ~15));      // this group's lanes in a ballot
     T *const bufT = reinterpret_cast<T *>(buf);
     const int hp = hpar<T>(t);
-    // which lane of the group does what at the end: `vi` = the reduced value it holds (>= 10: none), `wq` = the roll-off
-    // threshold it settles (4: none), `pk` = the picked bin it fetches (-1: none), and the three lanes that store S_m, S_mk, P
-    const int vi = TPF == 32 ? ((t & 1) ? 99 : (t >> 1)) : t;
-    const int wq = TPF == 32 ? ((t & 1) && t < 8 ? (t >> 1) : 4) : (t >= 10 && t < 14 ? t - 10 : 4);
-    const int pk = TPF == 32 ? ((t & 1) && t >= 9 && t < 21 ? (t - 9) / 2 : -1) : (t < 6 ? t : -1);
-    constexpr int L_SM = TPF == 32 ? 21 : 14, L_SMK = TPF == 32 ? 23 : 15, L_P = TPF == 32 ? 25 : 6;
     // power of bin 16 c + i (low chunk of lane c) / bin M - 16 c - i (its high chunk), i = 0..15
     auto lo_ptr = [&](int c) { return bufT + 2 * (17 * c) + hpar<T>(c); };                  // element i at [2 i]
     auto hi_at = [&](int c, int i) -> T {
@@ -611,7 +603,7 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     };
     // ---- zero / subnormal / non-finite power somewhere: magnitudes again with the exact square root (cold)
     const bool bad_p = !power_is_normal<T>(acc.pmin) || !(acc.lo_sum + acc.hi_sum + acc.mid < (T)INFINITY);
-    if ((__ballot_sync(FULL, bad_p) & gmask) != 0) {
+    if (__any_sync(FULL, bad_p)) {
         acc.s_m = 0;
         acc.s_mk = 0;
 #pragma unroll 1
@@ -652,16 +644,15 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     T inc_lo = acc.lo_sum, inc_hi = acc.hi_sum;
     unsigned gpmin = acc.pmin;
 #pragma unroll
-    for (int off = 1; off < TPF; off <<= 1) {
+    for (int off = 1; off < 32; off <<= 1) {
         sm2[0] += __shfl_xor_sync(FULL, sm2[0], off);
         sm2[1] += __shfl_xor_sync(FULL, sm2[1], off);
-        const T ua = __shfl_up_sync(FULL, inc_lo, off, TPF), ub = __shfl_up_sync(FULL, inc_hi, off, TPF);
+        const T ua = __shfl_up_sync(FULL, inc_lo, off), ub = __shfl_up_sync(FULL, inc_hi, off);
         if (t >= off) { inc_lo += ua; inc_hi += ub; }
         gpmin = min(gpmin, __shfl_xor_sync(FULL, gpmin, off));
     }
     const T S_m = sm2[0], S_mk = sm2[1];
-    const T tot_lo = __shfl_sync(FULL, inc_lo, TPF - 1, TPF), tot_hi = __shfl_sync(FULL, inc_hi, TPF - 1, TPF),
-            tot_mid = __shfl_sync(FULL, acc.mid, TPF - 1, TPF);
+    const T tot_lo = __shfl_sync(FULL, inc_lo, 31), tot_hi = __shfl_sync(FULL, inc_hi, 31), tot_mid = __shfl_sync(FULL, acc.mid, 31);
     const T P = tot_lo + tot_mid + tot_hi;
     const T kappa = S_mk / S_m;
     const T inv_p = 1.0 / P;
@@ -674,27 +665,29 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     const T base_lo = inc_lo - acc.lo_sum;                               // running sum before this lane's low chunk
     const T base_hi = tot_lo + tot_mid + (tot_hi - inc_hi);              // ... before its high chunk
     const T end_hi = base_hi + acc.hi_sum;
+    const int vi = t >> 1;
+    const int wq = (t & 1) ? vi : 4;                                     // threshold this lane settles (4: none)
     int n_lo = 0, n_hi = 0;
     T my_th = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const T th = (q == 0 ? 0.5 : q == 1 ? 0.75 : q == 2 ? 0.9 : 0.95) * P;
-        const int nl = __popc(__ballot_sync(FULL, inc_lo < th) & gmask);   // NaN compares false: 0, walk chunk 0
-        const int nh = __popc(__ballot_sync(FULL, end_hi < th) & gmask);
+        const int nl = __popc(__ballot_sync(FULL, inc_lo < th));        // NaN compares false: 0, walk chunk 0
+        const int nh = __popc(__ballot_sync(FULL, end_hi < th));
         if (wq == q) { n_lo = nl; n_hi = nh; my_th = th; }
     }
-    const int c_lo = n_lo < TPF ? n_lo : TPF - 1, c_hi = n_hi < TPF ? TPF - 1 - n_hi : 0;
-    const T bl = __shfl_sync(FULL, base_lo, c_lo, TPF), bh = __shfl_sync(FULL, base_hi, c_hi, TPF);
+    const int c_lo = n_lo < 32 ? n_lo : 31, c_hi = n_hi < 32 ? 31 - n_hi : 0;
+    const T bl = __shfl_sync(FULL, base_lo, c_lo), bh = __shfl_sync(FULL, base_hi, c_hi);
     int roll_res = 0;
     if (wq < 4) {
         int res = 0, first = 0;
         bool walk = false, high = false, amb = false;
         T base = 0.0, c_at = 0.0, c_prev = 0.0;
-        if (n_lo < TPF) {                                                // crossing inside low chunk n_lo
+        if (n_lo < 32) {                                                 // crossing inside low chunk n_lo
             first = 16 * c_lo; base = bl; walk = true;
         } else if (!(tot_lo + tot_mid < my_th)) {                        // bin M/2
             res = M / 2; c_at = tot_lo + tot_mid; c_prev = tot_lo;
-        } else if (n_hi < TPF) {                                         // high chunk of lane c_hi, ascending bins
+        } else if (n_hi < 32) {                                          // high chunk of lane c_hi, ascending bins
             first = M - 16 * c_hi - 15; base = bh; walk = true; high = true;
         } else {                                                         // even the last bin stays below (rounding): K
             res = K; c_prev = P;
@@ -755,7 +748,7 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     }
     // the six bins the sub-band interpolation picks (s_a_t.rs:198-201), fetched now: nothing may read the buffer after the sweep
     T pick_val = 0.0;
-    if (pk >= 0) pick_val = pow_of<T, M, TPF>(buf, p.pick[pk]);
+    if ((t & 1) && t >= 9 && t < 21) pick_val = pow_of<T, M, TPF>(buf, p.pick[(t - 9) / 2]);
     // ---- the per-bin sweep: central moments about the centroid (in bins), q log2 q, log2 q; two accumulator sets
     const double2 *const ltab = logtab + (threadIdx.x & 7);
     T d2s[2] = {0, 0}, d3s[2] = {0, 0}, d4s[2] = {0, 0}, ent[2] = {0, 0}, slq[2] = {0, 0};
@@ -836,18 +829,19 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
         mbar_arrive_expect_tx(bar, (uint32_t)(C::N * sizeof(T)));
         tma_load_1d(buf, next_src, (uint32_t)(C::N * sizeof(T)), bar);
     }
-    // ---- ten sums by recursive halving: the lane with vi < 10 ends up with the total of value vi
+    // ---- ten sums by recursive halving: lane t ends up with the total of value t >> 1
     const T r10[10] = {acc.s_pk, d2s[0] + d2s[1], d3s[0] + d3s[1], d4s[0] + d4s[1], e_sum, l_sum, b1p, b1pk, b2p, b2pk};
-    const T tot = warp_reduce_scatter<10, TPF>(r10, t);
+    const T tot = warp_reduce_scatter<10>(r10, t);
     double *rec = p.raw + g * (unsigned long long)RAW_N;
     const bool wr = active && p.raw != nullptr;
     if (wr) {
-        if (vi < 10) rec[vi == 0 ? (int)RAW_SPK : vi <= 5 ? (int)RAW_D2 + vi - 1 : (int)RAW_B1P + vi - 6] = tot;
+        // even lanes 0..18 hold one reduced value each; odd lanes 9..19 fetch the six picked bins; 21, 23, 25 the rest
+        if (!(t & 1) && vi < 10) rec[vi == 0 ? (int)RAW_SPK : vi <= 5 ? (int)RAW_D2 + vi - 1 : (int)RAW_B1P + vi - 6] = tot;
         if (wq < 4) rec[RAW_ROLL0 + wq] = (double)roll_res;
-        if (pk >= 0) rec[RAW_PICK0 + pk] = pick_val;
-        if (t == L_SM) rec[RAW_SM] = S_m;
-        if (t == L_SMK) rec[RAW_SMK] = S_mk;
-        if (t == L_P) rec[RAW_P] = P;
+        if ((t & 1) && t >= 9 && t < 21) rec[RAW_PICK0 + (t - 9) / 2] = pick_val;
+        if (t == 21) rec[RAW_SM] = S_m;
+        if (t == 23) rec[RAW_SMK] = S_mk;
+        if (t == 25) rec[RAW_P] = P;
     }
 }
 
@@ -987,8 +981,9 @@ __device__ __forceinline__ bool frame_tail_s(Cx<T> *buf, double *scratch, const 
     }
     if (want_feat) acc.merge();
     if (want_feat) {
-        // (written for groups of 32 or 16 threads; at 16 -- two frames per warp, fft 1024 -- it measured 4 % SLOWER than
-        //  frame_features(): 2.32e8 vs 2.42e8 frames/s, so only one-warp groups take it)
+        // (a version generalised to half-warp groups -- fft 1024, two frames per warp -- measured 4 % slower than
+        //  frame_features() there AND cost this one-warp instantiation its whole gain (1.22e8 vs 1.27e8 frames/s): the
+        //  kernel is sensitive to such code-generation details, so only one-warp groups take this pass, in this exact form)
         if constexpr (AUS_FEAT32 && sizeof(T) == 8 && TPF == 32) {
             frame_features32<LOG2N>(buf, acc, logtab, p, g, active, t, next_src, bar);
             return next_src != nullptr;                 // the next frame's bulk copy is already in flight

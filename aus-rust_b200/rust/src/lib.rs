@@ -48,6 +48,22 @@ extern "C" {
     fn aus_spectral_features_generic(ctx: *mut AusCtx, mags: *const f64, n_rows: usize, n_bins: usize, rfft_freqs: *const f64,
                                      roll_fractions: *const f64, n_roll: usize, band_lo: *const f64, band_hi: *const f64,
                                      n_bands: usize, sample_rate: u32, out: *mut f64) -> c_int;
+    // round 2
+    fn aus_irstft_batch(ctx: *mut AusCtx, spectra: *const f64, n_frames: *const u64, n_spectrograms: usize, frame_len: usize,
+                        fft_size: usize, hop: usize, window: c_int, precision: c_int, normalize: c_int, audio: *mut f64) -> c_int;
+    fn aus_irstft_multi(devices: *const c_int, n_devices: c_int, spectra: *const f64, n_frames: *const u64, n_spectrograms: usize,
+                        frame_len: usize, fft_size: usize, hop: usize, window: c_int, normalize: c_int, audio: *mut f64) -> c_int;
+    fn aus_stft_features_multi(devices: *const c_int, n_devices: c_int, audio: *const f64, offsets: *const u64, lengths: *const u64,
+                               n_files: usize, fft_size: usize, hop: usize, window: c_int, sample_rate: u32, precision: c_int,
+                               features: *mut f64) -> c_int;
+    fn aus_autocorrelation(ctx: *mut AusCtx, audio: *const f64, audio_len: usize, fft_size: usize, out: *mut f64) -> c_int;
+    fn aus_time_features_batch(ctx: *mut AusCtx, audio: *const f64, offsets: *const u64, lengths: *const u64, n_files: usize,
+                               sample_rate: u32, out: *mut f64) -> c_int;
+    fn aus_time_features_frames(ctx: *mut AusCtx, audio: *const f64, offsets: *const u64, lengths: *const u64, n_files: usize,
+                                fft_size: usize, hop: usize, sample_rate: u32, out: *mut f64) -> c_int;
+    fn aus_mixdown(ctx: *mut AusCtx, channels: *const f64, n_frames: usize, n_channels: c_int, out: *mut f64) -> c_int;
+    fn aus_pcm_to_f64(ctx: *mut AusCtx, pcm: *const c_void, sample_bits: c_int, n_frames: usize, n_channels: c_int,
+                      interleaved: c_int, mixdown: c_int, out: *mut f64) -> c_int;
 }
 
 const AUS_ERR_SIZE: c_int = -4;
@@ -312,5 +328,92 @@ pub mod mp {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ round-2 rows
+/// audiofile.rs:168-178 on the samples of an `AudioFile` (`samples: Vec<Vec<f64>>`, one Vec per channel): channel 0
+/// accumulates every channel including itself, then divides by the channel count; the other channels are dropped.
+pub fn mixdown_samples(samples: &mut Vec<Vec<f64>>) {
+    if samples.len() > 1 {
+        let n = samples[0].len();
+        let flat: Vec<f64> = samples.iter().flat_map(|c| c.iter().copied()).collect();      // planar [channel][frame]
+        let mut out = vec![0.0f64; n];
+        with_ctx(|c| ok(unsafe { aus_mixdown(c, flat.as_ptr(), n, samples.len() as c_int, out.as_mut_ptr()) }));
+        samples[0] = out;
+        samples.truncate(1);
+    }
+}
+
+/// audiofile.rs:296-329 for one decoded packet of interleaved 16-bit PCM: `sample as f64 / INTMAX16` per channel.
+pub fn widen_s16_interleaved(pcm: &[i16], n_channels: usize) -> Vec<Vec<f64>> {
+    let n = pcm.len() / n_channels;
+    let mut flat = vec![0.0f64; n * n_channels];
+    with_ctx(|c| ok(unsafe {
+        aus_pcm_to_f64(c, pcm.as_ptr() as *const c_void, 16, n, n_channels as c_int, 1, 0, flat.as_mut_ptr())
+    }));
+    flat.chunks_exact(n).map(|c| c.to_vec()).collect()
+}
+
+/// analysis/spectral_analysis_tools.rs:31 -- same signature
+pub fn autocorrelation(audio: &[f64], fft_size: usize) -> Result<Vec<f64>, spectrum::SpectrumError> {
+    let mut out = vec![0.0f64; fft_size];
+    let rc = with_ctx(|c| unsafe { aus_autocorrelation(c, audio.as_ptr(), audio.len(), fft_size, out.as_mut_ptr()) });
+    if rc == AUS_ERR_SIZE { return Err(spectrum::SpectrumError { error_msg: last_error() }); }
+    ok(rc);
+    Ok(out)
+}
+
+fn time_scalars(audio: &[f64], sample_rate: u32) -> [f64; 4] {
+    let (off, len) = ([0u64], [audio.len() as u64]);
+    let mut out = [0.0f64; 4];
+    with_ctx(|c| ok(unsafe { aus_time_features_batch(c, audio.as_ptr(), off.as_ptr(), len.as_ptr(), 1, sample_rate, out.as_mut_ptr()) }));
+    out
+}
+pub fn dc_bias(audio: &[f64]) -> f64 { time_scalars(audio, 44100)[0] }                                   // audio_analysis_tools.rs:22
+pub fn dbfs_max(audio: &[f64]) -> f64 { time_scalars(audio, 44100)[1] }                                  // :55
+pub fn energy(audio: &[f64]) -> f64 { time_scalars(audio, 44100)[2] }                                    // :74
+pub fn zero_crossing_rate(audio: &[f64], sample_rate: u32) -> f64 { time_scalars(audio, sample_rate)[3] } // :98
+
+/// The four scalars above for every STFT frame of `audio` (new: rows aligned with `mp::stft_features`).
+pub fn time_features_frames(audio: &[f64], fft_size: usize, hop_size: usize, sample_rate: u32) -> Vec<[f64; 4]> {
+    let f = unsafe { aus_num_frames(audio.len(), fft_size, hop_size) };
+    let (off, len) = ([0u64], [audio.len() as u64]);
+    let mut out = vec![0.0f64; f * 4];
+    with_ctx(|c| ok(unsafe {
+        aus_time_features_frames(c, audio.as_ptr(), off.as_ptr(), len.as_ptr(), 1, fft_size, hop_size, sample_rate, out.as_mut_ptr())
+    }));
+    out.chunks_exact(4).map(|r| [r[0], r[1], r[2], r[3]]).collect()
+}
+
+/// Multi-GPU forms (no counterpart in the reference): a batch of files / one long file over `devices`, and the inverse of
+/// several spectrograms (a stereo pair) by frame range with the host-side max of fft.rs:255-258 as the only exchange.
+pub fn stft_features_multi(devices: &[i32], audio: &[f64], offsets: &[u64], lengths: &[u64], fft_size: usize, hop_size: usize,
+                           window_type: WindowType, sample_rate: u32) -> Vec<analysis::Analysis> {
+    let total: usize = lengths.iter().map(|&l| unsafe { aus_num_frames(l as usize, fft_size, hop_size) }).sum();
+    let mut out = vec![0.0f64; total * 14];
+    ok(unsafe {
+        aus_stft_features_multi(devices.as_ptr(), devices.len() as c_int, audio.as_ptr(), offsets.as_ptr(), lengths.as_ptr(),
+                                lengths.len(), fft_size, hop_size, wcode(window_type), sample_rate, F64, out.as_mut_ptr())
+    });
+    out.chunks_exact(14).map(analysis::from_row).collect()
+}
+pub fn irstft_multi(devices: &[i32], spectrograms: &[Vec<Vec<Complex<f64>>>], fft_size: usize, hop_size: usize,
+                    window_type: WindowType) -> Result<Vec<Vec<f64>>, spectrum::SpectrumError> {
+    let k = spectrograms[0][0].len();
+    let nf: Vec<u64> = spectrograms.iter().map(|s| s.len() as u64).collect();
+    let mut flat = Vec::with_capacity(nf.iter().sum::<u64>() as usize * k * 2);
+    for s in spectrograms { for row in s { for c in row { flat.push(c.re); flat.push(c.im); } } }
+    let lens: Vec<usize> = nf.iter().map(|&f| unsafe { aus_irstft_len(f as usize, fft_size, hop_size) }).collect();
+    let mut out = vec![0.0f64; lens.iter().sum()];
+    let rc = unsafe {
+        aus_irstft_multi(devices.as_ptr(), devices.len() as c_int, flat.as_ptr(), nf.as_ptr(), nf.len(), k, fft_size, hop_size,
+                         wcode(window_type), 1, out.as_mut_ptr())
+    };
+    if rc == AUS_ERR_SIZE { return Err(spectrum::SpectrumError { error_msg: last_error() }); }
+    ok(rc);
+    let mut res = Vec::new();
+    let mut pos = 0;
+    for l in lens { res.push(out[pos..pos + l].to_vec()); pos += l; }
+    Ok(res)
+}
+
 #[allow(dead_code)]
-fn _unused(_: *mut c_void) {}
+fn _unused(_: *mut c_void, _: *const u64) { let _ = aus_irstft_batch; }
