@@ -18,6 +18,7 @@ independent, there is no data-path collective.
 
 Other legs (each prints ONE JSON line of its own; none of them is the driver's default):
   --config 1..4   the other BASELINE.json configurations, device-timed with the same clock / L2 rules
+  --corpus        sustained config-5 run on one GPU: generate -> analyse -> stream the feature rows out, three streams
   --multi         the product's single-process multi-GPU entry points (aus_stft_features_multi, aus_irstft_multi) over
                   the visible GPUs, strong scaling on config 4 (one 1-h file by frame range) and config 3 (1000 clips)
 """
@@ -647,6 +648,84 @@ def run_multi(args):
     print(json.dumps(out))
 
 
+# --------------------------------------------------------------------------------------------- sustained corpus leg
+def run_corpus(args):
+    """SURVEY 7 hard part 5 / BASELINE config 5 as a sustained run on one GPU: a stream of 1-hour files is generated on the
+    device, analysed (one fused launch per file) and its feature rows are streamed to pinned host memory, with the three
+    stages on three streams and double buffers (generation of file i+1 and the D2H of file i-1 overlap the analysis of
+    file i).  Reported with and without the generation stage; the corpus rate of a node is this times its GPUs."""
+    import numpy as np
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    import aus_rust_b200 as aus
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    prec = args.precision
+    tdt = torch.float64 if prec == "f64" else torch.float32
+    n_files = args.corpus_files
+    F = _frames(FILE_SAMPLES)
+    s_gen, s_cmp, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+    ctx_gen, ctx_cmp = aus.Context(0), aus.Context(0)
+    ctx_gen.set_stream(s_gen.cuda_stream)
+    ctx_cmp.set_stream(s_cmp.cuda_stream)
+    audio = [torch.empty(FILE_SAMPLES, dtype=tdt, device=dev) for _ in range(2)]
+    feat = [torch.empty((F, 14), dtype=tdt, device=dev) for _ in range(2)]
+    host = [torch.empty((F, 14), dtype=tdt, pin_memory=True) for _ in range(2)]
+    lens, offs = np.array([FILE_SAMPLES], dtype=np.uint64), np.array([0], dtype=np.uint64)
+    checks = []
+
+    def run(generate: bool):
+        ev_gen = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        if not generate:                                   # analysis + output stream only: both buffers hold a file already
+            for b in range(2):
+                ctx_gen.synth_dev(audio[b], 0, SR, file_freq(b), 0, b, prec)
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n_files + 1):
+            b = i & 1
+            if i < n_files and generate:
+                if i >= 2:
+                    s_gen.wait_event(ev_cmp[b])            # the analysis of file i-2 has released audio[b]
+                ctx_gen.synth_dev(audio[b], 0, SR, file_freq(i), 0, i, prec)
+                ev_gen[b].record(s_gen)
+            if i >= 1:                                     # analyse file i-1 while file i is being generated
+                j, bj = i - 1, (i - 1) & 1
+                if generate:
+                    s_cmp.wait_event(ev_gen[bj])
+                if j >= 2:
+                    s_cmp.wait_event(ev_out[bj])           # the D2H of file j-2 has released feat[bj]
+                ctx_cmp.stft_features_batch_dev(audio[bj], offs, lens, FFT, HOP, WINDOW, SR, prec, feat[bj])
+                ev_cmp[bj].record(s_cmp)
+                s_out.wait_event(ev_cmp[bj])
+                with torch.cuda.stream(s_out):
+                    host[bj].copy_(feat[bj], non_blocking=True)
+                ev_out[bj].record(s_out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        checks.append(float(host[(n_files - 1) & 1].double().abs().sum()))
+        return n_files * F / dt
+
+    run(True)                                              # warm-up (tables, allocations)
+    with_gen = run(True)
+    without = run(False)
+    esz = 8 if prec == "f64" else 4
+    print(json.dumps({
+        "metric": "corpus_sustained_frames_per_sec_fft2048_hop512", "unit": "frames/s", "n_gpus": 1, "dtype": prec, "data": "synthetic",
+        "higher_is_better": True, "files": n_files, "hours_of_audio": n_files,
+        "generate_analyse_stream": with_gen, "analyse_stream": without,
+        "audio_hours_per_hour_per_gpu": {"generate_analyse_stream": with_gen * HOP / SR, "analyse_stream": without * HOP / SR},
+        "feature_d2h_gbs": without * 14 * esz / 1e9,
+        "ten_thousand_hour_corpus_seconds_on_8_gpus": {"generate_analyse_stream": 10000 * 3600 / (8 * with_gen * HOP / SR),
+                                                       "analyse_stream": 10000 * 3600 / (8 * without * HOP / SR)},
+        "config": {"workload": "config 5 sustained: 1-hour files through double buffers, three streams (generate / fused K1 + finalize / "
+                               "feature rows to pinned host memory)"},
+        "finite": bool(np.isfinite(checks).all()),
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -660,12 +739,16 @@ def main():
     ap.add_argument("--no-other-precision", action="store_true")
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (5 = the metric's)")
     ap.add_argument("--multi", action="store_true", help="single-process multi-GPU strong-scaling leg")
+    ap.add_argument("--corpus", action="store_true", help="sustained generate -> analyse -> stream-out leg on one GPU")
+    ap.add_argument("--corpus-files", type=int, default=48, help="1-hour files of the --corpus leg")
     ap.add_argument("--direct-load", type=int, default=None, help="experiment: 1 = global->register input loads, 0 = TMA staging")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.multi:
         run_multi(args)
+    elif args.corpus:
+        run_corpus(args)
     elif args.config != 5:
         run_config(args)
     else:

@@ -80,3 +80,11 @@ def test_gpu_arm_other_baseline_configs(cfg):
     assert d["clocks"] is not None and d["gpu_launches"] >= 3
     if cfg == 2:
         assert d["reconstruction_max_abs_error_body"] < 1e-9 and abs(d["peak_after_normalisation"] - 10 ** (-6 / 20)) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_gpu_corpus_leg():
+    d = _run(["--corpus", "--corpus-files", "6"], 580)
+    assert d["finite"] and d["analyse_stream"] > 1e7 and 0 < d["generate_analyse_stream"] <= 1.05 * d["analyse_stream"]
+    assert d["feature_d2h_gbs"] > 1
