@@ -10,7 +10,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import torch
 
@@ -22,7 +21,7 @@ ap.add_argument("--hop", type=int, default=512)
 ap.add_argument("--seconds", type=int, default=3600)
 ap.add_argument("--kernels", default="k1,k2,mix,k3,k4")
 ap.add_argument("--prec", default="f64,f32")
-ap.add_argument("--check", action="store_true", help="compare a short signal with the numpy oracle first")
+ap.add_argument("--check", action="store_true", help="run tests/soak/quick_check.py (oracle comparison of a short signal) first")
 ap.add_argument("--tag", default="")
 args = ap.parse_args()
 
@@ -51,42 +50,10 @@ def timeit(fn, reps=5, warm=2):
     return best
 
 
-if args.check:
-    import aus_oracle as orc
-    x = orc.synth_signal(3 * SR)
-    ref = orc.stft_features(x, args.n, args.hop, orc.HANNING, SR)
-    got = ctx.stft_features(x, args.n, args.hop, aus.WindowType.Hanning, SR, "f64")
-    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
-    print("check f64 features max rel", rel.max(axis=0).tolist(), flush=True)
-    got32 = ctx.stft_features(x, args.n, args.hop, aus.WindowType.Hanning, SR, "f32")
-    rel32 = np.abs(got32 - ref) / np.maximum(np.abs(ref), 1e-300)
-    print("check f32 features max rel", rel32.max(axis=0).tolist(), flush=True)
-    sref = orc.rstft(x, args.n, args.hop, orc.HANNING)
-    sgot = np.asarray(ctx.rstft(x, args.n, args.hop, int(aus.WindowType.Hanning)))
-    print("check f64 spectra max |d| / max|X|", float(np.abs(sgot - sref).max() / np.abs(sref).max()), flush=True)
-
-if args.check:
-    rng = np.random.default_rng(3)
-    mags = np.abs(rng.normal(size=(40, args.n // 2 + 1))) + 1e-3
-    mags[5, :] = 0.0
-    mags[6, 10] = 0.0
-    ref = orc.analyze_spectrogram(mags, args.n, SR)
-    got = ctx.analyzer_batch(mags, args.n, SR)
-    with np.errstate(all="ignore"):
-        rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
-    rel = np.where(np.isnan(got) & np.isnan(ref), 0.0, rel)
-    print("check k3 f64 max rel per feature", np.nanmax(rel, axis=0).tolist(), "nan pattern equal",
-          bool(np.array_equal(np.isnan(got), np.isnan(ref))), flush=True)
-
-if args.check:
-    xs = orc.synth_signal(40 * args.n + 123, SR, seed=8, file_id=args.n)
-    for wt in (orc.HAMMING, orc.HANNING):
-        S = orc.rstft(xs, args.n, args.hop, wt)
-        ref = orc.irstft(S, args.n, args.hop, wt)
-        got = ctx.irstft(S, args.n, args.hop, wt)
-        fin = np.isfinite(ref)
-        print("check k4 f64 window", wt, "max |d| / peak", float(np.max(np.abs(got[fin] - ref[fin])) / np.max(np.abs(ref[fin]))),
-              "nan pattern equal", bool(np.array_equal(np.isnan(got), np.isnan(ref))), flush=True)
+if args.check:          # the oracle comparisons live with the tests (only tests/ may touch oracle/): run them as a child process
+    import subprocess
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "soak", "quick_check.py"), "--n", str(args.n), "--hop", str(args.hop)],
+                   check=False, env=dict(os.environ))
 
 N, hop, n = args.n, args.hop, args.seconds * SR
 K = N // 2 + 1

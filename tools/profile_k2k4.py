@@ -2,7 +2,7 @@
 """Small driver for ncu: one K2 (rstft, spectra out) and one K4+K5 (irstft) launch at fft 2048 / hop 512, 10 min f64."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import aus_rust_b200 as aus
 ctx = aus.Context(0); ctx.use_torch_stream()

@@ -5,9 +5,14 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
-import aus_oracle as orc
+
+
+def synth(n, seed=0):
+    """sine + noise; any signal will do here (results are not checked: the sanitizer watches the accesses)"""
+    r = np.random.default_rng(seed)
+    return 0.5 * np.sin(0.0627 * np.arange(n)) + 0.1 * r.uniform(-1, 1, n)
+
 import aus_rust_b200 as aus
 
 ctx = aus.Context(0)
@@ -15,7 +20,7 @@ SR = 44100
 sizes = [int(a) for a in sys.argv[1:]] or [64, 512, 1024, 2048, 4096, 16384]
 for N in sizes:
     hop = N // 4
-    x = orc.synth_signal(3 * N + 101, SR, seed=N)           # 10 frames, the last one short; odd length
+    x = synth(3 * N + 101, N)           # 10 frames, the last one short; odd length
     for prec in ("f64", "f32"):
         f = ctx.stft_features(x, N, hop, 2, SR, prec)
         S = ctx.rstft(x, N, hop, 3, prec)
@@ -25,14 +30,14 @@ for N in sizes:
         print(N, prec, f.shape, S.shape, y.shape, a.shape, float(np.nanmax(np.abs(f))), flush=True)
 lens = [0, 5, 700, 3000]
 offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
-print(ctx.stft_features_batch(orc.synth_signal(sum(lens)), offs, lens, 256, 64, 2, SR)[0].shape)
+print(ctx.stft_features_batch(synth(sum(lens)), offs, lens, 256, 64, 2, SR)[0].shape)
 print("sanitize smoke done")
 # round-2 entry points: producer/consumer variant, irstft batch / shards, per-frame time features, PCM + mixdown, polar
 c2 = aus.Context(0)
 c2.set_forward_variant(2)
-x = orc.synth_signal(9000, SR, seed=5)
+x = synth(9000, 5)
 print("pc", c2.stft_features(x, 2048, 512, 2, SR).shape, c2.stft_features(x[1:], 2048, 511, 1, SR).shape)
-S = [ctx.rstft(orc.synth_signal(n, SR, seed=6), 1024, 256, 3) for n in (5000, 1024, 9001)]
+S = [ctx.rstft(synth(n, 6), 1024, 256, 3) for n in (5000, 1024, 9001)]
 print("irstft_batch", [y.shape for y in ctx.irstft_batch(S, 1024, 256, 3)])
 print("irstft_multi", [y.shape for y in aus.irstft_multi([0, 0, 0], S, 1024, 256, 3)])
 print("time frames", ctx.time_features_frames(x, [0, 4000], [4000, 5000], 1024, 256, SR).shape)
