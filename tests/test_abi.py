@@ -104,6 +104,18 @@ def test_no_cpu_fallback(aus):
             assert "aus_oracle" not in open(os.path.join(ROOT, "aus-rust_b200", f)).read(), f"{f} references the oracle"
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package or tools/ may import, link or execute it."""
+    import re
+    pat = re.compile(r"(import\s+aus_oracle|from\s+aus_oracle|libaus_oracle|oracle/_ref|sys\.path[^\n]*oracle)")
+    for top in ("aus-rust_b200", "tools"):
+        for d, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".rs", "Makefile")):
+                    src = open(os.path.join(d, f), errors="replace").read()
+                    assert not pat.search(src), f"{os.path.join(d, f)} reaches into oracle/"
+
+
 # ---------------------------------------------------------------------------------------------- shard plan (pure host)
 @pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
 def test_shard_plan_single_long_file_reproduces_whole_file_features(aus, orc, n_dev):
