@@ -14,11 +14,8 @@
 #include "aus_stft_kernel.cuh"
 #include "aus_stft_r.cuh"
 
-#ifndef AUS_K4_KEEP
-#define AUS_K4_KEEP 1               // last inverse-FFT pass stays in registers: the overlap-add reads v[], not shared memory
-#endif
-#ifndef AUS_K4_BATCH
-#define AUS_K4_BATCH 8              // butterfly outputs whose partial sums / window pairs are in flight together (AUS_K4_KEEP)
+#ifndef AUS_K4_PRE_REG
+#define AUS_K4_PRE_REG 0            // experiment: correct, -2 %
 #endif
 
 namespace aus {
@@ -69,15 +66,20 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
     for (unsigned long long it = 0; it < iters; ++it) {
         const unsigned long long sidx = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
         const bool seg_ok = sidx < p.n_seg;
-        // Only what the frame loop needs BEFORE the inverse FFT stays in registers across it (b, h_begin, the row base); the
-        // rest of the segment's description is re-read (L1 hits) after the FFT, when the 32 outputs are no longer all live.
-        long long b = 0, h_begin = 0, rowbase = 0;
+        long long a = 0, b = 0, F = 0, h_begin = 0;
+        unsigned long long gfirst = 0, ooff = 0;
+        long long row0 = 0, samp0 = 0;
+        int file = 0;
         if (seg_ok) {
-            const int file0 = (int)p.seg_file[sidx];
-            const long long a0 = (long long)p.seg_a[sidx];
+            file = (int)p.seg_file[sidx];
+            a = (long long)p.seg_a[sidx];
             b = (long long)p.seg_b[sidx];
-            rowbase = (long long)p.file_first[file0] - (long long)p.file_row0[file0];
-            h_begin = a0 - p.halo > 0 ? a0 - p.halo : 0;
+            gfirst = p.file_first[file];
+            F = (long long)p.file_frames[file];
+            row0 = (long long)p.file_row0[file];
+            samp0 = (long long)p.file_samp0[file];
+            ooff = p.file_out_off[file];
+            h_begin = a - p.halo > 0 ? a - p.halo : 0;
         }
         // groups that share a warp must run the same number of frame steps (barriers are warp-wide for TPF <= 32)
         long long steps = seg_ok ? b - h_begin : 0;
@@ -88,13 +90,15 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                 steps = o > steps ? o : steps;
             }
         }
+        const long long own_lo = a * hop;
+        const long long out_len = (F > 0) ? (long long)N + hop * (F - 1) : 0;
+        const long long own_hi = (b == F) ? out_len : b * hop;
         T vmax = (T)0;
 
         for (long long st = 0; st < steps; ++st) {
             const long long h = h_begin + st;
             const bool active = seg_ok && h < b;
-            const unsigned long long rowi = (unsigned long long)(rowbase + (active ? h : 0));      // row of `spec` holding frame h
-            const Cx<T> *row = p.spec + rowi * (unsigned long long)K;
+            const Cx<T> *row = p.spec + (gfirst + (unsigned long long)(active ? h - row0 : 0)) * (unsigned long long)K;
 #if AUS_L2_PREFETCH
             if (active && t == 0 && h + 1 < b && ((K * sizeof(Cx<T>)) % 16 == 0) && p.tma_ok)
                 prefetch_l2(row + K, (uint32_t)(K * sizeof(Cx<T>)));        // next frame of this segment -> L2
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             if constexpr (ROW16) {
                 use_tma = use_tma && (ra & 15) == 0;
             } else {
-                use_tma = use_tma && rowi + 1 < p.total_rows;
+                use_tma = use_tma && gfirst + (unsigned long long)(h - row0) + 1 < p.total_rows;
                 if (use_tma) sh = (int)((ra & 15) >> 3);
             }
             constexpr uint32_t ROWB = (uint32_t)((K * sizeof(Cx<T>) + 15) & ~(size_t)15);     // f32: 8208 for either alignment
@@ -138,6 +142,39 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             // ---- Hermitian pre-twiddle, in place: buf[k] <- conj(Zi[k]),
             //      Zi[k] = (Y[k] + conj Y[M-k]) + i W_N^{-k} (Y[k] - conj Y[M-k])   (fft.rs:221-229 folded in)
             //      The twiddles (cos, sin)(2 pi k / N) of this thread's pairs were loaded before the wait for the row (Wp).
+            // Experiment, off: f32, fft 2048 (one warp per frame, two radix-32 passes), pre-twiddled values kept out of shared memory.
+            // Thread t forms conj Zi[k] and conj Zi[M-k] for its k = t + 32 i; the first is its own pass-1 input r = i,
+            // the second is input 31 - i of thread 32 - t (thread 0: its own input 32 - i), handed over by a shuffle --
+            // 64 shared-memory accesses per thread less, 32 shuffles more: measured -2 % (the shuffles use the same data pipe).
+            constexpr bool PRE_REG = AUS_K4_PRE_REG && sizeof(T) == 4 && TPF == 32 && C::R1 == 32 && !C::THREE;
+            if constexpr (PRE_REG) {
+                Cx<T> v[32];
+                auto pretw = [&](Cx<T> Yk, Cx<T> Ym, const Cx<T> W, Cx<T> &A, Cx<T> &B) {
+                    const T sx = Yk.x + Ym.x, sy = Yk.y - Ym.y;
+                    const T dx = Yk.x - Ym.x, dy = Yk.y + Ym.y;
+                    const T ux = W.x * dx - W.y * dy;
+                    const T uy = W.x * dy + W.y * dx;
+                    A = Cx<T>{sx - uy, -(sy + ux)};
+                    B = Cx<T>{sx + uy, sy - ux};
+                };
+                static_for<0, 16>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    const int k = t + TPF * i;
+                    Cx<T> Yk = fb[k], Ym = fb[M - k];
+                    if (i == 0 && t == 0) { Yk.y = (T)0; Ym.y = (T)0; }        // DC / Nyquist: fft.rs:235
+                    pretw(Yk, Ym, Wp[i], v[i], v[31 - i]);
+                });
+                Cx<T> mid = Cx<T>{(T)0, (T)0}, dummy;
+                if (t == 0) pretw(fb[M / 2], fb[M / 2], Cx<T>{(T)0, (T)1}, mid, dummy);    // k = M/2 pairs with itself
+                const int partner = (TPF - t) & (TPF - 1);
+                static_for<0, 16>([&](auto c_) {                               // r = 31 .. 16: thread 0's sources stay intact
+                    constexpr int r = 31 - decltype(c_)::value;
+                    Cx<T> snd = v[r];
+                    if (t == 0) snd = (r == 16) ? mid : v[r == 16 ? 16 : r - 1];
+                    v[r] = shfl_cx<TPF>(snd, partner);
+                });
+                frame_fft<T, LOG2N>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false, /*vin=*/true);
+            } else {
             static_for<0, 17>([&](auto i_) {
                 constexpr int i = decltype(i_)::value;
                 const int k = t + TPF * i;                 // pairs (k, M-k), k = 0 .. M/2
@@ -157,15 +194,11 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             });
             group_sync<TPF, C::BLOCK>(grp);
 
-            // the inverse FFT proper
-            Cx<T> v[32];
-#if AUS_K4_KEEP
-            // its last pass stays in registers: natural output s of this thread's final butterfly, conj z[t + TPF s], is
-            // v[bitrev(s, 5)] -- exactly the 32 sample pairs this thread windows and adds below
-            frame_fft_keep<T, LOG2N, C, false>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);
-#else
-            frame_fft<T, LOG2N>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);     // buf: conj(z) in the Z layout
-#endif
+            {
+                Cx<T> v[32];
+                frame_fft<T, LOG2N>(fb, p.fwd, t, grp, /*prewindowed=*/true, nullptr, v, false);     // buf: conj(z) in the Z layout
+            }
+            }
 
             // ---- window + overlap-add into the output (ascending frame order), finalise completed samples.
             //      u = offset inside the frame.  Frames h - b (b >= 1) also cover the sample iff b <= (N-1-u)/hop, frames
@@ -174,18 +207,6 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
             // (h >= halo) and a later frame follows.  Then both samples of a butterfly output share their class -- has a
             // partial sum from earlier frames iff u < N - hop, complete after this frame iff u < hop -- so each pair is one
             // 16-byte read-modify-write, the window norm is a table multiply, and nothing is computed per sample.
-            asm volatile("" ::: "memory");                 // the re-reads below are not to be hoisted above the FFT
-            int file = 0;
-            long long F = 0, samp0 = 0, own_lo = 0, own_hi = 0;
-            unsigned long long ooff = 0;
-            if (active) {
-                file = (int)p.seg_file[sidx];
-                F = (long long)p.file_frames[file];
-                samp0 = (long long)p.file_samp0[file];
-                ooff = p.file_out_off[file];
-                own_lo = (long long)p.seg_a[sidx] * hop;
-                own_hi = (b == F) ? (long long)N + hop * (F - 1) : b * hop;
-            }
             const bool fastf = active && p.fast_ok && h >= p.halo && h < F - 1 &&
                                ((reinterpret_cast<uintptr_t>(p.out + ooff + (h * hop - samp0)) & (2 * sizeof(T) - 1)) == 0);
             if (fastf) {
@@ -194,39 +215,6 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                 const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;     // owned range, relative (even)
                 const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);
                 const int nprev = N - p.hop;
-#if AUS_K4_KEEP
-                constexpr int B = AUS_K4_BATCH;
-                static_for<0, 32 / B>([&](auto q_) {
-                    constexpr int i0 = decltype(q_)::value * B;
-                    V2 prev[B], rn[B];
-                    Cx<T> w[B];
-#pragma unroll
-                    for (int c = 0; c < B; ++c) {
-                        const int n = t + TPF * (i0 + c), u0 = 2 * n;
-                        prev[c] = V2{(T)0, (T)0};
-                        rn[c] = V2{(T)1, (T)1};
-                        if (u0 >= ulo && u0 < uhi && u0 < nprev) prev[c] = __ldcg(reinterpret_cast<const V2 *>(outh + u0));
-                        if (u0 < p.hop) rn[c] = __ldg(reinterpret_cast<const V2 *>(p.rnorm + u0));   // with the other loads
-                        w[c] = ldg_cx(&p.winf[n]);
-                    }
-                    static_for<0, B>([&](auto c_) {
-                        constexpr int c = decltype(c_)::value;
-                        const int u0 = 2 * (t + TPF * (i0 + c));
-                        if (u0 >= ulo && u0 < uhi) {
-                            const Cx<T> z = v[bitrev(i0 + c, 5)];
-                            T v0 = z.x * w[c].x + prev[c].x;                    // fft.rs:234-236 + overlap-add (ascending frames)
-                            T v1 = -z.y * w[c].y + prev[c].y;
-                            if (u0 < p.hop) {                                   // no later frame reaches it: fft.rs:250-258
-                                v0 *= rn[c].x;
-                                v1 *= rn[c].y;
-                                if (v0 > vmax) vmax = v0;                       // f64::max skips NaN
-                                if (v1 > vmax) vmax = v1;
-                            }
-                            *reinterpret_cast<V2 *>(outh + u0) = V2{v0, v1};
-                        }
-                    });
-                });
-#else
 #pragma unroll 1
                 for (int i0 = 0; i0 < 32; i0 += 8) {
                     V2 prev[8], rn[8];
@@ -256,16 +244,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                         *reinterpret_cast<V2 *>(outh + u0) = V2{v0, v1};
                     }
                 }
-#endif
             } else if (active) {
-#if AUS_K4_KEEP
-                // rare frames (file ends, odd hops, irfft): park the outputs in this thread's own slots of the frame buffer
-                // (frame_fft_keep() returned after every thread's last read of it) and index them at run time below
-                static_for<0, 32>([&](auto s_) {
-                    constexpr int sidx2 = decltype(s_)::value;
-                    fb[padi<4>(t + TPF * sidx2)] = v[bitrev(sidx2, 5)];
-                });
-#endif
                 T *outh = p.out + ooff + (h * hop - samp0);
                 const long long rlo = own_lo - h * hop, rhi = own_hi - h * hop;
                 const int ulo = rlo < 0 ? 0 : (rlo > N ? N : (int)rlo), uhi = rhi < 0 ? 0 : (rhi > N ? N : (int)rhi);
@@ -330,7 +309,7 @@ __global__ void __launch_bounds__(Cfg<T, LOG2N>::BLOCK, Cfg<T, LOG2N>::MINB) ist
                 vmax = o > vmax ? o : vmax;
             }
             if ((t & (W - 1)) == 0 && seg_ok && vmax > (T)0)
-                atomicMax(p.file_max_bits + p.seg_file[sidx], (unsigned long long)__double_as_longlong((double)vmax));
+                atomicMax(p.file_max_bits + file, (unsigned long long)__double_as_longlong((double)vmax));
         }
     }
 }
