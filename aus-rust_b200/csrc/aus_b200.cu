@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -14,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+namespace anyn { static void release_all(aus_ctx *c); }      // aus_anyn.cuh (included further down)
+
 static int log2_exact(size_t n) {
     if (n == 0 || (n & (n - 1))) return -1;
     int l = 0;
@@ -21,10 +24,13 @@ static int log2_exact(size_t n) {
     return l;
 }
 
+// fft sizes: powers of two in [64, 16384] run on the radix-32 kernels; every other size in [2, 8192] (rustfft plans any
+// length, fft.rs:120-121) takes the chirp-z path of aus_anyn.cuh on top of them.
 static int check_fft_args(size_t N, size_t hop) {
     const int lg = log2_exact(N);
-    if (lg < 0) return fail(AUS_ERR_UNSUPPORTED, "fft_size must be a power of two (rustfft accepts any size; this build does not)");
-    if (lg < 6 || lg > 14) return fail(AUS_ERR_UNSUPPORTED, "fft_size must be in [64, 16384]");
+    const bool native = lg >= 6 && lg <= 14;
+    if (!native && (N < 2 || N > 8192))
+        return fail(AUS_ERR_UNSUPPORTED, "fft_size must be a power of two in [64, 16384] or any size in [2, 8192]");
     if (hop == 0) return fail(AUS_ERR_INVALID, "hop_size must be > 0 (the reference loops forever, fft.rs:126)");
     if (hop > N) return fail(AUS_ERR_INVALID, "hop_size must be <= fft_size (the reference panics on slice bounds, fft.rs:153)");
     return AUS_OK;
@@ -141,6 +147,8 @@ extern "C" void aus_ctx_destroy(aus_ctx *c) {
         for (void *w : kv.second.winf) cudaFree(w);
     }
     cudaFree(c->log2tab);
+    anyn::release_all(c);
+    for (DevBuf *b : {&c->any_a, &c->any_s, &c->any_y, &c->any_mag, &c->any_desc, &c->any_par, &c->any_feat}) b->release();
     for (DevBuf *b : {&c->in64, &c->in32, &c->out64, &c->out32, &c->aux64, &c->aux32, &c->desc, &c->misc, &c->raw, &c->normtab, &c->acorr,
                       &c->pin64[0], &c->pin64[1], &c->pin32[0], &c->pin32[1], &c->pout64[0], &c->pout64[1], &c->pout32[0], &c->pout32[1], &c->ppcm[0], &c->ppcm[1]})
         b->release();
@@ -492,75 +500,143 @@ __global__ void time_final_kernel(const double *partials, const unsigned long lo
     out[f * 4 + 3] = zc * (double)sr / n;                                     // zero_crossing_rate, :98-108
 }
 
-// analysis/spectral_analysis_tools.rs:306-471, generic parameters: one thread per row, the reference's loop order
-__global__ void __launch_bounds__(128) spectral_generic_kernel(const double *mags, unsigned long long n_rows, int K, const double *freqs,
+// analysis/spectral_analysis_tools.rs:306-471 with the caller's own parameters (any row length, frequency table, roll-off
+// fractions, slope bands).  One WARP per row: every pass reads the row lane-strided (coalesced 256-byte requests; the row
+// stays in L1/L2 between passes), sums are combined by a fixed xor tree (deterministic), and the roll-off index comes from a
+// lane scan of contiguous chunk sums plus one in-chunk walk by the lane that holds the crossing.  Where a threshold lies
+// within rounding distance of a running sum, the reference's own sequential arithmetic decides (:137-145), so lane 0 redoes
+// exactly that (rare); the result is then identical to the reference's for identical inputs, ties included.
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__global__ void __launch_bounds__(256) spectral_generic_kernel(const double *mags, unsigned long long n_rows, int K, const double *freqs,
                                                               const double *roll, int n_roll, const double *blo, const double *bhi,
-                                                              int n_bands, double sr, double *out) {
-    const unsigned long long row = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    const double *m = mags + row * (unsigned long long)K;
-    double *o = out + row * (unsigned long long)(7 + n_roll + n_bands);
+                                                              int n_bands, double sr, double *out, int analyzer_order) {
+    // columns: centroid, variance, skewness, kurtosis, entropy, flatness, then slope | roll-offs | bands -- or, in
+    // analyzer order (analyzer.rs:10-23), roll-offs | slope | bands
+    const int col_slope = analyzer_order ? 6 + n_roll : 6, col_roll = analyzer_order ? 6 : 7;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     const double n = (double)K;
-    double msum = 0.0, psum = 0.0, mf = 0.0, lsum = 0.0, px = 0.0;
-    for (int i = 0; i < K; ++i) {
-        const double mi = m[i], pi = mi * mi;                       // make_power_spectrum, :273-279
-        msum += mi;
-        psum += pi;
-        mf += mi * freqs[i];                                        // :79-85
-        lsum += log(mi);                                            // :107-114
-        px += pi * (double)i;                                       // dot_product(power, x), :167-182
-    }
-    const double c = mf / msum;
-    double var = 0.0, ent = 0.0;
-    for (int i = 0; i < K; ++i) {
-        const double q = (m[i] * m[i]) / psum;                      // make_spectrum_pmf, :284-290
-        var += pow(freqs[i] - c, 2.0) * q;                          // :238-244
-        ent += q * log2(q);                                         // :93-99
-    }
-    double sk = 0.0, ku = 0.0;
-    for (int i = 0; i < K; ++i) {
-        const double q = (m[i] * m[i]) / psum;
-        sk += pow(freqs[i] - c, 3.0) * q;                           // :153-160
-        ku += pow(freqs[i] - c, 4.0) * q;                           // :122-129
-    }
-    o[0] = c;
-    o[1] = var;
-    o[2] = sk / pow(var, 1.5);
-    o[3] = ku / pow(var, 2.0);
-    o[4] = -ent;
-    o[5] = exp(lsum / n) * n / msum;
-    const double sum_x = n * (n - 1.0) / 2.0, sum_x2 = n * (n - 1.0) * (2.0 * n - 1.0) / 6.0;
-    o[6] = (n * px - sum_x * psum) / (n * sum_x2 - pow(sum_x, 2.0));
-    for (int r = 0; r < n_roll; ++r) {                              // :137-145
-        const double frac = roll[r];
-        long long i = -1;
-        double cum = 0.0;
-        while (cum < frac && i < (long long)K - 1) {
-            ++i;
-            cum += (m[i] * m[i]) / psum;
+    const int C = (K + 31) / 32;                                            // contiguous chunk of the roll-off scan
+    const int c_lo = lane * C < K ? lane * C : K, c_hi = c_lo + C < K ? c_lo + C : K;
+    for (unsigned long long row = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+        const double *m = mags + row * (unsigned long long)K;
+        double *o = out + row * (unsigned long long)(7 + n_roll + n_bands);
+        double msum = 0.0, psum = 0.0, mf = 0.0, lsum = 0.0, px = 0.0;
+        for (int i = lane; i < K; i += 32) {
+            const double mi = m[i], pi = mi * mi;                           // make_power_spectrum, :273-279
+            msum += mi;
+            psum += pi;
+            mf += mi * freqs[i];                                            // :79-85
+            lsum += log(mi);                                                // :107-114
+            px += pi * (double)i;                                           // dot_product(power, x), :167-182
         }
-        o[7 + r] = freqs[i < 0 ? 0 : i];                            // i == -1 (frac <= 0): the reference indexes [-1] and panics
-    }
-    const double fund = sr / ((double)(K - 1) * 2.0);
-    for (int b = 0; b < n_bands; ++b) {                             // :190-230 (bounds checked on the host)
-        const double fl = blo[b], fu = bhi[b];
-        const double m_fl = fl / fund, m_fu = fu / fund;
-        const int lc = (int)ceil(m_fl), lf = (int)floor(m_fl), uc = (int)ceil(m_fu), uf = (int)floor(m_fu);
-        double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0;
-        for (int i = lc; i < uf; ++i) {
-            const double pi = m[i] * m[i];
-            sx += freqs[i];
-            sy += pi;
-            sxx += freqs[i] * freqs[i];
-            sxy += pi * freqs[i];
+        msum = warp_sum_all(msum); psum = warp_sum_all(psum); mf = warp_sum_all(mf); lsum = warp_sum_all(lsum); px = warp_sum_all(px);
+        const double c = mf / msum;
+        double var = 0.0, ent = 0.0, sk = 0.0, ku = 0.0;
+        for (int i = lane; i < K; i += 32) {
+            const double q = (m[i] * m[i]) / psum;                          // make_spectrum_pmf, :284-290
+            const double d = freqs[i] - c, d2 = d * d;
+            var += d2 * q;                                                  // :238-244
+            sk += d2 * d * q;                                               // :153-160
+            ku += d2 * d2 * q;                                              // :122-129
+            ent += q * log2(q);                                             // :93-99 (0 * -inf = NaN like the reference)
         }
-        const double pl = m[lf] * m[lf] + (m_fl - (double)lf) * (m[lc] * m[lc] - m[lf] * m[lf]);
-        const double pu = m[uf] * m[uf] + (m_fu - (double)uf) * (m[uc] * m[uc] - m[uf] * m[uf]);
-        const double sum_x = fl + sx + fu;
-        const double sum_y = pl + sy + pu;
-        const double sum_x2 = pow(fl, 2.0) + sxx + pow(fu, 2.0);
-        const double sum_xy = fl * pl + sxy + fu * pu;
-        o[7 + n_roll + b] = (n * sum_xy - sum_x * sum_y) / (n * sum_x2 - pow(sum_x, 2.0));
+        var = warp_sum_all(var); ent = warp_sum_all(ent); sk = warp_sum_all(sk); ku = warp_sum_all(ku);
+        if (lane == 0) {
+            o[0] = c;
+            o[1] = var;
+            o[2] = sk / pow(var, 1.5);
+            o[3] = ku / (var * var);
+            o[4] = -ent;
+            o[5] = exp(lsum / n) * n / msum;
+            const double sum_x = n * (n - 1.0) / 2.0, sum_x2 = n * (n - 1.0) * (2.0 * n - 1.0) / 6.0;
+            o[col_slope] = (n * px - sum_x * psum) / (n * sum_x2 - sum_x * sum_x);
+        }
+        if (n_roll > 0) {                                                   // :137-145
+            double cs = 0.0;
+            for (int i = c_lo; i < c_hi; ++i) cs += (m[i] * m[i]) / psum;
+            double incl = cs;                                               // inclusive scan of the chunk sums over the lanes
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += up;
+            }
+            const double base = incl - cs;
+            const double tol = 1e-12 + 1e-15 * n;
+            double pseq = -1.0;                                             // sequential power sum, made on first use (lane 0)
+            for (int r = 0; r < n_roll; ++r) {
+                const double frac = roll[r];
+                // first lane whose inclusive sum is not below the threshold holds the crossing (NaN compares "not below")
+                const unsigned reached = __ballot_sync(0xffffffffu, !(incl < frac) && c_lo < c_hi);
+                int idx = K - 1;
+                double at = 0.0, before = 0.0;                              // running sum at idx and at idx - 1
+                const int L = reached ? __ffs(reached) - 1 : 31;
+                if (lane == L) {
+                    double cum = base;
+                    if (reached) {
+                        for (int i = c_lo; i < c_hi; ++i) {
+                            before = cum;
+                            cum += (m[i] * m[i]) / psum;
+                            if (!(cum < frac)) { idx = i; break; }
+                        }
+                        at = cum;
+                    }
+                }
+                if (!reached) {                                             // never reached: the loop stops at the last bin
+                    const double tot = __shfl_sync(0xffffffffu, incl, 31);
+                    at = tot;
+                    before = tot - (m[K - 1] * m[K - 1]) / psum;
+                }
+                idx = __shfl_sync(0xffffffffu, idx, L);
+                at = __shfl_sync(0xffffffffu, at, reached ? L : lane);
+                before = __shfl_sync(0xffffffffu, before, reached ? L : lane);
+                if (lane == 0) {
+                    const bool amb = !(fabs(at - frac) > tol) || !(fabs(frac - before) > tol);     // NaN -> sequential rule
+                    if (amb) {
+                        if (pseq < 0.0) {
+                            pseq = 0.0;
+                            for (int i = 0; i < K; ++i) pseq += m[i] * m[i];
+                        }
+                        long long i = -1;
+                        double cum = 0.0;
+                        while (cum < frac && i < (long long)K - 1) {
+                            ++i;
+                            cum += (m[i] * m[i]) / pseq;
+                        }
+                        idx = (int)i;
+                    }
+                    o[col_roll + r] = freqs[idx < 0 ? 0 : idx];                    // frac <= 0 is rejected on the host (reference: [-1] panics)
+                }
+            }
+        }
+        const double fund = sr / ((double)(K - 1) * 2.0);
+        for (int b = 0; b < n_bands; ++b) {                                 // :190-230 (bounds checked on the host)
+            const double fl = blo[b], fu = bhi[b];
+            const double m_fl = fl / fund, m_fu = fu / fund;
+            const int lc = (int)ceil(m_fl), lf = (int)floor(m_fl), uc = (int)ceil(m_fu), uf = (int)floor(m_fu);
+            double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0;
+            for (int i = lc + lane; i < uf; i += 32) {
+                const double pi = m[i] * m[i], f = freqs[i];
+                sx += f;
+                sy += pi;
+                sxx += f * f;
+                sxy += pi * f;
+            }
+            sx = warp_sum_all(sx); sy = warp_sum_all(sy); sxx = warp_sum_all(sxx); sxy = warp_sum_all(sxy);
+            if (lane == 0) {
+                const double pl = m[lf] * m[lf] + (m_fl - (double)lf) * (m[lc] * m[lc] - m[lf] * m[lf]);
+                const double pu = m[uf] * m[uf] + (m_fu - (double)uf) * (m[uc] * m[uc] - m[uf] * m[uf]);
+                const double sum_x = fl + sx + fu;
+                const double sum_y = pl + sy + pu;
+                const double sum_x2 = fl * fl + sxx + fu * fu;
+                const double sum_xy = fl * pl + sxy + fu * pu;
+                o[7 + n_roll + b] = (n * sum_xy - sum_x * sum_y) / (n * sum_x2 - sum_x * sum_x);
+            }
+        }
     }
 }
 
@@ -722,11 +798,119 @@ static int xfer_d2h(aus_ctx *c, void *dst, const void *src, size_t bytes) {
     return AUS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ any fft_size (chirp-z)
+template <typename T>
+static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t N, size_t hop, int wtype, uint32_t sr,
+                            T *d_feat, Cx<T> *d_spec);
+#include "aus_anyn.cuh"
+namespace anyn {
+// frames per pass: the workspace (two real rows of Lp doubles + their two half spectra per frame) stays near 512 MB
+static size_t chunk_frames(size_t Lp, size_t total) {
+    const size_t per = 2 * Lp * sizeof(double) + 2 * (Lp / 2 + 1) * sizeof(double2);
+    return std::max<size_t>(1, std::min<size_t>(total, ((size_t)512 << 20) / per));
+}
+static int workspace(aus_ctx *c, size_t Lp, size_t n) {
+    AUS_TRY(c->any_a.ensure(2 * n * Lp * sizeof(double)));
+    return c->any_s.ensure(2 * n * (Lp / 2 + 1) * sizeof(double2));
+}
+// c->any_a (n frames, prepared by a pre kernel) -> c->any_s = half spectra of the rows of FFT(conj(FFT(a) * bhat))
+static int convolve(aus_ctx *c, Tab *tb, size_t n) {
+    const size_t Lp = tb->Lp;
+    Batch inner;
+    inner.off = {0ull};
+    inner.len = {(unsigned long long)(2 * n * Lp)};
+    inner.first = {0ull, (unsigned long long)(2 * n)};
+    inner.total_frames = 2 * n;
+    inner.span = 2 * n * Lp;
+    AUS_TRY(stft_batch_dev_t<double>(c, (const double *)c->any_a.p, inner, Lp, Lp, AUS_WINDOW_RECTANGULAR, 44100, nullptr, (Cx<double> *)c->any_s.p));
+    mul_kernel<<<(unsigned int)n, 256, 0, c->stream>>>((const double2 *)c->any_s.p, (const double2 *)tb->bhat.p, (int)Lp, (double *)c->any_a.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return stft_batch_dev_t<double>(c, (const double *)c->any_a.p, inner, Lp, Lp, AUS_WINDOW_RECTANGULAR, 44100, nullptr, (Cx<double> *)c->any_s.p);
+}
+// the analyzer's own parameters (analyzer.rs:41-81) for the generic kernel: frequency table, roll-off fractions, slope bands
+struct AnalyzerPar { const double *freqs, *roll, *blo, *bhi; };
+static int analyzer_par(aus_ctx *c, size_t N, uint32_t sr, AnalyzerPar &ap) {
+    AUS_TRY(fill_feature_params_check(N, sr));
+    const size_t K = N / 2 + 1;
+    std::vector<double> h(K + 10);
+    AUS_TRY(aus_rfftfreq(N, sr, h.data()));
+    const double tail[10] = {0.5, 0.75, 0.9, 0.95, 0.0, 1000.0, 0.0, 1000.0, 5000.0, 5000.0};   // analyzer.rs:54-62
+    for (int i = 0; i < 10; ++i) h[K + i] = tail[i];
+    AUS_TRY(c->any_par.ensure(h.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->any_par.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                 // h is a temporary
+    const double *d = (const double *)c->any_par.p;
+    ap = AnalyzerPar{d, d + K, d + K + 4, d + K + 7};
+    return AUS_OK;
+}
+// 14 analyzer features of n magnitude rows of K bins (any K) -> d_feat (T), through the generic warp-per-row kernel
+template <typename T> static int analyze_rows(aus_ctx *c, const double *d_mags, size_t n, size_t K, uint32_t sr, const AnalyzerPar &ap, T *d_feat) {
+    double *dst = nullptr;
+    if constexpr (sizeof(T) == 8) dst = (double *)d_feat;
+    else {
+        AUS_TRY(c->any_feat.ensure(n * 14 * sizeof(double)));
+        dst = (double *)c->any_feat.p;
+    }
+    const unsigned int grid = (unsigned int)std::min<unsigned long long>((n + 7) / 8, (unsigned long long)c->sm_count * 32);
+    spectral_generic_kernel<<<grid, 256, 0, c->stream>>>(d_mags, n, (int)K, ap.freqs, ap.roll, 4, ap.blo, ap.bhi, 3, (double)sr, dst, 1);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    if constexpr (sizeof(T) == 4) AUS_TRY((cast_dev<double, float>(c, dst, (float *)d_feat, n * 14)));
+    return AUS_OK;
+}
+// forward: the stft_batch_dev_t contract for a non-native fft_size
+template <typename T>
+static int stft_batch(aus_ctx *c, const T *d_audio, const Batch &b, size_t N, size_t hop, int wtype, uint32_t sr, T *d_feat, Cx<T> *d_spec) {
+    Tab *tb = nullptr;
+    AUS_TRY(get_tab(c, N, &tb));
+    AUS_TRY(need_window(c, tb, wtype));
+    const size_t Lp = tb->Lp, K = N / 2 + 1;
+    AnalyzerPar ap{};
+    if (d_feat) AUS_TRY(analyzer_par(c, N, sr, ap));
+    std::vector<const unsigned long long *> dp;
+    AUS_TRY(upload_desc(c, c->any_desc, {&b.off, &b.len, &b.first}, dp));
+    const size_t Fc = chunk_frames(Lp, (size_t)b.total_frames);
+    AUS_TRY(workspace(c, Lp, Fc));
+    if (d_feat) AUS_TRY(c->any_mag.ensure(Fc * K * sizeof(double)));
+    for (unsigned long long g0 = 0; g0 < b.total_frames; g0 += Fc) {
+        const size_t n = (size_t)std::min<unsigned long long>(Fc, b.total_frames - g0);
+        pre_audio_kernel<T><<<(unsigned int)n, 256, 0, c->stream>>>(d_audio, dp[0], dp[1], dp[2], (int)b.off.size(), g0, (int)N, (int)Lp, (int)hop,
+                                                                    wtype, (const double *)tb->win[wtype].p, (const double2 *)tb->chirp.p,
+                                                                    (double *)c->any_a.p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        AUS_TRY(convolve(c, tb, n));
+        post_fwd_kernel<T><<<(unsigned int)n, 256, 0, c->stream>>>((const double2 *)c->any_s.p, (const double2 *)tb->chirp.p, (int)N, (int)Lp,
+                                                                   d_spec ? d_spec + g0 * K : nullptr, d_feat ? (double *)c->any_mag.p : nullptr);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        if (d_feat) AUS_TRY(analyze_rows<T>(c, (const double *)c->any_mag.p, n, K, sr, ap, d_feat + g0 * 14));
+    }
+    return AUS_OK;
+}
+// analyzer() on caller-supplied magnitude rows of a non-native fft_size
+template <typename T> static int analyzer(aus_ctx *c, const T *d_mags, size_t F, size_t N, uint32_t sr, T *d_feat) {
+    const size_t K = N / 2 + 1;
+    AnalyzerPar ap{};
+    AUS_TRY(analyzer_par(c, N, sr, ap));
+    const double *m = nullptr;
+    if constexpr (sizeof(T) == 8) m = (const double *)d_mags;
+    else {
+        AUS_TRY(c->any_mag.ensure(F * K * sizeof(double)));
+        AUS_TRY((cast_dev<float, double>(c, (const float *)d_mags, (double *)c->any_mag.p, F * K)));
+        m = (const double *)c->any_mag.p;
+    }
+    return analyze_rows<T>(c, m, F, K, sr, ap, d_feat);
+}
+}  // namespace anyn
+
 // features and/or spectra of a batch already resident on the device, in compute type T
 template <typename T>
 static int stft_batch_dev_t(aus_ctx *c, const T *d_audio, const Batch &b, size_t N, size_t hop, int wtype, uint32_t sr,
                             T *d_feat, Cx<T> *d_spec) {
     if (b.total_frames == 0) return AUS_OK;
+    if (!anyn::native_size(N)) return anyn::stft_batch<T>(c, d_audio, b, N, hop, wtype, sr, d_feat, d_spec);
     const int lg = log2_exact(N);
     Tables *tb = nullptr;
     AUS_TRY(get_tables<T>(c, lg, wtype, &tb));
@@ -1163,6 +1347,7 @@ extern "C" int aus_polar_to_complex(aus_ctx *c, const double *mag, const double 
 // ------------------------------------------------------------------------------------------------ analyzer (K3)
 template <typename T> static int analyzer_dev_t(aus_ctx *c, const T *d_mags, size_t F, size_t N, uint32_t sr, T *d_feat) {
     if (F == 0) return AUS_OK;
+    if (!anyn::native_size(N)) return anyn::analyzer<T>(c, d_mags, F, N, sr, d_feat);
     StftParams<T> p;
     memset(&p, 0, sizeof(p));
     AUS_TRY(fill_feature_params<T>(p, N, sr));
@@ -1219,9 +1404,58 @@ struct IShard {
 
 // K4 over a list of shards.  Leaves the signed, NaN-skipping max (fft.rs:255-258, starting at 0.0) of every shard's own
 // samples in c->misc[shard] (bit pattern of a double) and the K5 descriptors in c->desc.
+// K4's contract for a non-native fft_size (aus_anyn.cuh): every row through the chirp-z inverse, then a gather overlap-add
+template <typename T>
+static int irstft_k4_anyn(aus_ctx *c, const Cx<T> *d_spec, unsigned long long total_rows, const std::vector<IShard> &sh, size_t N,
+                          size_t hop, int wtype, int apply_window, T *d_out) {
+    if (N % 2) return fail(AUS_ERR_INVALID, "odd fft_size: the reference rebuilds fft_size - 1 bins and rustfft panics on the length (fft.rs:221-231)");
+    anyn::Tab *tb = nullptr;
+    AUS_TRY(anyn::get_tab(c, N, &tb));
+    AUS_TRY(anyn::need_window(c, tb, wtype));
+    const size_t Lp = tb->Lp;
+    AUS_TRY(c->any_y.ensure((size_t)total_rows * N * sizeof(double)));
+    const size_t Fc = anyn::chunk_frames(Lp, (size_t)total_rows);
+    AUS_TRY(anyn::workspace(c, Lp, Fc));
+    for (unsigned long long r0 = 0; r0 < total_rows; r0 += Fc) {
+        const size_t n = (size_t)std::min<unsigned long long>(Fc, total_rows - r0);
+        anyn::pre_spec_kernel<T><<<(unsigned int)n, 256, 0, c->stream>>>(d_spec, r0, (int)N, (int)Lp, (const double2 *)tb->chirp.p, (double *)c->any_a.p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        AUS_TRY(anyn::convolve(c, tb, n));
+        anyn::post_inv_kernel<<<(unsigned int)n, 256, 0, c->stream>>>((const double2 *)c->any_s.p, (const double2 *)tb->chirp.p, (int)N, (int)Lp,
+                                                                      (double *)c->any_y.p + r0 * N);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    const size_t ns = sh.size();
+    std::vector<unsigned long long> first(ns), frames(ns), row0(ns), samp0(ns), ooff(ns), olen(ns);
+    unsigned long long longest = 1;
+    for (size_t i = 0; i < ns; ++i) {
+        const IShard &x = sh[i];
+        first[i] = x.row_off; frames[i] = x.F; row0[i] = x.row0; samp0[i] = x.samp0(hop); ooff[i] = x.out_off; olen[i] = x.out_len(N, hop);
+        longest = std::max(longest, olen[i]);
+    }
+    std::vector<const unsigned long long *> dp;
+    AUS_TRY(upload_desc(c, c->desc, {&first, &frames, &row0, &samp0, &ooff, &olen}, dp));     // after the inner transforms used c->desc
+    c->k5_out_off = dp[4];
+    c->k5_out_len = dp[5];
+    AUS_TRY(c->misc.ensure(ns * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(c->misc.p, 0, ns * sizeof(unsigned long long), c->stream));     // maxval = 0.0, fft.rs:255
+    for (size_t s0 = 0; s0 < ns; s0 += 65535) {                 // grid.y = shard, at most 65535 per launch
+        const size_t cnt = std::min<size_t>(65535, ns - s0);
+        dim3 grid((unsigned int)std::min<unsigned long long>((longest + 255) / 256, (unsigned long long)c->sm_count * 8), (unsigned int)cnt);
+        anyn::ola_kernel<T><<<grid, 256, 0, c->stream>>>((const double *)c->any_y.p, d_out, dp[0] + s0, dp[1] + s0, dp[2] + s0, dp[3] + s0,
+                                                         dp[4] + s0, dp[5] + s0, (int)N, (int)hop, (const double *)tb->win[wtype].p,
+                                                         apply_window, (unsigned long long *)c->misc.p + s0);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    return AUS_OK;
+}
 template <typename T>
 static int irstft_k4(aus_ctx *c, const Cx<T> *d_spec, unsigned long long total_rows, const std::vector<IShard> &sh, size_t N,
                      size_t hop, int wtype, int apply_window, T *d_out) {
+    if (!anyn::native_size(N)) return irstft_k4_anyn<T>(c, d_spec, total_rows, sh, N, hop, wtype, apply_window, d_out);
     const int lg = log2_exact(N);
     Tables *tb = nullptr;
     AUS_TRY(get_tables<T>(c, lg, wtype, &tb));
@@ -1362,8 +1596,10 @@ extern "C" int aus_spectral_features_generic(aus_ctx *c, const double *mags, siz
         CUDA_TRY(cudaMemcpyAsync(d_bl, band_lo, n_bands * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(d_bh, band_hi, n_bands * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
-    spectral_generic_kernel<<<(unsigned int)((n_rows + 127) / 128), 128, 0, c->stream>>>(
-        d_m, n_rows, (int)n_bins, d_f, d_r, (int)n_roll, d_bl, d_bh, (int)n_bands, (double)sr, (double *)c->out64.p);
+    const unsigned long long want = (n_rows + 7) / 8;                       // 8 warps (rows) per CTA, grid-stride beyond 32 CTAs per SM
+    const unsigned int grid = (unsigned int)std::min<unsigned long long>(want, (unsigned long long)c->sm_count * 32);
+    spectral_generic_kernel<<<grid, 256, 0, c->stream>>>(
+        d_m, n_rows, (int)n_bins, d_f, d_r, (int)n_roll, d_bl, d_bh, (int)n_bands, (double)sr, (double *)c->out64.p, 0);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, n_rows * w * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -65,6 +65,8 @@ struct Tables {
     void *winf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};     // full-scale window pairs (inverse transform)
 };
 
+namespace anyn { struct Tab; }        // chirp-z tables of one non-native fft_size (aus_anyn.cuh)
+
 struct aus_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -81,6 +83,8 @@ struct aus_ctx {
     long long normtab_key = -1;            // (fft_size, hop, window, precision) the reciprocal-norm table was built for
     const unsigned long long *k5_out_off = nullptr, *k5_out_len = nullptr;   // K5 descriptors of the last irstft_k4 (in `desc`)
     DevBuf acorr;                          // padded chunks of aus_autocorrelation_batch
+    std::map<size_t, anyn::Tab *> anytabs; // fft sizes outside the radix-32 kernels' range (aus_anyn.cuh), by fft_size
+    DevBuf any_a, any_s, any_y, any_mag, any_desc, any_par, any_feat;   // their workspace
     std::vector<unsigned long long> desc_stage, desc_last;   // packed descriptor image being built / last uploaded to `desc`
     bool desc_valid = false;
     void *hostreg_ptr = nullptr;           // caller buffer currently page-locked by the host pipeline (cudaHostRegister)

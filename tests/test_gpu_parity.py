@@ -186,7 +186,7 @@ def test_error_codes(ctx, aus, orc):
     with pytest.raises(aus.AusError):
         ctx.rstft(x, 2048, 4096, 2)                   # hop > N: the reference panics
     with pytest.raises(aus.AusError):
-        ctx.rstft(x, 1000, 250, 2)                    # rustfft takes any N; this build is power-of-two only
+        ctx.rstft(x, 10000, 2500, 2)                  # rustfft takes any N; here: powers of two to 16384, anything to 8192
     with pytest.raises(aus.AusError):
         ctx.stft_features(x, 2048, 512, 2, 8000)      # 5 kHz band above Nyquist: the reference panics
     S = orc.rstft(x, 2048, 1024, 3)
@@ -571,6 +571,13 @@ def test_single_feature_wrappers_generic_parameters(ctx, aus, orc):
     m[7] = 0.0
     assert np.isnan(aus.analysis.spectral_entropy(m)) and np.isnan(orc.spectral_entropy(m))
     assert aus.analysis.spectral_flatness(m) == 0.0 == orc.spectral_flatness(m)
+    # exact ties: flat rows put thresholds exactly on (or within rounding of) a running sum; the reference's sequential
+    # arithmetic decides and the device must reproduce its index, not a neighbour's
+    for K in (64, 96, 1000, 1025):
+        m = np.full(K, 0.37)
+        f = np.arange(K, dtype=np.float64) * 3.0
+        for n in (1.0 / 64, 0.25, 0.5, 0.75, 1.0 - 1.0 / 64, 1.0):
+            assert aus.analysis.spectral_roll_off_point(m, f, n) == orc.spectral_roll_off_point(m, f, n), (K, n)
     # many rows in one call
     M = np.abs(rng.normal(size=(300, 513))) + 1e-3
     f = orc.rfftfreq(1024, 44100)
@@ -580,6 +587,17 @@ def test_single_feature_wrappers_generic_parameters(ctx, aus, orc):
         assert got[r, 0] == pytest.approx(orc.spectral_centroid(M[r], f), rel=RTOL64)
         assert got[r, 7] == orc.spectral_roll_off_point(M[r], f, 0.25) and got[r, 8] == orc.spectral_roll_off_point(M[r], f, 0.9)
         assert got[r, 9] == pytest.approx(orc.spectral_slope_region(M[r], f, 105.0, 852.0, 44100), rel=1e-7)
+    # more rows than one grid pass covers (the kernel walks rows warp by warp), every row checked on two columns
+    M = np.abs(rng.normal(size=(40000, 65))) + 1e-3
+    f = orc.rfftfreq(128, 8000)
+    got = ctx.spectral_features_generic(M, f, (0.5,), (), 8000)
+    assert got.shape == (40000, 8)
+    cen = (M @ f) / M.sum(axis=1)
+    np.testing.assert_allclose(got[:, 0], cen, rtol=1e-12)
+    P = M * M
+    cum = np.cumsum(P / P.sum(axis=1, keepdims=True), axis=1)
+    idx = np.minimum((cum < 0.5).sum(axis=1), 64)
+    assert np.array_equal(got[:, 7], f[idx])
 
 
 @pytest.mark.parametrize("fft_size,hop", [(1024, 256), (2048, 512), (4096, 1024)])
