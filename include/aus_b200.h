@@ -18,8 +18,11 @@
  *   - `_dev` entry points are stream-ordered on the context's stream and do NOT synchronise; host-pointer entry
  *     points copy H2D, run, copy D2H and return when the result is in the caller's buffer.
  *   - there is no CPU fallback: without a usable CUDA device every compute call fails with AUS_ERR_CUDA.
- *   - fft_size must be a power of two in [64, 16384]; 1 <= hop <= fft_size.  (The reference loops forever on
- *     hop == 0 and panics on hop > fft_size, spectrum/fft.rs:126-144; here both are AUS_ERR_INVALID.)
+ *   - fft_size: powers of two in [64, 16384] run on the tuned radix-32 kernels; every other size in [2, 8192] -- rustfft
+ *     plans any length, spectrum/fft.rs:120-121 -- runs as a chirp-z transform on top of them (same results to rounding,
+ *     about 20x the work; the inverse needs an even size, like the reference).  Anything else is AUS_ERR_UNSUPPORTED.
+ *   - 1 <= hop <= fft_size.  (The reference loops forever on hop == 0 and panics on hop > fft_size,
+ *     spectrum/fft.rs:126-144; here both are AUS_ERR_INVALID.)
  */
 #ifndef AUS_B200_H
 #define AUS_B200_H
@@ -37,7 +40,7 @@ typedef enum aus_status {
     AUS_ERR_CUDA = -2,         /* CUDA runtime error or no device */
     AUS_ERR_ALLOC = -3,        /* host or device allocation failed */
     AUS_ERR_SIZE = -4,         /* spectrum length mismatch (irfft / irstft `Err(SpectrumError)`, fft.rs:70-72, :217-219) */
-    AUS_ERR_UNSUPPORTED = -5   /* valid for the reference but not built here (e.g. non power-of-two fft_size) */
+    AUS_ERR_UNSUPPORTED = -5   /* valid for the reference but not built here (a non power-of-two fft_size above 8192) */
 } aus_status;
 
 /* window.rs:9-15 `WindowType`, same order */

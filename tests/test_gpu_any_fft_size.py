@@ -147,3 +147,22 @@ def test_any_size_many_frames_and_device_pointers(ctx, aus, orc):
     mag = np.abs(ref_s)
     ref_f = orc.analyze_spectrogram(mag, N, SR)
     assert_features(dfeat.cpu().numpy()[sel], ref_f, RTOL64, "device features")
+
+
+def test_any_size_multi_device_entry_points(aus, orc):
+    """Frame-range shards with recomputed halo (features and irstft) work the same for a chirp-z size: four shards over the
+    visible devices (all on device 0 when there is one)."""
+    torch = pytest.importorskip("torch")
+    devs = [i % torch.cuda.device_count() for i in range(4)]
+    N, hop = 1000, 250
+    x = orc.synth_signal(60 * N + 77, SR, seed=51)
+    try:
+        got = aus.stft_features_multi(devs, x, [0], [x.size], N, hop, orc.HAMMING, SR)
+        assert_features(got, orc.stft_features(x, N, hop, orc.HAMMING, SR), RTOL64, "multi features N=1000")
+        S = orc.rstft(x, N, hop, orc.HAMMING)
+        outs = aus.irstft_multi(devs, [S, S[:7]], N, hop, orc.HAMMING)
+        for o, s in zip(outs, (S, S[:7])):
+            ref = orc.irstft(s, N, hop, orc.HAMMING)
+            assert o.shape == ref.shape and np.max(np.abs(o - ref)) <= RTOL64 * np.max(np.abs(ref))
+    finally:
+        aus.multi_shutdown()
