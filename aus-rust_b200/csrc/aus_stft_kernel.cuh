@@ -528,6 +528,9 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     }
 }
 
+#ifndef AUS_PSUM_ENTROPY
+#define AUS_PSUM_ENTROPY 0       // experiment: entropy / flatness sums over p instead of q = p / P (one multiply per bin less)
+#endif
 #ifndef AUS_FEAT32
 #define AUS_FEAT32 1             // f64, one warp per frame: latency-trimmed second half of the feature computation (below)
 #endif
@@ -755,8 +758,14 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     constexpr int SW = AUS_SWEEP_W;
     auto sweep4 = [&](const T (&pv)[SW], T d0) {
         T q[SW], l[SW];
+#if AUS_PSUM_ENTROPY
+        // sum p log2 p and sum log2 p; -sum q log2 q = log2 P - S / P and sum log2 q = sum log2 p - K log2 P follow per frame
+#pragma unroll
+        for (int c = 0; c < SW; ++c) q[c] = pv[c];
+#else
 #pragma unroll
         for (int c = 0; c < SW; ++c) q[c] = pv[c] * inv_p;                // make_spectrum_pmf, s_a_t.rs:284-290
+#endif
 #pragma unroll
         for (int c = 0; c < SW; ++c) l[c] = Mth<T>::log2_(q[c], ltab);
 #pragma unroll
@@ -798,7 +807,7 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
             const T pw = acc.mid;
             const T d = (T)(M / 2) - kappa;
             const T dd = d * d, w2 = dd * pw;
-            const T q = pw * inv_p;
+            const T q = AUS_PSUM_ENTROPY ? pw : pw * inv_p;
             const T l = Mth<T>::log2_(q, ltab);
             d2s[0] += w2;
             d3s[0] = fma(w2, d, d3s[0]);
@@ -831,7 +840,14 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     }
     // ---- ten sums by recursive halving: lane t ends up with the total of value t >> 1
     const T r10[10] = {acc.s_pk, d2s[0] + d2s[1], d3s[0] + d3s[1], d4s[0] + d4s[1], e_sum, l_sum, b1p, b1pk, b2p, b2pk};
-    const T tot = warp_reduce_scatter<10>(r10, t);
+    T tot = warp_reduce_scatter<10>(r10, t);
+#if AUS_PSUM_ENTROPY
+    if (!badq) {                                         // lanes 8, 9 hold sum p log2 p, lanes 10, 11 sum log2 p
+        const T l2P = log2(P);
+        if (vi == 4) tot = fma(tot, inv_p, -l2P);        // sum q log2 q = S / P - log2 P
+        if (vi == 5) tot = fma(-(T)K, l2P, tot);         // sum log2 q = sum log2 p - K log2 P
+    }
+#endif
     double *rec = p.raw + g * (unsigned long long)RAW_N;
     const bool wr = active && p.raw != nullptr;
     if (wr) {
