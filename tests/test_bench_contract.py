@@ -88,3 +88,15 @@ def test_gpu_corpus_leg():
     d = _run(["--corpus", "--corpus-files", "6"], 580)
     assert d["finite"] and d["analyse_stream"] > 1e7 and 0 < d["generate_analyse_stream"] <= 1.05 * d["analyse_stream"]
     assert d["feature_d2h_gbs"] > 1
+
+
+def test_build_is_quiet_on_stdout_and_safe_to_call_concurrently():
+    """bench.py calls build() in every torchrun rank and prints ONE JSON line on stdout: build() must serialise on its lock
+    (two `make`s in one directory race) and send all tool output to stderr."""
+    code = "import __graft_entry__ as g; g.build()"
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+             for _ in range(3)]
+    for p in procs:
+        out, err = p.communicate(timeout=1500)
+        assert p.returncode == 0, err.decode()[-2000:]
+        assert out == b"", out[:500]
