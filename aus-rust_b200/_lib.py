@@ -13,6 +13,10 @@ FEATURE_NAMES = (
     "spectral_slope_0_5_khz",
 )  # analysis/analyzer.rs:10-23
 
+# aus_compute_kind (include/aus_b200.h)
+(COMPUTE_CENTROID, COMPUTE_ENTROPY, COMPUTE_FLATNESS, COMPUTE_KURTOSIS, COMPUTE_ROLL_OFF, COMPUTE_SKEWNESS, COMPUTE_SLOPE,
+ COMPUTE_SLOPE_REGION, COMPUTE_VARIANCE, COMPUTE_DOT_PRODUCT, COMPUTE_POWER_SPECTRUM, COMPUTE_SPECTRUM_PMF) = range(12)
+
 AUS_OK, AUS_ERR_INVALID, AUS_ERR_CUDA, AUS_ERR_ALLOC, AUS_ERR_SIZE, AUS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 
@@ -86,6 +90,9 @@ SIGNATURES = {
     "aus_polar_to_complex_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "aus_spectral_features_generic": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, _p_d, _p_d, c_size_t, _p_d, _p_d, c_size_t,
                                               c_uint32, _p_d]),
+    "aus_spectral_compute": (c_int, [c_void_p, c_int, _p_d, _p_d, c_size_t, c_double, c_double, c_uint32, _p_d]),
+    "aus_overlap_add": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_size_t, _p_d]),
+    "aus_overlap_add_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "aus_analyzer_batch": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_uint32, c_int, _p_d]),
     "aus_analyzer_batch_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, c_int, c_void_p]),
     "aus_irstft": (c_int, [c_void_p, _p_d, c_size_t, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, _p_d]),

@@ -5,6 +5,7 @@ from dataclasses import dataclass, fields
 
 import numpy as np
 
+from . import _lib
 from .api import default_context
 from ._lib import FEATURE_NAMES
 
@@ -48,9 +49,58 @@ def analyzer_batch(magnitude_spectrogram, fft_size: int, sample_rate: int) -> np
     return default_context().analyzer_batch(magnitude_spectrogram, fft_size, sample_rate)
 
 
-def make_power_spectrum(magnitude_spectrum) -> np.ndarray:
-    """spectral_analysis_tools.rs:273 (trivial, host)."""
-    return np.asarray(magnitude_spectrum, dtype=np.float64) ** 2.0
+def _c(what, a, b=None, s0=0.0, s1=0.0, sample_rate=44100):
+    return default_context().spectral_compute(what, a, b, s0, s1, sample_rate)
+
+
+# the public building blocks of spectral_analysis_tools.rs:79-290: same names, arguments and meaning -- they use whatever
+# intermediates (sums, pmf, centroid, variance) the caller passes, like the reference
+def make_power_spectrum(magnitude_spectrum) -> np.ndarray:                                          # :273
+    return _c(_lib.COMPUTE_POWER_SPECTRUM, magnitude_spectrum)
+
+
+def make_spectrum_pmf(power_spectrum, power_spectrum_sum: float) -> np.ndarray:                     # :284
+    return _c(_lib.COMPUTE_SPECTRUM_PMF, power_spectrum, None, power_spectrum_sum)
+
+
+def dot_product(vec1, vec2) -> float:                                                               # :253
+    return _c(_lib.COMPUTE_DOT_PRODUCT, vec1, vec2)
+
+
+def compute_spectral_centroid(magnitude_spectrum, rfft_freqs, magnitude_spectrum_sum: float) -> float:        # :79
+    return _c(_lib.COMPUTE_CENTROID, magnitude_spectrum, rfft_freqs, magnitude_spectrum_sum)
+
+
+def compute_spectral_entropy(spectrum_pmf) -> float:                                                # :93
+    return _c(_lib.COMPUTE_ENTROPY, spectrum_pmf)
+
+
+def compute_spectral_flatness(magnitude_spectrum, magnitude_spectrum_sum: float) -> float:          # :107
+    return _c(_lib.COMPUTE_FLATNESS, magnitude_spectrum, None, magnitude_spectrum_sum)
+
+
+def compute_spectral_kurtosis(spectrum_pmf, rfft_freqs, spectral_centroid: float, spectral_variance: float) -> float:   # :122
+    return _c(_lib.COMPUTE_KURTOSIS, spectrum_pmf, rfft_freqs, spectral_centroid, spectral_variance)
+
+
+def compute_spectral_roll_off_point(power_spectrum, rfft_freqs, power_spectrum_sum: float, n: float) -> float:          # :137
+    return _c(_lib.COMPUTE_ROLL_OFF, power_spectrum, rfft_freqs, power_spectrum_sum, n)
+
+
+def compute_spectral_skewness(spectrum_pmf, rfft_freqs, spectral_centroid: float, spectral_variance: float) -> float:   # :153
+    return _c(_lib.COMPUTE_SKEWNESS, spectrum_pmf, rfft_freqs, spectral_centroid, spectral_variance)
+
+
+def compute_spectral_slope(power_spectrum, power_spectrum_sum: float) -> float:                     # :167
+    return _c(_lib.COMPUTE_SLOPE, power_spectrum, None, power_spectrum_sum)
+
+
+def compute_spectral_slope_region(power_spectrum, rfft_freqs, f_lower: float, f_upper: float, sample_rate: int) -> float:  # :190
+    return _c(_lib.COMPUTE_SLOPE_REGION, power_spectrum, rfft_freqs, f_lower, f_upper, sample_rate)
+
+
+def compute_spectral_variance(spectrum_pmf, rfft_freqs, spectral_centroid: float) -> float:         # :238
+    return _c(_lib.COMPUTE_VARIANCE, spectrum_pmf, rfft_freqs, spectral_centroid)
 
 
 def _one(magnitude_spectrum, rfft_freqs, roll=(), bands=(), sample_rate=None) -> np.ndarray:

@@ -268,6 +268,33 @@ class Context:
                                                            _pd(lo), _pd(hi), lo.size, int(sample_rate), _pd(out)))
         return out
 
+    def spectral_compute(self, what: int, a, b=None, s0: float = 0.0, s1: float = 0.0, sample_rate: int = 44100):
+        """One of the `compute_*` / `make_*` / `dot_product` helpers of spectral_analysis_tools.rs:79-290 on one vector, with
+        the caller's own intermediates (see aus_compute_kind in include/aus_b200.h) -> float, or an array for the two
+        vector-valued kinds."""
+        av = _f64(a).reshape(-1)
+        bv = None if b is None else _f64(b).reshape(-1)
+        if bv is not None and bv.size != av.size:
+            raise IndexError("the two vectors differ in length (the reference panics)")
+        vec = what in (_lib.COMPUTE_POWER_SPECTRUM, _lib.COMPUTE_SPECTRUM_PMF)
+        out = np.empty(av.size if vec else 1, dtype=np.float64)
+        _lib.check(self._lib.aus_spectral_compute(self._h, int(what), _pd(av), None if bv is None else _pd(bv), av.size,
+                                                  float(s0), float(s1), int(sample_rate), _pd(out)))
+        return out if vec else float(out[0])
+
+    def overlap_add(self, audio_chunks, fft_size: int, hop: int) -> np.ndarray:
+        """spectrum/fft_tools.rs:69: [n_chunks, fft_size] rows -> fft_size + hop (n_chunks - 1) samples."""
+        ch = _f64(audio_chunks)
+        if ch.ndim != 2 or ch.shape[1] != fft_size:
+            raise IndexError("every chunk must hold fft_size samples (the reference indexes out of bounds)")
+        out = np.empty(int(fft_size) + int(hop) * (ch.shape[0] - 1) if ch.shape[0] else 0, dtype=np.float64)
+        _lib.check(self._lib.aus_overlap_add(self._h, _pd(ch), ch.shape[0], int(fft_size), int(hop), _pd(out)))
+        return out
+
+    def overlap_add_dev(self, d_chunks, n_chunks: int, fft_size: int, hop: int, d_audio):
+        _lib.check(self._lib.aus_overlap_add_dev(self._h, self._check_dev(d_chunks, "f64", "d_chunks"), int(n_chunks), int(fft_size),
+                                                 int(hop), self._check_dev(d_audio, "f64", "d_audio")))
+
     def autocorrelation(self, audio, fft_size: int) -> np.ndarray:
         """analysis/spectral_analysis_tools.rs:31 (one chunk, or [n_chunks, fft_size] rows)."""
         a = _f64(audio)

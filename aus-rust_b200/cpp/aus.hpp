@@ -106,6 +106,18 @@ inline std::vector<double> rfftfreq(size_t fft_size, uint32_t sample_rate) {    
     detail::ok(aus_rfftfreq(fft_size, sample_rate, f.data()));
     return f;
 }
+inline std::vector<double> overlap_add(const std::vector<std::vector<double>> &audio_chunks, size_t fft_size, size_t hop_size) {   // fft_tools.rs:69
+    if (audio_chunks.empty()) return {};
+    std::vector<double> flat;
+    flat.reserve(audio_chunks.size() * fft_size);
+    for (auto &ch : audio_chunks) {
+        if (ch.size() != fft_size) throw std::runtime_error("overlap_add: every chunk must hold fft_size samples");
+        flat.insert(flat.end(), ch.begin(), ch.end());
+    }
+    std::vector<double> out(fft_size + hop_size * (audio_chunks.size() - 1));
+    detail::ok(aus_overlap_add(detail::ctx(), flat.data(), audio_chunks.size(), fft_size, hop_size, out.data()));
+    return out;
+}
 }  // namespace spectrum
 
 namespace analysis {
@@ -136,6 +148,35 @@ inline std::vector<double> one(const std::vector<double> &m, const std::vector<d
     return out;
 }
 }  // namespace detail
+// The public building blocks of spectral_analysis_tools.rs:79-290 with the caller's own intermediates (aus_compute_kind).
+namespace detail {
+inline double compute(int what, const std::vector<double> &a, const std::vector<double> *b, double s0, double s1, uint32_t sr = 44100) {
+    if (b && b->size() != a.size()) throw std::runtime_error("the two vectors differ in length");
+    double out = 0.0;
+    aus::detail::ok(aus_spectral_compute(aus::detail::ctx(), what, a.data(), b ? b->data() : nullptr, a.size(), s0, s1, sr, &out));
+    return out;
+}
+inline std::vector<double> compute_vec(int what, const std::vector<double> &a, double s0) {
+    std::vector<double> out(a.size());
+    aus::detail::ok(aus_spectral_compute(aus::detail::ctx(), what, a.data(), nullptr, a.size(), s0, 0.0, 44100, out.data()));
+    return out;
+}
+}  // namespace detail
+inline double compute_spectral_centroid(const std::vector<double> &m, const std::vector<double> &f, double m_sum) { return detail::compute(AUS_COMPUTE_CENTROID, m, &f, m_sum, 0.0); }   // :79
+inline double compute_spectral_entropy(const std::vector<double> &pmf) { return detail::compute(AUS_COMPUTE_ENTROPY, pmf, nullptr, 0.0, 0.0); }                                      // :93
+inline double compute_spectral_flatness(const std::vector<double> &m, double m_sum) { return detail::compute(AUS_COMPUTE_FLATNESS, m, nullptr, m_sum, 0.0); }                        // :107
+inline double compute_spectral_kurtosis(const std::vector<double> &pmf, const std::vector<double> &f, double c, double var) { return detail::compute(AUS_COMPUTE_KURTOSIS, pmf, &f, c, var); }   // :122
+inline double compute_spectral_roll_off_point(const std::vector<double> &p, const std::vector<double> &f, double p_sum, double n) { return detail::compute(AUS_COMPUTE_ROLL_OFF, p, &f, p_sum, n); }   // :137
+inline double compute_spectral_skewness(const std::vector<double> &pmf, const std::vector<double> &f, double c, double var) { return detail::compute(AUS_COMPUTE_SKEWNESS, pmf, &f, c, var); }   // :153
+inline double compute_spectral_slope(const std::vector<double> &p, double p_sum) { return detail::compute(AUS_COMPUTE_SLOPE, p, nullptr, p_sum, 0.0); }                              // :167
+inline double compute_spectral_slope_region(const std::vector<double> &p, const std::vector<double> &f, double f_lower, double f_upper, uint32_t sample_rate) {                      // :190
+    return detail::compute(AUS_COMPUTE_SLOPE_REGION, p, &f, f_lower, f_upper, sample_rate);
+}
+inline double compute_spectral_variance(const std::vector<double> &pmf, const std::vector<double> &f, double c) { return detail::compute(AUS_COMPUTE_VARIANCE, pmf, &f, c, 0.0); }     // :238
+inline double dot_product(const std::vector<double> &a, const std::vector<double> &b) { return detail::compute(AUS_COMPUTE_DOT_PRODUCT, a, &b, 0.0, 0.0); }                          // :253
+inline std::vector<double> make_power_spectrum(const std::vector<double> &m) { return detail::compute_vec(AUS_COMPUTE_POWER_SPECTRUM, m, 0.0); }                                     // :273
+inline std::vector<double> make_spectrum_pmf(const std::vector<double> &p, double p_sum) { return detail::compute_vec(AUS_COMPUTE_SPECTRUM_PMF, p, p_sum); }                          // :284
+
 inline double spectral_centroid(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[0]; }   // :306
 inline double spectral_variance(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[1]; }   // :466
 inline double spectral_skewness(const std::vector<double> &m, const std::vector<double> &f) { return detail::one(m, &f, {}, {}, {}, 44100)[2]; }   // :405

@@ -640,6 +640,149 @@ __global__ void __launch_bounds__(256) spectral_generic_kernel(const double *mag
     }
 }
 
+// ------------------------------------------------------------------------------------------------ compute_* helpers
+// spectral_analysis_tools.rs:79-290 on ONE vector with the caller's own intermediates: a single 256-thread CTA, thread-strided
+// coalesced passes, sums combined in a fixed order (warp xor tree, then the eight warp totals in ascending order).
+__device__ __forceinline__ double block_sum256(double v, double *sm) {
+    v = warp_sum_all(v);
+    __syncthreads();                                   // sm may still be read from the previous sum
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    return t;
+}
+__global__ void __launch_bounds__(256) spectral_compute_kernel(int what, const double *a, const double *b, int n, double s0, double s1,
+                                                              double sr, double *out) {
+    __shared__ double sm[8];
+    __shared__ double scan[256];
+    const int t = threadIdx.x;
+    const double nn = (double)n;
+    switch (what) {
+    case AUS_COMPUTE_POWER_SPECTRUM:
+        for (int i = t; i < n; i += 256) out[i] = a[i] * a[i];
+        return;
+    case AUS_COMPUTE_SPECTRUM_PMF:
+        for (int i = t; i < n; i += 256) out[i] = a[i] / s0;
+        return;
+    case AUS_COMPUTE_CENTROID: case AUS_COMPUTE_DOT_PRODUCT: {
+        double acc = 0.0;
+        for (int i = t; i < n; i += 256) acc += a[i] * b[i];
+        acc = block_sum256(acc, sm);
+        if (t == 0) out[0] = what == AUS_COMPUTE_CENTROID ? acc / s0 : acc;
+        return;
+    }
+    case AUS_COMPUTE_ENTROPY: {
+        double acc = 0.0;
+        for (int i = t; i < n; i += 256) acc += a[i] * log2(a[i]);
+        acc = block_sum256(acc, sm);
+        if (t == 0) out[0] = -acc;
+        return;
+    }
+    case AUS_COMPUTE_FLATNESS: {
+        double acc = 0.0;
+        for (int i = t; i < n; i += 256) acc += log(a[i]);
+        acc = block_sum256(acc, sm);
+        if (t == 0) out[0] = exp(acc / nn) * nn / s0;
+        return;
+    }
+    case AUS_COMPUTE_VARIANCE: case AUS_COMPUTE_SKEWNESS: case AUS_COMPUTE_KURTOSIS: {
+        double acc = 0.0;
+        for (int i = t; i < n; i += 256) {
+            const double d = b[i] - s0, d2 = d * d;
+            acc += (what == AUS_COMPUTE_VARIANCE ? d2 : what == AUS_COMPUTE_SKEWNESS ? d2 * d : d2 * d2) * a[i];
+        }
+        acc = block_sum256(acc, sm);
+        if (t == 0) out[0] = what == AUS_COMPUTE_VARIANCE ? acc : what == AUS_COMPUTE_SKEWNESS ? acc / pow(s1, 1.5) : acc / (s1 * s1);
+        return;
+    }
+    case AUS_COMPUTE_SLOPE: {
+        double acc = 0.0;
+        for (int i = t; i < n; i += 256) acc += a[i] * (double)i;
+        acc = block_sum256(acc, sm);
+        const double sum_x = nn * (nn - 1.0) / 2.0, sum_x2 = nn * (nn - 1.0) * (2.0 * nn - 1.0) / 6.0;
+        if (t == 0) out[0] = (nn * acc - sum_x * s0) / (nn * sum_x2 - sum_x * sum_x);
+        return;
+    }
+    case AUS_COMPUTE_SLOPE_REGION: {                   // bounds checked on the host
+        const double fund = sr / ((double)(n - 1) * 2.0);
+        const double m_fl = s0 / fund, m_fu = s1 / fund;
+        const int lc = (int)ceil(m_fl), lf = (int)floor(m_fl), uc = (int)ceil(m_fu), uf = (int)floor(m_fu);
+        double sx = 0.0, sy = 0.0, sxx = 0.0, sxy = 0.0;
+        for (int i = lc + t; i < uf; i += 256) {
+            const double f = b[i], p = a[i];
+            sx += f; sy += p; sxx += f * f; sxy += p * f;
+        }
+        sx = block_sum256(sx, sm); sy = block_sum256(sy, sm); sxx = block_sum256(sxx, sm); sxy = block_sum256(sxy, sm);
+        if (t == 0) {
+            const double pl = a[lf] + (m_fl - (double)lf) * (a[lc] - a[lf]);
+            const double pu = a[uf] + (m_fu - (double)uf) * (a[uc] - a[uf]);
+            const double sum_x = s0 + sx + s1, sum_y = pl + sy + pu;
+            const double sum_x2 = s0 * s0 + sxx + s1 * s1, sum_xy = s0 * pl + sxy + s1 * pu;
+            out[0] = (nn * sum_xy - sum_x * sum_y) / (nn * sum_x2 - sum_x * sum_x);
+        }
+        return;
+    }
+    case AUS_COMPUTE_ROLL_OFF: {                       // s0 = power sum, s1 = fraction; the reference's loop is sequential
+        const int C = (n + 255) / 256;
+        const int lo = t * C < n ? t * C : n, hi = lo + C < n ? lo + C : n;
+        double cs = 0.0;
+        for (int i = lo; i < hi; ++i) cs += a[i] / s0;
+        scan[t] = cs;
+        __syncthreads();
+        if (t == 0) {
+            double run = 0.0;
+            int idx = n - 1;
+            double at = 0.0, before = 0.0;
+            bool found = false;
+            for (int c = 0; c < 256 && !found; ++c) {                 // chunk whose end is not below the fraction
+                const double end = run + scan[c];
+                const int clo = c * C < n ? c * C : n, chi = clo + C < n ? clo + C : n;
+                if (clo < chi && !(end < s1)) {
+                    double cum = run;
+                    for (int i = clo; i < chi; ++i) {
+                        before = cum;
+                        cum += a[i] / s0;
+                        if (!(cum < s1)) { idx = i; found = true; break; }
+                    }
+                    at = cum;
+                    if (!found) { found = true; idx = n - 1; }         // rounding: settled by the sequential redo below
+                } else {
+                    run = end;
+                }
+            }
+            if (!found) { at = run; before = run - a[n - 1] / s0; }
+            const double tol = 1e-12 + 1e-15 * nn;
+            if (!(fabs(at - s1) > tol) || !(fabs(s1 - before) > tol)) {       // knife edge (or NaN): the reference's own arithmetic
+                long long i = -1;
+                double cum = 0.0;
+                while (cum < s1 && i < (long long)n - 1) {
+                    ++i;
+                    cum += a[i] / s0;
+                }
+                idx = (int)i;
+            }
+            out[0] = b[idx < 0 ? 0 : idx];
+        }
+        return;
+    }
+    }
+}
+
+// fft_tools.rs:69-112 as a gather: one thread per output sample, covering rows added in ascending row order
+__global__ void __launch_bounds__(256) overlap_add_kernel(const double *chunks, unsigned long long F, int N, int hop, double *out,
+                                                         unsigned long long n_out) {
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_out; s += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long h_lo = s >= (unsigned long long)N ? (s - N) / hop + 1 : 0ull;
+        unsigned long long h_hi = s / hop;
+        if (h_hi > F - 1) h_hi = F - 1;
+        double acc = 0.0;
+        for (unsigned long long h = h_lo; h <= h_hi; ++h) acc += chunks[h * (unsigned long long)N + (s - h * hop)];
+        out[s] = acc;
+    }
+}
+
 // fft_tools.rs:41-55
 __global__ void to_polar_kernel(const double2 *s, double *mag, double *ph, unsigned long long n) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -2268,6 +2411,73 @@ extern "C" int aus_time_features_frames(aus_ctx *c, const double *audio, const u
 // host-pointer feature path, pageable input (a Rust `Vec<f64>`): 0 = hand it to cudaMemcpyAsync (the driver stages it),
 // 1 = page-lock it for the duration of the call (cudaHostRegister), 2 = copy it chunk by chunk into the pipeline's own
 // pinned buffers with several host threads, -1 (default) = 2 for inputs of at least 64 MB, 0 below.
+// ------------------------------------------------------------------------------------------------ compute_* / overlap_add (ABI)
+extern "C" int aus_spectral_compute(aus_ctx *c, int what, const double *a, const double *b, size_t n, double s0, double s1,
+                                    uint32_t sr, double *out) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (what < AUS_COMPUTE_CENTROID || what > AUS_COMPUTE_SPECTRUM_PMF) return fail(AUS_ERR_INVALID, "unknown compute kind");
+    const bool needs_b = what == AUS_COMPUTE_CENTROID || what == AUS_COMPUTE_KURTOSIS || what == AUS_COMPUTE_ROLL_OFF ||
+                         what == AUS_COMPUTE_SKEWNESS || what == AUS_COMPUTE_SLOPE_REGION || what == AUS_COMPUTE_VARIANCE ||
+                         what == AUS_COMPUTE_DOT_PRODUCT;
+    if (!a || !out || (needs_b && !b)) return fail(AUS_ERR_INVALID, "null argument");
+    if (n == 0 || n > (1u << 24)) return fail(AUS_ERR_INVALID, "bad size");
+    if (what == AUS_COMPUTE_ROLL_OFF && !(s1 > 0.0)) return fail(AUS_ERR_INVALID, "roll-off fraction must be > 0 (the reference indexes [-1] and panics)");
+    if (what == AUS_COMPUTE_SLOPE_REGION) {
+        if (n < 2) return fail(AUS_ERR_INVALID, "bad size");
+        const double fund = (double)sr / ((double)(n - 1) * 2.0), m_fl = s0 / fund, m_fu = s1 / fund;
+        if (!(m_fl >= 0.0) || !(m_fu >= m_fl) || !(std::ceil(m_fu) < (double)n) || std::ceil(m_fl) > std::floor(m_fu))
+            return fail(AUS_ERR_INVALID, "slope band outside the spectrum (the reference panics: index out of bounds)");
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool vec_out = what == AUS_COMPUTE_POWER_SPECTRUM || what == AUS_COMPUTE_SPECTRUM_PMF;
+    const size_t n_out = vec_out ? n : 1;
+    AUS_TRY(c->in64.ensure(2 * n * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n_out * sizeof(double)));
+    double *d_a = (double *)c->in64.p, *d_b = d_a + n;
+    CUDA_TRY(cudaMemcpyAsync(d_a, a, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (needs_b) CUDA_TRY(cudaMemcpyAsync(d_b, b, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    spectral_compute_kernel<<<1, 256, 0, c->stream>>>(what, d_a, needs_b ? d_b : nullptr, (int)n, s0, s1, (double)sr, (double *)c->out64.p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, c->out64.p, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
+static int check_overlap_add(aus_ctx *c, size_t F, size_t N, size_t hop) {
+    if (!c) return fail(AUS_ERR_INVALID, "null context");
+    if (F == 0) return fail(AUS_ERR_INVALID, "no chunks (the reference underflows at fft_tools.rs:70)");
+    if (N == 0 || N > (1u << 24)) return fail(AUS_ERR_INVALID, "bad fft_size");
+    if (hop == 0) return fail(AUS_ERR_INVALID, "hop_size must be > 0 (fft_tools.rs:68)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return AUS_OK;
+}
+extern "C" int aus_overlap_add_dev(aus_ctx *c, const void *d_chunks, size_t F, size_t N, size_t hop, void *d_audio) {
+    AUS_TRY(check_overlap_add(c, F, N, hop));
+    if (!d_chunks || !d_audio) return fail(AUS_ERR_INVALID, "null argument");
+    AUS_TRY(check_dev_align(d_chunks, AUS_F64, false, "d_chunks"));
+    AUS_TRY(check_dev_align(d_audio, AUS_F64, false, "d_audio"));
+    const unsigned long long n_out = N + hop * (F - 1);
+    const unsigned int grid = (unsigned int)std::min<unsigned long long>((n_out + 255) / 256, (unsigned long long)c->sm_count * 16);
+    overlap_add_kernel<<<grid, 256, 0, c->stream>>>((const double *)d_chunks, F, (int)N, (int)std::min<size_t>(hop, (size_t)1 << 30), (double *)d_audio, n_out);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return AUS_OK;
+}
+extern "C" int aus_overlap_add(aus_ctx *c, const double *chunks, size_t F, size_t N, size_t hop, double *audio) {
+    AUS_TRY(check_overlap_add(c, F, N, hop));
+    if (!chunks || !audio) return fail(AUS_ERR_INVALID, "null argument");
+    if (hop > ((size_t)1 << 30)) return fail(AUS_ERR_INVALID, "hop_size too large");
+    const size_t n_in = F * N, n_out = N + hop * (F - 1);
+    AUS_TRY(c->in64.ensure(n_in * sizeof(double)));
+    AUS_TRY(c->out64.ensure(n_out * sizeof(double)));
+    AUS_TRY(xfer_h2d(c, c->in64.p, chunks, n_in * sizeof(double)));
+    AUS_TRY(aus_overlap_add_dev(c, c->in64.p, F, N, hop, c->out64.p));
+    AUS_TRY(xfer_d2h(c, audio, c->out64.p, n_out * sizeof(double)));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return AUS_OK;
+}
+
 extern "C" int aus_ctx_set_host_register(aus_ctx *c, int mode) {
     if (!c || mode < -1 || mode > 2) return fail(AUS_ERR_INVALID, "bad argument");
     c->hostreg_mode = mode;

@@ -56,6 +56,9 @@ extern "C" {
     fn aus_stft_features_multi(devices: *const c_int, n_devices: c_int, audio: *const f64, offsets: *const u64, lengths: *const u64,
                                n_files: usize, fft_size: usize, hop: usize, window: c_int, sample_rate: u32, precision: c_int,
                                features: *mut f64) -> c_int;
+    fn aus_spectral_compute(ctx: *mut AusCtx, what: c_int, a: *const f64, b: *const f64, n: usize, s0: f64, s1: f64, sample_rate: u32,
+                            out: *mut f64) -> c_int;
+    fn aus_overlap_add(ctx: *mut AusCtx, chunks: *const f64, n_chunks: usize, fft_size: usize, hop: usize, audio: *mut f64) -> c_int;
     fn aus_autocorrelation(ctx: *mut AusCtx, audio: *const f64, audio_len: usize, fft_size: usize, out: *mut f64) -> c_int;
     fn aus_time_features_batch(ctx: *mut AusCtx, audio: *const f64, offsets: *const u64, lengths: *const u64, n_files: usize,
                                sample_rate: u32, out: *mut f64) -> c_int;
@@ -220,6 +223,16 @@ pub mod spectrum {
     }
 
     /// spectrum/fft_tools.rs:199
+    /// fft_tools.rs:69
+    pub fn overlap_add(audio_chunks: &Vec<Vec<f64>>, fft_size: usize, hop_size: usize) -> Vec<f64> {
+        if audio_chunks.is_empty() { return Vec::new(); }
+        let mut flat: Vec<f64> = Vec::with_capacity(audio_chunks.len() * fft_size);
+        for ch in audio_chunks { assert_eq!(ch.len(), fft_size); flat.extend_from_slice(ch); }
+        let mut out = vec![0.0f64; fft_size + hop_size * (audio_chunks.len() - 1)];
+        with_ctx(|c| ok(unsafe { aus_overlap_add(c, flat.as_ptr(), audio_chunks.len(), fft_size, hop_size, out.as_mut_ptr()) }));
+        out
+    }
+
     pub fn rfftfreq(fft_size: usize, sample_rate: u32) -> Vec<f64> {
         let mut f = vec![0.0; fft_size / 2 + 1];
         ok(unsafe { aus_rfftfreq(fft_size, sample_rate, f.as_mut_ptr()) });
@@ -268,9 +281,50 @@ pub mod analysis {
         from_row(&out)
     }
 
-    /// spectral_analysis_tools.rs:273
-    pub fn make_power_spectrum(magnitude_spectrum: &Vec<f64>) -> Vec<f64> {
-        magnitude_spectrum.iter().map(|m| m * m).collect()
+    // The public building blocks of spectral_analysis_tools.rs:79-290: same signatures, and -- like the reference -- they use
+    // whatever intermediates (sums, pmf, centroid, variance) the caller passes.  `what` = aus_compute_kind of aus_b200.h.
+    fn compute(what: c_int, a: &[f64], b: Option<&[f64]>, s0: f64, s1: f64, sample_rate: u32) -> f64 {
+        if let Some(b) = b { assert_eq!(a.len(), b.len()); }
+        let mut out = 0.0f64;
+        with_ctx(|c| ok(unsafe {
+            aus_spectral_compute(c, what, a.as_ptr(), b.map_or(std::ptr::null(), |b| b.as_ptr()), a.len(), s0, s1, sample_rate, &mut out)
+        }));
+        out
+    }
+    fn compute_vec(what: c_int, a: &[f64], s0: f64) -> Vec<f64> {
+        let mut out = vec![0.0f64; a.len()];
+        with_ctx(|c| ok(unsafe { aus_spectral_compute(c, what, a.as_ptr(), std::ptr::null(), a.len(), s0, 0.0, 44100, out.as_mut_ptr()) }));
+        out
+    }
+    pub fn compute_spectral_centroid(magnitude_spectrum: &Vec<f64>, rfft_freqs: &Vec<f64>, magnitude_spectrum_sum: f64) -> f64 {   // :79
+        compute(0, magnitude_spectrum, Some(rfft_freqs), magnitude_spectrum_sum, 0.0, 44100)
+    }
+    pub fn compute_spectral_entropy(spectrum_pmf: &Vec<f64>) -> f64 { compute(1, spectrum_pmf, None, 0.0, 0.0, 44100) }             // :93
+    pub fn compute_spectral_flatness(magnitude_spectrum: &Vec<f64>, magnitude_spectrum_sum: f64) -> f64 {                          // :107
+        compute(2, magnitude_spectrum, None, magnitude_spectrum_sum, 0.0, 44100)
+    }
+    pub fn compute_spectral_kurtosis(spectrum_pmf: &Vec<f64>, rfft_freqs: &Vec<f64>, spectral_centroid: f64, spectral_variance: f64) -> f64 {   // :122
+        compute(3, spectrum_pmf, Some(rfft_freqs), spectral_centroid, spectral_variance, 44100)
+    }
+    pub fn compute_spectral_roll_off_point(power_spectrum: &Vec<f64>, rfft_freqs: &Vec<f64>, power_spectrum_sum: f64, n: f64) -> f64 {          // :137
+        compute(4, power_spectrum, Some(rfft_freqs), power_spectrum_sum, n, 44100)
+    }
+    pub fn compute_spectral_skewness(spectrum_pmf: &Vec<f64>, rfft_freqs: &Vec<f64>, spectral_centroid: f64, spectral_variance: f64) -> f64 {   // :153
+        compute(5, spectrum_pmf, Some(rfft_freqs), spectral_centroid, spectral_variance, 44100)
+    }
+    pub fn compute_spectral_slope(power_spectrum: &Vec<f64>, power_spectrum_sum: f64) -> f64 {                                     // :167
+        compute(6, power_spectrum, None, power_spectrum_sum, 0.0, 44100)
+    }
+    pub fn compute_spectral_slope_region(power_spectrum: &Vec<f64>, rfft_freqs: &Vec<f64>, f_lower: f64, f_upper: f64, sample_rate: u32) -> f64 {  // :190
+        compute(7, power_spectrum, Some(rfft_freqs), f_lower, f_upper, sample_rate)
+    }
+    pub fn compute_spectral_variance(spectrum_pmf: &Vec<f64>, rfft_freqs: &Vec<f64>, spectral_centroid: f64) -> f64 {               // :238
+        compute(8, spectrum_pmf, Some(rfft_freqs), spectral_centroid, 0.0, 44100)
+    }
+    pub fn dot_product(vec1: &[f64], vec2: &[f64]) -> f64 { compute(9, vec1, Some(vec2), 0.0, 0.0, 44100) }                        // :253
+    pub fn make_power_spectrum(magnitude_spectrum: &Vec<f64>) -> Vec<f64> { compute_vec(10, magnitude_spectrum, 0.0) }              // :273
+    pub fn make_spectrum_pmf(power_spectrum: &Vec<f64>, power_spectrum_sum: f64) -> Vec<f64> {                                      // :284
+        compute_vec(11, power_spectrum, power_spectrum_sum)
     }
 
     // The single-feature wrappers (spectral_analysis_tools.rs:306-471) keep the reference's full parameter space -- rows of

@@ -56,6 +56,11 @@ def polar_to_complex_rstft(magnitude_spectrogram, phase_spectrogram) -> np.ndarr
     return default_context().polar_to_complex(m, p)
 
 
+def overlap_add(audio_chunks, fft_size: int, hop_size: int) -> np.ndarray:
+    """fft_tools.rs:69 -- chunk h added at offset h * hop_size, ascending chunk order per sample."""
+    return default_context().overlap_add(audio_chunks, fft_size, hop_size)
+
+
 def rfftfreq(fft_size: int, sample_rate: int) -> np.ndarray:
     """fft_tools.rs:199."""
     out = np.empty(fft_size // 2 + 1, dtype=np.float64)

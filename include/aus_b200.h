@@ -195,9 +195,10 @@ int aus_analyzer_batch_dev(aus_ctx *ctx, const void *d_magnitudes, size_t n_fram
 /* analysis::spectral_centroid / _variance / _skewness / _kurtosis / _entropy / _flatness / _slope / _roll_off_point /
  * _slope_region (analysis/spectral_analysis_tools.rs:306-471) with the reference's full parameter space: rows of ANY
  * length n_bins, the caller's own rfft_freqs table (need not be uniform), any roll-off fractions and any slope bands
- * (band i = [band_lo[i], band_hi[i]] Hz at sample_rate).  One device thread per row walks the bins in the reference's
- * summation order, so roll-off decisions are those of the reference's own `cum += p[i] / P` arithmetic.  This is the
- * generic fallback of the single-feature wrappers, not the hot path (aus_analyzer_batch is).
+ * (band i = [band_lo[i], band_hi[i]] Hz at sample_rate).  One warp per row (coalesced lane-strided passes, fixed-order
+ * tree sums); a roll-off threshold within rounding distance of a running sum is decided by the reference's own sequential
+ * `cum += p[i] / P` arithmetic, so exact ties give the reference's index.  The single-feature wrappers' path, not the
+ * hot path (aus_analyzer_batch is).
  * out: n_rows x (7 + n_roll + n_bands) = centroid, variance, skewness, kurtosis, entropy, flatness, slope, roll-offs, band
  * slopes.  A band whose upper edge reaches the last bin (the reference indexes out of bounds) gives AUS_ERR_INVALID. */
 int aus_spectral_features_generic(aus_ctx *ctx, const double *magnitudes, size_t n_rows, size_t n_bins,
@@ -205,7 +206,35 @@ int aus_spectral_features_generic(aus_ctx *ctx, const double *magnitudes, size_t
                                   const double *band_lo, const double *band_hi, size_t n_bands, uint32_t sample_rate,
                                   double *out);
 
+/* The public building blocks of analysis/spectral_analysis_tools.rs:79-290, which take the CALLER'S intermediates (sums,
+ * pmf, centroid, variance) instead of deriving them -- a drop-in must honour whatever the caller passes.  One call = one
+ * vector of n elements; a, b and the two scalars mean, per `what`:
+ *   CENTROID      a = magnitudes, b = rfft_freqs, s0 = magnitude sum                      (:79-85)
+ *   ENTROPY       a = pmf                                                                  (:93-99)
+ *   FLATNESS      a = magnitudes, s0 = magnitude sum                                       (:107-114)
+ *   KURTOSIS      a = pmf, b = rfft_freqs, s0 = centroid, s1 = variance                    (:122-129)
+ *   ROLL_OFF      a = power spectrum, b = rfft_freqs, s0 = power sum, s1 = n (fraction)    (:137-145)
+ *   SKEWNESS      a = pmf, b = rfft_freqs, s0 = centroid, s1 = variance                    (:153-160)
+ *   SLOPE         a = power spectrum, s0 = power sum                                       (:167-182)
+ *   SLOPE_REGION  a = power spectrum, b = rfft_freqs, s0 = f_lower, s1 = f_upper, sample_rate   (:190-230)
+ *   VARIANCE      a = pmf, b = rfft_freqs, s0 = centroid                                   (:238-244)
+ *   DOT_PRODUCT   a, b                                                                     (:253-259)
+ *   POWER_SPECTRUM  a = magnitudes -> out[n]                                               (:273-279)
+ *   SPECTRUM_PMF    a = power spectrum, s0 = power sum -> out[n]                           (:284-290)
+ * out: one double (the last two kinds: n doubles).  b may be NULL where unused. */
+typedef enum aus_compute_kind {
+    AUS_COMPUTE_CENTROID = 0, AUS_COMPUTE_ENTROPY = 1, AUS_COMPUTE_FLATNESS = 2, AUS_COMPUTE_KURTOSIS = 3,
+    AUS_COMPUTE_ROLL_OFF = 4, AUS_COMPUTE_SKEWNESS = 5, AUS_COMPUTE_SLOPE = 6, AUS_COMPUTE_SLOPE_REGION = 7,
+    AUS_COMPUTE_VARIANCE = 8, AUS_COMPUTE_DOT_PRODUCT = 9, AUS_COMPUTE_POWER_SPECTRUM = 10, AUS_COMPUTE_SPECTRUM_PMF = 11
+} aus_compute_kind;
+int aus_spectral_compute(aus_ctx *ctx, int what, const double *a, const double *b, size_t n, double s0, double s1,
+                         uint32_t sample_rate, double *out);
+
 /* ---- inverse (kernels K4/K5) ------------------------------------------------------------------------- */
+/* spectrum/fft_tools.rs:69 `overlap_add`: n_chunks rows of fft_size samples, row h added at offset h * hop, every output
+ * sample summing its covering rows in ascending row order -> fft_size + hop (n_chunks - 1) samples.  f64. */
+int aus_overlap_add(aus_ctx *ctx, const double *chunks, size_t n_chunks, size_t fft_size, size_t hop, double *audio);
+int aus_overlap_add_dev(aus_ctx *ctx, const void *d_chunks, size_t n_chunks, size_t fft_size, size_t hop, void *d_audio);
 /* spectrum/fft.rs:204 `irstft`: Hermitian extend, un-normalised inverse, window, overlap-add, window-norm divide,
  * peak-normalise to -6 dBFS.  frame_len must be fft_size/2+1, else AUS_ERR_SIZE with the reference's message.
  * normalize == 0 skips the peak normalisation (new knob; the reference always normalises -> pass 1). */

@@ -69,14 +69,27 @@ def test_mirror_has_the_reference_api(aus):
                        "complex_to_polar_rfft": ["spectrum"], "complex_to_polar_rstft": ["spectrogram"],
                        "polar_to_complex_rfft": ["magnitude_spectrum", "phase_spectrum"],
                        "polar_to_complex_rstft": ["magnitude_spectrogram", "phase_spectrogram"],
-                       "rfftfreq": ["fft_size", "sample_rate"]},
+                       "rfftfreq": ["fft_size", "sample_rate"],
+                       "overlap_add": ["audio_chunks", "fft_size", "hop_size"]},
         aus.analysis: {"analyzer": ["magnitude_spectrum", "fft_size", "sample_rate"],
                        "spectral_centroid": ["magnitude_spectrum", "rfft_freqs"], "spectral_entropy": ["magnitude_spectrum"],
                        "spectral_flatness": ["magnitude_spectrum"], "spectral_kurtosis": ["magnitude_spectrum", "rfft_freqs"],
                        "spectral_roll_off_point": ["magnitude_spectrum", "rfft_freqs", "n"],
                        "spectral_skewness": ["magnitude_spectrum", "rfft_freqs"], "spectral_slope": ["magnitude_spectrum"],
                        "spectral_slope_region": ["magnitude_spectrum", "rfft_freqs", "f_lower", "f_upper", "sample_rate"],
-                       "spectral_variance": ["magnitude_spectrum", "rfft_freqs"], "make_power_spectrum": ["magnitude_spectrum"]},
+                       "spectral_variance": ["magnitude_spectrum", "rfft_freqs"], "make_power_spectrum": ["magnitude_spectrum"],
+                       # the public building blocks (spectral_analysis_tools.rs:79-290), argument names as upstream
+                       "make_spectrum_pmf": ["power_spectrum", "power_spectrum_sum"], "dot_product": ["vec1", "vec2"],
+                       "compute_spectral_centroid": ["magnitude_spectrum", "rfft_freqs", "magnitude_spectrum_sum"],
+                       "compute_spectral_entropy": ["spectrum_pmf"],
+                       "compute_spectral_flatness": ["magnitude_spectrum", "magnitude_spectrum_sum"],
+                       "compute_spectral_kurtosis": ["spectrum_pmf", "rfft_freqs", "spectral_centroid", "spectral_variance"],
+                       "compute_spectral_roll_off_point": ["power_spectrum", "rfft_freqs", "power_spectrum_sum", "n"],
+                       "compute_spectral_skewness": ["spectrum_pmf", "rfft_freqs", "spectral_centroid", "spectral_variance"],
+                       "compute_spectral_slope": ["power_spectrum", "power_spectrum_sum"],
+                       "compute_spectral_slope_region": ["power_spectrum", "rfft_freqs", "f_lower", "f_upper", "sample_rate"],
+                       "compute_spectral_variance": ["spectrum_pmf", "rfft_freqs", "spectral_centroid"],
+                       "autocorrelation": ["audio", "fft_size"]},
         aus.mp: {"stft_analysis": ["audio", "fft_size", "sample_rate", "max_num_threads"]},
     }
     for mod, fns in want.items():

@@ -166,3 +166,25 @@ def test_any_size_multi_device_entry_points(aus, orc):
             assert o.shape == ref.shape and np.max(np.abs(o - ref)) <= RTOL64 * np.max(np.abs(ref))
     finally:
         aus.multi_shutdown()
+
+
+def test_any_size_chunked_host_pipeline_pcm_and_f32_inverse(ctx, aus, orc):
+    """The chunked copy/compute pipeline (virtual files with a recomputed halo), the PCM entry and the f32 inverse all reach
+    the chirp-z path through the same funnels as the native sizes."""
+    N, hop = 1000, 250
+    x = orc.synth_signal(70000, SR, seed=61)
+    ref = orc.stft_features(x, N, hop, orc.HANNING, SR)
+    try:
+        ctx.set_chunk_samples(9000)                               # eight chunks
+        got = ctx.stft_features(x, N, hop, orc.HANNING, SR)
+    finally:
+        ctx.set_chunk_samples(32 << 20)
+    assert_features(got, ref, RTOL64, "chunked N=1000")
+    pcm = np.round(x * 20000).astype(np.int16)
+    xf = orc.pcm_to_f64(pcm, 16)
+    got_p, _ = ctx.stft_features_batch_pcm(pcm, [0], [pcm.size], N, hop, orc.HANNING, SR)
+    assert_features(got_p, orc.stft_features(xf, N, hop, orc.HANNING, SR), RTOL64, "pcm N=1000")
+    S = orc.rstft(x, N, hop, orc.HAMMING)
+    ref_i = orc.irstft(S, N, hop, orc.HAMMING)
+    got_i = ctx.irstft(S, N, hop, orc.HAMMING, precision="f32")
+    assert np.max(np.abs(got_i - ref_i)) <= 1e-4 * np.max(np.abs(ref_i))
