@@ -13,7 +13,8 @@
 //! crate's public functions return, flattened:
 //!   rstft (spectrum/fft.rs:119), irstft (:204), complex_to_polar_rstft + analyzer per frame (fft_tools.rs:41,
 //!   analysis/analyzer.rs:41 -- the loop of analyzer.rs:99-104), mp::stft_analysis (mp.rs:26), generate_window
-//!   (window.rs:110), rfftfreq (fft_tools.rs:199), autocorrelation, dc_bias / dbfs_max / energy / zero_crossing_rate.
+//!   (window.rs:110), rfftfreq (fft_tools.rs:199), autocorrelation, dc_bias / dbfs_max / energy / zero_crossing_rate, a fft_size
+//!   that is not a power of two (1000), overlap_add (fft_tools.rs:69) and the compute_* building blocks (s_a_t.rs:79-290).
 //!
 //! File format (little endian), both files: b"AUSFIX01", u64 n_arrays, then per array: u64 name_len, name (utf-8),
 //! u64 ndim, ndim x u64 dims, prod(dims) x f64.
@@ -24,7 +25,10 @@ use std::fs::File;
 use std::io::{Read, Write};
 
 use aus::analysis::{analyzer, autocorrelation, dbfs_max, dc_bias, energy, zero_crossing_rate, Analysis};
-use aus::spectrum::{complex_to_polar_rstft, irstft, rfftfreq, rstft};
+use aus::analysis::{compute_spectral_centroid, compute_spectral_entropy, compute_spectral_flatness, compute_spectral_kurtosis,
+                    compute_spectral_roll_off_point, compute_spectral_skewness, compute_spectral_slope,
+                    compute_spectral_slope_region, compute_spectral_variance, make_power_spectrum, make_spectrum_pmf};
+use aus::spectrum::{complex_to_polar_rstft, irstft, overlap_add, rfftfreq, rstft};
 use aus::{generate_window, WindowType};
 
 type Arrays = BTreeMap<String, (Vec<u64>, Vec<f64>)>;
@@ -193,6 +197,37 @@ fn main() {
     out.insert("acorr_2048".into(), (vec![ac.len() as u64], ac));
     out.insert("time_scalars".into(),
                (vec![4], vec![dc_bias(&x), dbfs_max(&x), energy(&x), zero_crossing_rate(&x, sr)]));
+
+    // a fft_size that is not a power of two (rustfft plans any length): fft 1000 / hop 250 on the first 20 000 samples of c1_x
+    let x = get("c1_x");
+    let short: Vec<f64> = x[..20000].to_vec();
+    out.insert("np2_feat".into(), stft_features(&short, 1000, 250, WindowType::Hanning, sr));
+    let spec = rstft(&short, 1000, 250, WindowType::Hamming);
+    out.insert("np2_spec".into(), flatten_spec(&spec));
+    let audio = irstft(&spec, 1000, 250, WindowType::Hamming).expect("irstft 1000");
+    out.insert("np2_audio".into(), (vec![audio.len() as u64], audio));
+
+    // overlap_add (fft_tools.rs:69) on the first 9 x 16 samples of c1_x, hop 4
+    let chunks: Vec<Vec<f64>> = (0..9).map(|h| x[h * 16..(h + 1) * 16].to_vec()).collect();
+    let ola = overlap_add(&chunks, 16, 4);
+    out.insert("ola_9x16_4".into(), (vec![ola.len() as u64], ola));
+
+    // the compute_* building blocks (spectral_analysis_tools.rs:79-290) on the first row of an_mag, chained like analyzer.rs:42-62
+    let (dims, m) = inp.get("an_mag").unwrap().clone();
+    let k = dims[1] as usize;
+    let row: Vec<f64> = m[..k].to_vec();
+    let freqs = rfftfreq(2048, sr);
+    let p = make_power_spectrum(&row);
+    let m_sum: f64 = row.iter().sum();
+    let p_sum: f64 = p.iter().sum();
+    let pmf = make_spectrum_pmf(&p, p_sum);
+    let c = compute_spectral_centroid(&row, &freqs, m_sum);
+    let var = compute_spectral_variance(&pmf, &freqs, c);
+    let vals = vec![c, var, compute_spectral_skewness(&pmf, &freqs, c, var), compute_spectral_kurtosis(&pmf, &freqs, c, var),
+                    compute_spectral_entropy(&pmf), compute_spectral_flatness(&row, m_sum),
+                    compute_spectral_roll_off_point(&p, &freqs, p_sum, 0.85), compute_spectral_slope(&p, p_sum),
+                    compute_spectral_slope_region(&p, &freqs, 105.0, 852.0, sr)];
+    out.insert("compute_row0".into(), (vec![vals.len() as u64], vals));
 
     write_arrays(&args[2], &out);
     println!("wrote {} arrays to {}", out.len(), args[2]);
