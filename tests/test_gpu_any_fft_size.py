@@ -188,3 +188,24 @@ def test_any_size_chunked_host_pipeline_pcm_and_f32_inverse(ctx, aus, orc):
     ref_i = orc.irstft(S, N, hop, orc.HAMMING)
     got_i = ctx.irstft(S, N, hop, orc.HAMMING, precision="f32")
     assert np.max(np.abs(got_i - ref_i)) <= 1e-4 * np.max(np.abs(ref_i))
+
+
+def test_any_size_randomised_sweep(ctx, orc):
+    """Seeded sweep over arbitrary sizes, hops, windows and lengths: spectra against the oracle, frame count included."""
+    rng = np.random.default_rng(2026)
+    for case in range(40):
+        N = int(rng.integers(2, 3001))
+        if N >= 64 and (N & (N - 1)) == 0:
+            N += 1                                               # keep it off the native path
+        hop = int(rng.integers(1, N + 1))
+        window = int(rng.integers(0, 5))
+        n = int(rng.integers(0, 12 * N))
+        x = orc.synth_signal(n, SR, seed=100 + case, file_id=case)
+        ref = orc.rstft(x, N, hop, window)
+        if ref.shape[0] > 4000:                                  # hop = 1 on a long signal: keep the case small
+            x = x[:N + 300 * hop]
+            ref = orc.rstft(x, N, hop, window)
+        got = ctx.rstft(x, N, hop, window)
+        assert got.shape == ref.shape, (N, hop, window, n)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (N, hop, window, n)
+        assert_spectra(np.nan_to_num(got), np.nan_to_num(ref), RTOL64, f"N={N} hop={hop} w={window} n={n}")
