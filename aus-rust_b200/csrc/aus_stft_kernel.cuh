@@ -127,6 +127,54 @@ static __device__ __noinline__ double window_value(int wtype, double i, double L
     }
 }
 
+// The short last frame of a file (fft.rs:148-159): L < fft_size samples times the window of length L (half-scaled like
+// win2), zero-padded.  Kept out of line so that the hot loop's register allocation does not see it; the loop is inside, so
+// the call overhead (a spill of the caller's live registers) is paid once per frame, and eight samples per trip keep eight
+// independent cos() chains in flight (one warp works alone here: a dependent FP64 operation is ~25 cycles away).
+template <int W> __device__ __forceinline__ double short_window(double id, double Ld) {     // window.rs:26-98, its operation order
+    const double PI = 3.14159265358979323846264338327950288;
+    if constexpr (W == 0) return (2.0 / (Ld - 1.0)) * ((Ld - 1.0) / 2.0 - fabs(id - (Ld - 1.0) / 2.0));
+    else if constexpr (W == 1) return 0.42 - 0.5 * cos((2.0 * PI * id) / Ld) + 0.08 * cos((4.0 * PI * id) / Ld);
+    else if constexpr (W == 2) return 0.5 - 0.5 * cos((2.0 * PI * id) / (Ld - 1.0));
+    else if constexpr (W == 3) return 0.54 - 0.46 * cos((2.0 * PI * id) / (Ld - 1.0));
+    else return 1.0;
+}
+constexpr int SSF_W = 8;       // samples per trip = independent cos() chains in flight
+template <typename T, int W> __device__ __forceinline__ void stage_short_frame_w(T *bufr, const T *src, int L, int N, int t, int tpf) {
+    const double Ld = (double)L;
+    for (int i0 = t; i0 < N; i0 += SSF_W * tpf) {
+        if (i0 >= L) {                                                 // the zero padding (i0 is the trip's smallest index)
+#pragma unroll
+            for (int c = 0; c < SSF_W; ++c)
+                if (i0 + c * tpf < N) bufr[i0 + c * tpf] = (T)0;
+            continue;
+        }
+        double w[SSF_W];
+        T x[SSF_W];
+#pragma unroll
+        for (int c = 0; c < SSF_W; ++c) {
+            const int i = i0 + c * tpf;
+            x[c] = i < L ? src[i] : (T)0;
+            w[c] = short_window<W>((double)(i < L ? i : 0), Ld);
+        }
+#pragma unroll
+        for (int c = 0; c < SSF_W; ++c) {
+            const int i = i0 + c * tpf;
+            if (i < N) bufr[i] = i < L ? (T)((double)x[c] * (0.5 * w[c])) : (T)0;
+        }
+    }
+}
+template <typename T>
+static __device__ __noinline__ void stage_short_frame(T *bufr, const T *src, int L, int N, int wtype, int t, int tpf) {
+    switch (wtype) {
+    case 0: stage_short_frame_w<T, 0>(bufr, src, L, N, t, tpf); break;
+    case 1: stage_short_frame_w<T, 1>(bufr, src, L, N, t, tpf); break;
+    case 2: stage_short_frame_w<T, 2>(bufr, src, L, N, t, tpf); break;
+    case 3: stage_short_frame_w<T, 3>(bufr, src, L, N, t, tpf); break;
+    default: stage_short_frame_w<T, 4>(bufr, src, L, N, t, tpf); break;
+    }
+}
+
 template <int SHIFT> __device__ __forceinline__ int padi(int i) { return i + (i >> SHIFT); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -357,7 +405,7 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     // per bin) plus the finiteness of the totals decides it for the whole frame: a zero / subnormal / non-finite power
     // bin sends the frame through the exact library functions, which also reproduce the reference's NaN / -inf rules.
     // (f32 uses sqrtf / log2f throughout, which handle every argument; K3 gets its magnitudes from the caller.)
-    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt &&
+    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt && active &&   // (a group past the end of the batch skips the cold paths)
                        (!power_is_normal<T>(acc.pmin) || !(acc.lo_sum + acc.hi_sum + acc.mid < (T)INFINITY));
     if (group_any<TPF, C::BLOCK>(bad_p, scratch, t, grp)) {
         acc.s_m = 0;
@@ -404,8 +452,8 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     T d2s = 0, d3s = 0, d4s = 0, ent = 0, slq = 0;
     // q = p / P of the smallest bin must itself be a positive normal number (P finite and > 0 implied)
     const unsigned gpmin = group_min_u32<TPF, C::BLOCK>(acc.pmin, scratch, t, grp);
-    const bool badq = sizeof(T) == 8 && (!power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) ||
-                                         abnormal((T)(power_from_hi<T>(gpmin) * inv_p)));
+    const bool badq = sizeof(T) == 8 && active && (!power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) ||
+                                                   abnormal((T)(power_from_hi<T>(gpmin) * inv_p)));
     // four bins at a time: all shared-memory loads first, then four independent sqrt-free math chains, so the
     // load-to-use latency is paid once per block.  s0 = slot of the first bin, the 4th bin sits at s0 + 3 + skip.
     T *const bufT = reinterpret_cast<T *>(buf);
@@ -502,7 +550,9 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
                 const double tol = 1e-12 * P;
                 const bool amb = (lo <= M && fabs((double)cum_of<T, M, TPF>(buf, lo) - (double)th) <= tol) ||
                                  (lo >= 1 && fabs((double)th - (double)cum_of<T, M, TPF>(buf, lo - 1)) <= tol);
-                if (amb) {
+                if (amb && !(P > 0.0)) {                   // silent (or NaN) frame: the reference's loop stops at bin 0
+                    lo = 0;
+                } else if (amb) {
                     const double theta = qq == 0 ? 0.5 : qq == 1 ? 0.75 : qq == 2 ? 0.9 : 0.95;
                     double pseq = 0.0;                     // power_spectrum.iter().sum(): sequential (analyzer.rs:44)
                     for (int i = 0; i < K; ++i) pseq += (double)pow_of<T, M, TPF>(buf, i);
@@ -528,6 +578,9 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     }
 }
 
+#ifndef AUS_STAGGER_NS
+#define AUS_STAGGER_NS 0         // experiment: start frame group g of a CTA g * AUS_STAGGER_NS later (short launches run in lockstep)
+#endif
 #ifndef AUS_PSUM_ENTROPY
 #define AUS_PSUM_ENTROPY 0       // experiment: entropy / flatness sums over p instead of q = p / P (one multiply per bin less)
 #endif
@@ -735,7 +788,9 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
         const double tol = 1e-12 * P;
         if (!amb && res < K) amb = fabs(c_at - my_th) <= tol || (res >= 1 && fabs(my_th - c_prev) <= tol);
         if (!amb && res == K) amb = fabs(my_th - c_prev) <= tol;
-        if (amb) {
+        if (amb && !(P > 0.0)) {                                         // silent (or NaN) frame: the reference's loop stops at bin 0
+            res = 0;
+        } else if (amb) {
             const double theta = wq == 0 ? 0.5 : wq == 1 ? 0.75 : wq == 2 ? 0.9 : 0.95;
             double pseq = 0.0;                                           // power_spectrum.iter().sum(), analyzer.rs:44
             for (int i = 0; i < K; ++i) pseq += pow_of<T, M, TPF>(buf, i);
@@ -1039,6 +1094,12 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
     fence_mbar_init();
     __syncthreads();
     uint32_t parity = 0;
+#if AUS_STAGGER_NS
+    // All frame groups of an SM start in the same phase (bulk-copy wait, then loads, then butterflies ...) and, on a short
+    // job, stay in lockstep: every pipe is hit by all of them at once and idles in between (a 3-round launch runs at half
+    // the steady-state rate per round).  Spreading the starts over about one frame time breaks the lockstep.
+    if (FEAT && sizeof(T) == 8 && TPF == 32) __nanosleep((unsigned)grp * AUS_STAGGER_NS);
+#endif
 
     const unsigned long long stride = (unsigned long long)gridDim.x * FPB;
     const unsigned long long iters = (p.total_frames + stride - 1) / stride;
@@ -1071,6 +1132,13 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
         const T *src;
         int L;
         const bool active = locate(g, f, src, L);
+        // A group made of whole warps that has run out of frames is done (frames only move forward, and nobody waits for it:
+        // its barriers are its own).  Without this the last, partly filled round pushes all-zero frames through the cold
+        // silent-frame paths -- on a one-file call that doubled the launch time.  Groups that share a warp keep going (their
+        // shuffles and __syncwarp are warp-wide) and skip only the cold paths.
+        if constexpr (TPF >= 32) {
+            if (!active) break;
+        }
 #if AUS_L2_PREFETCH
         if (active && t == 0 && g + stride < p.file_first[f + 1]) {     // same file: its next frame of this group, if full
             const unsigned long long s2 = (g + stride - p.file_first[f]) * (unsigned long long)p.hop;
@@ -1093,14 +1161,11 @@ __global__ void __maxnreg__((Cfg<T, LOG2N, RR>::MAXREG)) stft_kernel(const StftP
             }
         } else if (!direct) {
             T *bufr = reinterpret_cast<T *>(buf);
+            if (prewindowed) {                                          // one call per frame, not one per sample (cold)
+                stage_short_frame<T>(bufr, src, L, N, p.wtype, t, TPF);
+            } else {
 #pragma unroll 1
-            for (int i = t; i < N; i += TPF) {
-                T x = (T)0;
-                if (i < L) {
-                    x = src[i];
-                    if (prewindowed) x = (T)((double)x * (0.5 * window_value(p.wtype, (double)i, (double)L)));
-                }
-                bufr[i] = x;
+                for (int i = t; i < N; i += TPF) bufr[i] = i < L ? src[i] : (T)0;
             }
         }
         // the window values this thread multiplies in pass 1 do not depend on the frame: fetch them (L1 / L2) while the bulk

@@ -215,7 +215,7 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
     group_sync<TPF, C::BLOCK>(grp);                     // every power bin visible to the whole group
 
     // zero / subnormal / non-finite power somewhere: magnitudes again with the exact square root (cold)
-    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt && (!power_is_normal<T>(pmin) || !(p_part < (T)INFINITY));
+    const bool bad_p = sizeof(T) == 8 && mags_from_sqrt && active && (!power_is_normal<T>(pmin) || !(p_part < (T)INFINITY));
     if (group_any<TPF, C::BLOCK>(bad_p, scratch, t, grp)) {
         s_m = 0;
         s_mk = 0;
@@ -248,7 +248,7 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
     bool badq = false;                                   // (f32 uses lg2.approx, which handles every argument)
     if constexpr (sizeof(T) == 8) {
         const unsigned gpmin = group_min_u32<TPF, C::BLOCK>(pmin, scratch, t, grp);
-        badq = !power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) || abnormal((T)(power_from_hi<T>(gpmin) * inv_p));
+        badq = active && (!power_is_normal<T>(gpmin) || !(P > 0.0 && P < (double)INFINITY) || abnormal((T)(power_from_hi<T>(gpmin) * inv_p)));
     }
     const double2 *const ltab = logtab + (C::LOGREP > 1 ? (threadIdx.x & 7) : 0);
     T cum = 0;
@@ -339,7 +339,9 @@ __device__ __forceinline__ void frame_features_r(T *pw, T *cw, T s_m, T s_mk, T 
             if (!amb && res < K)
                 amb = fabs((double)c_at - (double)th) <= tol || (res >= 1 && fabs((double)th - (double)c_prev) <= tol);
             if (!amb && res == K) amb = fabs((double)th - (double)c_prev) <= tol;
-            if (amb) {
+            if (amb && !(P > 0.0)) {                       // silent (or NaN) frame: the reference's loop stops at bin 0
+                res = 0;
+            } else if (amb) {
                 const double theta = theta_of(qq);
                 double pseq = 0.0;                         // power_spectrum.iter().sum(): sequential (analyzer.rs:44)
                 for (int i = 0; i < K; ++i) pseq += (double)pw[pslot<M>(i)];
@@ -687,7 +689,9 @@ __device__ __forceinline__ void frame_features_r32(T *pw, T s_m, T s_mk, T s_pk,
             const double tol = 1e-12 * P;
             if (!amb && res < K) amb = fabs((double)c_at - (double)my_th) <= tol || (res >= 1 && fabs((double)my_th - (double)c_prev) <= tol);
             if (!amb && res == K) amb = fabs((double)my_th - (double)c_prev) <= tol;
-            if (amb) {
+            if (amb && !(P > 0.0)) {                                     // silent (or NaN) frame: the reference's loop stops at bin 0
+                res = 0;
+            } else if (amb) {
                 const double theta = wq == 0 ? 0.5 : wq == 1 ? 0.75 : wq == 2 ? 0.9 : 0.95;
                 double pseq = 0.0;                                       // power_spectrum.iter().sum(), analyzer.rs:44
                 for (int i = 0; i < K; ++i) pseq += (double)pw[pslot<M>(i)];
@@ -888,6 +892,9 @@ __global__ void __maxnreg__((CfgA<T, LOG2N>::MAXREG)) analyzer_kernel(const Stft
     for (unsigned long long it = 0; it < iters; ++it) {
         const unsigned long long g = it * stride + (unsigned long long)blockIdx.x * FPB + grp;
         const bool active = g < p.total_frames;
+        if constexpr (TPF >= 32) {
+            if (!active) break;                            // whole-warp groups past the last row are done (see stft_kernel)
+        }
         const T *row = p.mags + (active ? g : 0ull) * (unsigned long long)K;
 #if AUS_L2_PREFETCH
         if (t == 0 && g + stride + 1 < p.total_frames) {   // this group's next row -> L2 (16-byte aligned superset; the row after
