@@ -578,6 +578,9 @@ __device__ __forceinline__ void frame_features(Cx<T> *buf, FeatAcc<T> &acc, doub
     }
 }
 
+#ifndef AUS_COLD_OUTLINE
+#define AUS_COLD_OUTLINE 0       // experiment: frame_features32() with its silent-frame and knife-edge fallbacks out of line
+#endif
 #ifndef AUS_STAGGER_NS
 #define AUS_STAGGER_NS 0         // experiment: start frame group g of a CTA g * AUS_STAGGER_NS later (short launches run in lockstep)
 #endif
@@ -628,6 +631,50 @@ template <int NV> __device__ __forceinline__ double warp_reduce_scatter(const do
     return v1;
 }
 
+// Cold paths of frame_features32(), out of line so that the hot function's code and register allocation do not carry them:
+// silent / subnormal / non-finite frames (exact sqrt and log2, the reference's NaN / -inf rules) and the knife-edge roll-off
+// threshold (the reference's own sequential arithmetic, s_a_t.rs:137-145).
+template <int M, int TPF>
+static __device__ __noinline__ double2 cold_exact_magnitudes(Cx<double> *buf, int t) {
+    double a = 0.0, b2 = 0.0;
+#pragma unroll 1
+    for (int u = 0; u < 33; ++u) {
+        if (u == 32 && t != TPF - 1) break;
+        const int b = u < 16 ? 16 * t + u : (u < 32 ? M - 16 * t - 15 + (u - 16) : M / 2);
+        const double m = sqrt(pow_of<double, M, TPF>(buf, b));
+        a += m;
+        b2 += m * (double)b;
+    }
+    return double2{a, b2};
+}
+template <int M, int TPF>
+static __device__ __noinline__ double2 cold_exact_log_sums(Cx<double> *buf, int t, double inv_p) {
+    double e = 0.0, l2 = 0.0;                            // library log2: 0 * -inf = NaN, sum = -inf, like the reference
+#pragma unroll 1
+    for (int u = 0; u < 33; ++u) {
+        if (u == 32 && t != TPF - 1) break;
+        const int b = u < 16 ? 16 * t + u : (u < 32 ? M - 16 * t - 15 + (u - 16) : M / 2);
+        const double q = pow_of<double, M, TPF>(buf, b) * inv_p;
+        const double l = log2(q);
+        e += q * l;
+        l2 += l;
+    }
+    return double2{e, l2};
+}
+template <int M, int TPF>
+static __device__ __noinline__ int cold_rolloff_sequential(Cx<double> *buf, double theta) {
+    constexpr int K = M + 1;
+    double pseq = 0.0;                                   // power_spectrum.iter().sum(), analyzer.rs:44
+    for (int i = 0; i < K; ++i) pseq += pow_of<double, M, TPF>(buf, i);
+    double csum = 0.0;
+    int i = -1;
+    while (csum < theta && i < K - 1) {
+        ++i;
+        csum += pow_of<double, M, TPF>(buf, i) / pseq;
+    }
+    return i;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // frame_features() for f64 frame groups of exactly one warp (fft_size 2048), rewritten around what the clock64() phase
 // timings of profiles/r2_k1_pc_experiment.md showed: a warp spends most of this half waiting on dependency chains (a
@@ -659,6 +706,13 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
     };
     // ---- zero / subnormal / non-finite power somewhere: magnitudes again with the exact square root (cold)
     const bool bad_p = !power_is_normal<T>(acc.pmin) || !(acc.lo_sum + acc.hi_sum + acc.mid < (T)INFINITY);
+#if AUS_COLD_OUTLINE
+    if (__any_sync(FULL, bad_p)) {
+        const double2 mm = cold_exact_magnitudes<M, TPF>(buf, t);
+        acc.s_m = mm.x;
+        acc.s_mk = mm.y;
+    }
+#else
     if (__any_sync(FULL, bad_p)) {
         acc.s_m = 0;
         acc.s_mk = 0;
@@ -671,6 +725,7 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
             acc.s_mk += m * (T)b;
         }
     }
+#endif
     __syncwarp();                                     // every power bin visible to the whole warp
 
     // ---- sub-band sums (s_a_t.rs:190-230), eight bins per trip: loads first, independent products, tree sums
@@ -792,6 +847,9 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
             res = 0;
         } else if (amb) {
             const double theta = wq == 0 ? 0.5 : wq == 1 ? 0.75 : wq == 2 ? 0.9 : 0.95;
+#if AUS_COLD_OUTLINE
+            res = cold_rolloff_sequential<M, TPF>(buf, theta);
+#else
             double pseq = 0.0;                                           // power_spectrum.iter().sum(), analyzer.rs:44
             for (int i = 0; i < K; ++i) pseq += pow_of<T, M, TPF>(buf, i);
             double csum = 0.0;
@@ -801,6 +859,7 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
                 csum += pow_of<T, M, TPF>(buf, i) / pseq;
             }
             res = i;
+#endif
         }
         roll_res = res;
     }
@@ -872,6 +931,13 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
         }
     }
     T e_sum = ent[0] + ent[1], l_sum = slq[0] + slq[1];
+#if AUS_COLD_OUTLINE
+    if (badq) {
+        const double2 el = cold_exact_log_sums<M, TPF>(buf, t, inv_p);
+        e_sum = el.x;
+        l_sum = el.y;
+    }
+#else
     if (badq) {                                          // warp-uniform, cold: library log2 (0 * -inf = NaN, sum = -inf)
         e_sum = 0;
         l_sum = 0;
@@ -885,6 +951,7 @@ __device__ __forceinline__ void frame_features32(Cx<double> *buf, FeatAcc<double
             l_sum += l;
         }
     }
+#endif
     // ---- nothing reads the group buffer any more: the next frame's bulk copy starts now and overlaps the reduction, the
     //      record stores and the set-up of the next iteration (its latency, ~1 000 cycles, used to be waited for in full)
     fence_proxy_async();
