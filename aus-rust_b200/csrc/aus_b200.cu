@@ -376,12 +376,15 @@ template <typename A, typename B> static int cast_dev(aus_ctx *c, const A *in, B
 // raw per-frame sums -> 14 features, one thread per frame
 template <typename T> static int launch_finalize(aus_ctx *c, const StftParams<T> &p, size_t N) {
     if (p.total_frames == 0) return AUS_OK;
-    const unsigned int grid = (unsigned int)((p.total_frames + 255) / 256);
+    // one thread per frame; a small batch is spread over more SMs (each thread runs a serial chain of FP64 divisions, exp,
+    // log2: with 256 of them per SM and few CTAs the tiny kernel takes microseconds that a one-file call notices)
+    const unsigned int block = p.total_frames <= 64ull * 148 * 8 ? 64u : 256u;
+    const unsigned int grid = (unsigned int)((p.total_frames + block - 1) / block);
     // programmatic dependent launch: the grid may be scheduled while the feature kernel drains (its threads wait in
     // griddepcontrol.wait until that kernel's writes are visible), which hides the launch gap of this tiny kernel
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(block);
     cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
