@@ -1611,14 +1611,16 @@ static int irstft_k4(aus_ctx *c, const Cx<T> *d_spec, unsigned long long total_r
     const unsigned long long groups = (unsigned long long)c->sm_count * (((sizeof(T) == 8 && tpf >= 16 && tpf <= 128) ? 384 : 256) / tpf) * (sizeof(T) == 4 ? 2 : 1);
     unsigned long long Ftot = 0;
     for (const IShard &x : sh) Ftot += x.b - x.a;
-    const unsigned long long seglen = std::max<unsigned long long>((Ftot + groups - 1) / groups, 4ull * (unsigned long long)(halo + 1));
+    // a shard gets its proportional share of the resident frame groups (rounded down, so one wave covers everything and
+    // no group idles for a rounding reason), as long as a segment stays >= 4 * (halo + 1) frames
+    const unsigned long long minlen = 4ull * (unsigned long long)(halo + 1);
     const size_t ns = sh.size();
     std::vector<unsigned long long> sfile, sa, sb, first(ns), frames(ns), row0(ns), samp0(ns), ooff(ns), olen(ns);
     for (size_t i = 0; i < ns; ++i) {
         const IShard &x = sh[i];
         first[i] = x.row_off; frames[i] = x.F; row0[i] = x.row0; samp0[i] = x.samp0(hop); ooff[i] = x.out_off; olen[i] = x.out_len(N, hop);
         const unsigned long long Fi = x.b - x.a;
-        const unsigned long long nseg = std::max<unsigned long long>(1, (Fi + seglen / 2) / seglen);
+        const unsigned long long nseg = std::max<unsigned long long>(1, std::min<unsigned long long>(Fi * groups / std::max<unsigned long long>(Ftot, 1), Fi / minlen));
         for (unsigned long long k = 0; k < nseg; ++k) {
             sfile.push_back(i);
             sa.push_back(x.a + Fi * k / nseg);
