@@ -297,29 +297,29 @@ pub mod analysis {
         out
     }
     pub fn compute_spectral_centroid(magnitude_spectrum: &Vec<f64>, rfft_freqs: &Vec<f64>, magnitude_spectrum_sum: f64) -> f64 {   // :79
-        compute(0, magnitude_spectrum, Some(rfft_freqs), magnitude_spectrum_sum, 0.0, 44100)
+        compute(0, magnitude_spectrum, Some(rfft_freqs.as_slice()), magnitude_spectrum_sum, 0.0, 44100)
     }
     pub fn compute_spectral_entropy(spectrum_pmf: &Vec<f64>) -> f64 { compute(1, spectrum_pmf, None, 0.0, 0.0, 44100) }             // :93
     pub fn compute_spectral_flatness(magnitude_spectrum: &Vec<f64>, magnitude_spectrum_sum: f64) -> f64 {                          // :107
         compute(2, magnitude_spectrum, None, magnitude_spectrum_sum, 0.0, 44100)
     }
     pub fn compute_spectral_kurtosis(spectrum_pmf: &Vec<f64>, rfft_freqs: &Vec<f64>, spectral_centroid: f64, spectral_variance: f64) -> f64 {   // :122
-        compute(3, spectrum_pmf, Some(rfft_freqs), spectral_centroid, spectral_variance, 44100)
+        compute(3, spectrum_pmf, Some(rfft_freqs.as_slice()), spectral_centroid, spectral_variance, 44100)
     }
     pub fn compute_spectral_roll_off_point(power_spectrum: &Vec<f64>, rfft_freqs: &Vec<f64>, power_spectrum_sum: f64, n: f64) -> f64 {          // :137
-        compute(4, power_spectrum, Some(rfft_freqs), power_spectrum_sum, n, 44100)
+        compute(4, power_spectrum, Some(rfft_freqs.as_slice()), power_spectrum_sum, n, 44100)
     }
     pub fn compute_spectral_skewness(spectrum_pmf: &Vec<f64>, rfft_freqs: &Vec<f64>, spectral_centroid: f64, spectral_variance: f64) -> f64 {   // :153
-        compute(5, spectrum_pmf, Some(rfft_freqs), spectral_centroid, spectral_variance, 44100)
+        compute(5, spectrum_pmf, Some(rfft_freqs.as_slice()), spectral_centroid, spectral_variance, 44100)
     }
     pub fn compute_spectral_slope(power_spectrum: &Vec<f64>, power_spectrum_sum: f64) -> f64 {                                     // :167
         compute(6, power_spectrum, None, power_spectrum_sum, 0.0, 44100)
     }
     pub fn compute_spectral_slope_region(power_spectrum: &Vec<f64>, rfft_freqs: &Vec<f64>, f_lower: f64, f_upper: f64, sample_rate: u32) -> f64 {  // :190
-        compute(7, power_spectrum, Some(rfft_freqs), f_lower, f_upper, sample_rate)
+        compute(7, power_spectrum, Some(rfft_freqs.as_slice()), f_lower, f_upper, sample_rate)
     }
     pub fn compute_spectral_variance(spectrum_pmf: &Vec<f64>, rfft_freqs: &Vec<f64>, spectral_centroid: f64) -> f64 {               // :238
-        compute(8, spectrum_pmf, Some(rfft_freqs), spectral_centroid, 0.0, 44100)
+        compute(8, spectrum_pmf, Some(rfft_freqs.as_slice()), spectral_centroid, 0.0, 44100)
     }
     pub fn dot_product(vec1: &[f64], vec2: &[f64]) -> f64 { compute(9, vec1, Some(vec2), 0.0, 0.0, 44100) }                        // :253
     pub fn make_power_spectrum(magnitude_spectrum: &Vec<f64>) -> Vec<f64> { compute_vec(10, magnitude_spectrum, 0.0) }              // :273

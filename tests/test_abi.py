@@ -192,3 +192,19 @@ def test_shard_plan_properties(aus, orc):
         assert row == starts[-1]
 
     run()
+
+
+def test_shard_plan_and_frame_count_for_a_non_power_of_two_size(aus, orc):
+    """fft sizes outside the native range are legal (chirp-z path): the pure-host helpers treat them like any other size."""
+    N, hop = 1000, 250
+    for n in (0, 1, 999, 1000, 1001, 1250, 1251, 123457):
+        assert aus.num_frames(n, N, hop) == orc.num_frames(n, N, hop)
+    vo, vl, vr, vd = aus.plan_shards([0], [123457], N, hop, 4)
+    F = orc.num_frames(123457, N, hop)
+    rows = 0
+    for o, l, r in zip(vo, vl, vr):
+        assert r == rows and o == r * hop                        # contiguous frame ranges, each starting on its first frame
+        rows += orc.num_frames(int(l), N, hop)
+    assert rows == F and sorted(set(vd)) == [0, 1, 2, 3]
+    with pytest.raises(aus.AusError):
+        aus.plan_shards([0], [50000], 10000, 2500, 2)            # not a power of two and above 8192: unsupported
