@@ -222,8 +222,7 @@ pub mod spectrum {
         magnitude_spectrogram.iter().zip(phase_spectrogram.iter()).map(|(m, p)| polar_to_complex_rfft(m, p)).collect()
     }
 
-    /// spectrum/fft_tools.rs:199
-    /// fft_tools.rs:69
+    /// spectrum/fft_tools.rs:69
     pub fn overlap_add(audio_chunks: &Vec<Vec<f64>>, fft_size: usize, hop_size: usize) -> Vec<f64> {
         if audio_chunks.is_empty() { return Vec::new(); }
         let mut flat: Vec<f64> = Vec::with_capacity(audio_chunks.len() * fft_size);
@@ -233,6 +232,7 @@ pub mod spectrum {
         out
     }
 
+    /// spectrum/fft_tools.rs:199
     pub fn rfftfreq(fft_size: usize, sample_rate: u32) -> Vec<f64> {
         let mut f = vec![0.0; fft_size / 2 + 1];
         ok(unsafe { aus_rfftfreq(fft_size, sample_rate, f.as_mut_ptr()) });
