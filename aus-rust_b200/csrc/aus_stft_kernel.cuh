@@ -131,12 +131,14 @@ static __device__ __noinline__ double window_value(int wtype, double i, double L
 // win2), zero-padded.  Kept out of line so that the hot loop's register allocation does not see it; the loop is inside, so
 // the call overhead (a spill of the caller's live registers) is paid once per frame, and eight samples per trip keep eight
 // independent cos() chains in flight (one warp works alone here: a dependent FP64 operation is ~25 cycles away).
-template <int W> __device__ __forceinline__ double short_window(double id, double Ld) {     // window.rs:26-98, its operation order
-    const double PI = 3.14159265358979323846264338327950288;
+// window.rs:26-98.  cos(2 pi i / D) is evaluated as cospi(2 i / D): the same value to the last ulp or two (neither device
+// function is the reference's libm anyway), but straight-line code -- cos() carries a branch to its large-argument path, which
+// keeps the compiler from interleaving the eight evaluations of a trip (measured: 460 cycles per sample instead of ~80).
+template <int W> __device__ __forceinline__ double short_window(double id, double Ld) {
     if constexpr (W == 0) return (2.0 / (Ld - 1.0)) * ((Ld - 1.0) / 2.0 - fabs(id - (Ld - 1.0) / 2.0));
-    else if constexpr (W == 1) return 0.42 - 0.5 * cos((2.0 * PI * id) / Ld) + 0.08 * cos((4.0 * PI * id) / Ld);
-    else if constexpr (W == 2) return 0.5 - 0.5 * cos((2.0 * PI * id) / (Ld - 1.0));
-    else if constexpr (W == 3) return 0.54 - 0.46 * cos((2.0 * PI * id) / (Ld - 1.0));
+    else if constexpr (W == 1) return 0.42 - 0.5 * cospi((2.0 * id) / Ld) + 0.08 * cospi((4.0 * id) / Ld);
+    else if constexpr (W == 2) return 0.5 - 0.5 * cospi((2.0 * id) / (Ld - 1.0));
+    else if constexpr (W == 3) return 0.54 - 0.46 * cospi((2.0 * id) / (Ld - 1.0));
     else return 1.0;
 }
 constexpr int SSF_W = 8;       // samples per trip = independent cos() chains in flight
