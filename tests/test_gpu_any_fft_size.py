@@ -209,3 +209,38 @@ def test_any_size_randomised_sweep(ctx, orc):
         assert got.shape == ref.shape, (N, hop, window, n)
         assert np.array_equal(np.isnan(got), np.isnan(ref)), (N, hop, window, n)
         assert_spectra(np.nan_to_num(got), np.nan_to_num(ref), RTOL64, f"N={N} hop={hop} w={window} n={n}")
+
+
+def test_any_size_device_entry_points_stay_inside_their_buffers(ctx, aus, orc):
+    """The memcheck stand-in (compute-sanitizer is closed on the pool) for the chirp-z path and overlap_add: every device
+    output sits between guard bands that must keep their fill value."""
+    torch = pytest.importorskip("torch")
+    ctx.use_torch_stream()
+    N, hop, G = 1000, 250, 4096
+    x = orc.synth_signal(9 * N + 77, SR, seed=71)
+    F, K = orc.num_frames(x.size, N, hop), N // 2 + 1
+
+    def guarded(n):
+        a = torch.full((n + 2 * G,), -7.25, dtype=torch.float64, device="cuda")
+        return a, a[G:G + n]
+
+    def intact(a, n):
+        return bool((a[:G] == -7.25).all()) and bool((a[G + n:] == -7.25).all())
+
+    dx = torch.from_numpy(x).cuda()
+    fa, feat = guarded(F * 14)
+    sa, spec = guarded(F * K * 2)
+    ctx.stft_features_batch_dev(dx, [0], [x.size], N, hop, orc.HAMMING, SR, "f64", feat, spec)
+    n_out = aus.irstft_len(F, N, hop)
+    oa, out = guarded(n_out)
+    ctx.irstft_dev(spec, F, N, hop, orc.HAMMING, "f64", out)
+    ch = torch.from_numpy(np.random.default_rng(3).normal(size=(F, N))).cuda()
+    la, ola = guarded(N + hop * (F - 1))
+    ctx.overlap_add_dev(ch, F, N, hop, ola)
+    ctx.synchronize()
+    assert intact(fa, F * 14) and intact(sa, F * K * 2) and intact(oa, n_out) and intact(la, N + hop * (F - 1))
+    ref = orc.stft_features(x, N, hop, orc.HAMMING, SR)
+    assert_features(feat.cpu().numpy().reshape(F, 14), ref, RTOL64, "guarded features")
+    S = orc.rstft(x, N, hop, orc.HAMMING)
+    refo = orc.irstft(S, N, hop, orc.HAMMING)
+    assert np.max(np.abs(out.cpu().numpy() - refo)) <= RTOL64 * np.max(np.abs(refo))
