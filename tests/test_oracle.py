@@ -326,3 +326,27 @@ def test_oracle_against_scipy(orc):
     # the reference's irfft is un-normalised (N x the signal, fft.rs:66-93) and irstft keeps that factor
     assert np.max(np.abs(y[body] / N - x[body])) < 1e-12
     assert np.max(np.abs(ys[body] - x[body])) < 1e-12
+
+
+def test_non_power_of_two_sizes_against_the_dft_definition(orc):
+    """rustfft plans any length (fft.rs:120-121); the oracle's rstft / irstft for such sizes are pinned against the DFT sum
+    itself (mpmath, 40 digits) and against the overlap-add identity, so the chirp-z path on the GPU is checked against
+    something that does not share its algorithm."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(17)
+    for N in (12, 45, 97):                                   # composite, odd composite, prime
+        x = rng.normal(size=N)
+        X = orc.rfft(x, N)
+        assert X.shape == (N // 2 + 1,)
+        for k in range(N // 2 + 1):
+            ref = sum(mp.mpf(float(x[n])) * mp.e ** (-2j * mp.pi * k * n / N) for n in range(N))
+            assert abs(complex(X[k]) - complex(ref)) < 1e-12 * max(1.0, abs(complex(ref)))
+    # rstft -> irstft at a non-power-of-two size reproduces N x the signal away from the ends (rustfft's inverse is unnormalised)
+    N, hop = 1000, 250
+    x = orc.synth_signal(12 * N + 5, 44100, seed=3)
+    S = orc.rstft(x, N, hop, orc.HAMMING)
+    assert S.shape == (orc.num_frames(x.size, N, hop), N // 2 + 1)
+    y = orc.irstft(S, N, hop, orc.HAMMING, normalize=False)
+    body = slice(N, x.size - N)
+    assert np.max(np.abs(y[body] / N - x[body])) < 1e-12
